@@ -1,0 +1,129 @@
+/* oake_b200 -- C ABI of the B200-native OAKE hot path (liboake_b200.so).
+ *
+ * The reference (LutingWang/OADP) is pure Python and has NO FFI of its own for this path; the
+ * boundary it exposes is the Python call `model.encode_image(x)` / `model.visual(objects, masks)`
+ * on a `clip.model.CLIP` object and `fc_cls(x)` on the mmdet linear layer.  Each entry point below
+ * names the reference interface it stands behind.  A maintainer binds these with ctypes (see
+ * INTEGRATION.md); `oadp_b200/binding.py` is that binding.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Every buffer (weights, inputs, outputs,
+ * workspace) is caller-owned DEVICE memory unless a parameter says "host".  Calls are
+ * stream-ordered on the `stream` argument (a cudaStream_t passed as void*), never synchronise and
+ * never allocate.  Return value 0 = ok, non-zero = error with a thread-local message available
+ * from oake_last_error(); nothing throws across the ABI.  One handle per (device, stream); a
+ * handle is not thread-safe.
+ */
+#ifndef OAKE_B200_H_
+#define OAKE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OAKE_ABI_VERSION 1
+
+/* Tower variants.
+ * T50 : un-modified CLIP ViT-B/32, conv1 stride 32, 7x7+1 tokens
+ *       (oadp/oake/globals.py:57, oadp/oake/blocks.py:129).
+ * T197: objects surgery -- conv1 stride 16 / padding 15, 14x14+1 tokens, mask-attended CLS side
+ *       stream whose token replaces the transformer output (oadp/oake/objects.py:198-314). */
+#define OAKE_VARIANT_T50 0
+#define OAKE_VARIANT_T197 1
+
+typedef struct oake_handle oake_handle;
+
+/* Device pointers for one ResidualAttentionBlock (openai/CLIP model.py state-dict names).
+ * "act" = the tensor-core element type reported by oake_act_dtype() ("f16" unless built with
+ * -DOAKE_USE_BF16); linear weights are stored [out_features, in_features] row-major exactly as
+ * in the checkpoint. */
+typedef struct {
+  const float* ln1_w; /* ln_1.weight              [768]        */
+  const float* ln1_b; /* ln_1.bias                [768]        */
+  const void* qkv_w;  /* attn.in_proj_weight      [2304,768] act */
+  const float* qkv_b; /* attn.in_proj_bias        [2304]       */
+  const void* out_w;  /* attn.out_proj.weight     [768,768] act  */
+  const float* out_b; /* attn.out_proj.bias       [768]        */
+  const float* ln2_w; /* ln_2.weight              [768]        */
+  const float* ln2_b; /* ln_2.bias                [768]        */
+  const void* fc1_w;  /* mlp.c_fc.weight          [3072,768] act */
+  const float* fc1_b; /* mlp.c_fc.bias            [3072]       */
+  const void* fc2_w;  /* mlp.c_proj.weight        [768,3072] act */
+  const float* fc2_b; /* mlp.c_proj.bias          [768]        */
+} oake_layer_weights;
+
+typedef struct {
+  int32_t layers;  /* 12 */
+  int32_t width;   /* 768 */
+  int32_t heads;   /* 12 */
+  int32_t patch;   /* 32 */
+  int32_t out_dim; /* 512 */
+  int32_t image;   /* 224 */
+  const void* conv1_w;     /* conv1.weight reshaped [768, 3*32*32] act, columns (c,ky,kx) */
+  const float* class_emb;  /* class_embedding [768] */
+  const float* pos_t50;    /* positional_embedding [50,768] */
+  const float* pos_t197;   /* resampled table [197,768] (objects.py:293-296) or NULL */
+  const float* ln_pre_w;
+  const float* ln_pre_b;
+  const float* ln_post_w;
+  const float* ln_post_b;
+  const void* proj_w;               /* proj^T [512,768] act */
+  const oake_layer_weights* layer;  /* HOST array of `layers` entries (device pointers inside) */
+} oake_weights;
+
+/* Replaces `clip.load_default(...)` + `.cuda()` (globals.py:47, blocks.py:123, objects.py:290):
+ * binds caller-owned device weights, builds the TMA descriptors for them.  The weights must
+ * outlive the handle. */
+int oake_create(oake_handle** out, int device, const oake_weights* weights);
+void oake_destroy(oake_handle* h);
+
+/* Bytes of caller-provided scratch for a batch of up to `max_crops` crops of `variant`. */
+int oake_workspace_bytes(const oake_handle* h, int max_crops, int variant, size_t* out_bytes);
+
+/* Replaces `model.encode_image(x)` (variant T50; globals.py:57, blocks.py:129) and
+ * `model.visual(o, m)` (variant T197; objects.py:330) PLUS the caller's `F.normalize(...).half()`
+ * (globals.py:58-59, blocks.py:130-133, objects.py:331-334).
+ *   pixels      : device fp32 [B,3,224,224], CLIP-normalised (what the reference's transform yields)
+ *   masks       : device fp32 [B,1,14,14], 1 = background (objects.py:129-155); NULL for T50
+ *   out_f16     : device fp16 [B,512]  L2-normalised embedding (the value the reference stores)
+ *   out_raw_f32 : device fp32 [B,512]  un-normalised tower output (what encode_image returns), or NULL
+ *   ws/ws_bytes : scratch of at least oake_workspace_bytes(B, variant) */
+int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, const float* masks,
+                       void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes, void* stream);
+
+/* Error string of the last failing call on this thread ("" if none). */
+const char* oake_last_error(void);
+/* "f16" or "bf16": element type of `act` tensors. */
+const char* oake_act_dtype(void);
+int oake_abi_version(void);
+
+/* ---- instrumentation (bench.py / tests) ------------------------------------------------- */
+/* Number of kernels this handle has launched since creation. */
+int oake_launch_count(const oake_handle* h, long long* out);
+/* When enabled every launch is bracketed by CUDA events on its stream (bench roofline pass). */
+int oake_profile_enable(oake_handle* h, int enable);
+/* Synchronises the recorded events, accumulates per kernel class, clears the event list.
+ * Writes up to `cap` entries; returns the number of classes in *n.  flops = algorithmic FLOPs
+ * issued by that class (0 for non-GEMM classes). */
+int oake_profile_collect(oake_handle* h, int cap, const char** names, double* ms, double* flops,
+                         long long* launches, int* n);
+
+/* ---- single-kernel entry points (unit tests; all pointers device, row-major) --------------- */
+/* out[M,N] = epi(A[M,K] * W[N,K]^T): bias fp32 [N] or NULL, act 0|1 (QuickGELU), residual fp32
+ * [M,N] or NULL (may alias out when out_f32), out act or fp32.  impl 0 = tcgen05, 1 = SIMT ref. */
+int oake_test_gemm(const void* A, const void* W, int M, int N, int K, const float* bias, int act,
+                   const float* residual, void* out, int out_f32, int impl, void* stream);
+int oake_test_layernorm(const float* x, const float* w, const float* b, void* out_act, int rows,
+                        void* stream);
+/* qkv act [R,2304], rows [B*P | B | (B)]; out act [R,768]. */
+int oake_test_attention_main(const void* qkv, void* out_act, int B, int P, void* stream);
+int oake_test_attention_side(const void* qkv, const float* mask, void* out_act, int B, int P,
+                             void* stream);
+int oake_test_im2col(const float* pixels, void* patches_act, int B, int variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OAKE_B200_H_ */

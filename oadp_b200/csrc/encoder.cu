@@ -1,0 +1,453 @@
+// Handle, workspace plan and launch schedule of the OAKE tower + the extern "C" surface declared
+// in include/oake_b200.h.
+//
+// Activation matrix layout (one row = one token, 768 wide):
+//     [ B*P patch rows (crop-major) | B class rows | B side rows (T197 only) ]
+// Every per-token op of a ResidualAttentionBlock (LayerNorm, QKV, out-proj, MLP) is row-wise, so
+// the objects side stream (oadp/oake/objects.py:224-247) is simply B extra rows riding through the
+// same launches; only attention distinguishes them.  Keeping the class / side rows contiguous at
+// the end lets the last block (whose main-stream output is dead, objects.py:249-258) run its
+// out-proj / MLP on those B rows alone.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/oake_b200.h"
+#include "kernels.cuh"
+
+using namespace oake;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+enum KClass {
+  K_FRONTEND = 0,
+  K_GEMM_PATCH,
+  K_ASSEMBLE,
+  K_LAYERNORM,
+  K_GEMM_QKV,
+  K_ATTN_MAIN,
+  K_ATTN_SIDE,
+  K_GEMM_OUT,
+  K_GEMM_FC1,
+  K_GEMM_FC2,
+  K_GEMM_PROJ,
+  K_L2NORM,
+  K_NUM
+};
+const char* kClassNames[K_NUM] = {"frontend",  "gemm_patch", "assemble_ln_pre", "layernorm",
+                                  "gemm_qkv",  "attn_main",  "attn_side",       "gemm_out",
+                                  "gemm_fc1",  "gemm_fc2",   "gemm_proj",       "l2norm_half"};
+
+struct LayerMaps {
+  CUtensorMap qkv, out, fc1, fc2;
+};
+
+struct ProfEvent {
+  int cls;
+  double flops;
+  cudaEvent_t a, b;
+};
+
+constexpr size_t kAlign = 1024;
+size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct Plan {
+  int B, P, T, R, tail_start;
+  size_t off_patches, off_patch_out, off_x, off_h, off_qkv, off_attn, off_mlp, off_head_in,
+      off_emb_raw, total;
+};
+
+}  // namespace
+
+struct oake_handle {
+  int device;
+  int num_sms;
+  oake_weights w;
+  std::vector<oake_layer_weights> layers;
+  CUtensorMap tm_conv1, tm_proj;
+  std::vector<LayerMaps> tm_layer;
+  long long launches;
+  bool profiling;
+  std::vector<ProfEvent> events;
+  std::vector<cudaEvent_t> pool;
+  double acc_ms[K_NUM];
+  double acc_flops[K_NUM];
+  long long acc_launches[K_NUM];
+};
+
+namespace {
+
+Plan make_plan(const oake_handle* h, int B, int variant) {
+  Plan p;
+  const int W = h->w.width;
+  p.B = B;
+  p.P = variant == OAKE_VARIANT_T197 ? 196 : 49;
+  p.T = p.P + 1;
+  p.R = B * p.T + (variant == OAKE_VARIANT_T197 ? B : 0);
+  p.tail_start = variant == OAKE_VARIANT_T197 ? B * p.T : B * p.P;
+  const size_t patch_cols = 3 * h->w.patch * h->w.patch;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  p.off_patches = take(static_cast<size_t>(B) * p.P * patch_cols * sizeof(act_t));
+  p.off_patch_out = take(static_cast<size_t>(B) * p.P * W * sizeof(float));
+  p.off_x = take(static_cast<size_t>(p.R) * W * sizeof(float));
+  p.off_h = take(static_cast<size_t>(p.R) * W * sizeof(act_t));
+  p.off_qkv = take(static_cast<size_t>(p.R) * 3 * W * sizeof(act_t));
+  p.off_attn = take(static_cast<size_t>(p.R) * W * sizeof(act_t));
+  p.off_mlp = take(static_cast<size_t>(p.R) * 4 * W * sizeof(act_t));
+  p.off_head_in = take(static_cast<size_t>(B) * W * sizeof(act_t));
+  p.off_emb_raw = take(static_cast<size_t>(B) * h->w.out_dim * sizeof(float));
+  p.total = off;
+  return p;
+}
+
+cudaEvent_t get_event(oake_handle* h) {
+  if (!h->pool.empty()) {
+    cudaEvent_t e = h->pool.back();
+    h->pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct Launcher {
+  oake_handle* h;
+  cudaStream_t st;
+  cudaError_t err = cudaSuccess;
+  const char* where = "";
+
+  template <class F>
+  void run(int cls, double flops, F&& f) {
+    if (err != cudaSuccess) return;
+    ProfEvent pe;
+    if (h->profiling) {
+      pe.cls = cls;
+      pe.flops = flops;
+      pe.a = get_event(h);
+      pe.b = get_event(h);
+      cudaEventRecord(pe.a, st);
+    }
+    err = f();
+    if (err != cudaSuccess) where = kClassNames[cls];
+    h->launches += 1;
+    if (h->profiling) {
+      cudaEventRecord(pe.b, st);
+      h->events.push_back(pe);
+    }
+  }
+};
+
+int check_weights(const oake_weights* w) {
+  if (w == nullptr) return fail("weights is NULL");
+  if (w->layers <= 0 || w->layers > 64) return fail("layers=%d out of range", w->layers);
+  if (w->width != 768 || w->heads != 12 || w->patch != 32 || w->out_dim != 512 || w->image != 224)
+    return fail("only ViT-B/32 geometry is built (width 768, heads 12, patch 32, out 512, image 224); got "
+                "%d/%d/%d/%d/%d",
+                w->width, w->heads, w->patch, w->out_dim, w->image);
+  if (!w->conv1_w || !w->class_emb || !w->pos_t50 || !w->ln_pre_w || !w->ln_pre_b || !w->ln_post_w ||
+      !w->ln_post_b || !w->proj_w || !w->layer)
+    return fail("a required weight pointer is NULL");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* oake_last_error(void) { return g_err.c_str(); }
+const char* oake_act_dtype(void) { return OAKE_ACT_NAME; }
+int oake_abi_version(void) { return OAKE_ABI_VERSION; }
+
+int oake_create(oake_handle** out, int device, const oake_weights* weights) {
+  if (out == nullptr) return fail("out is NULL");
+  *out = nullptr;
+  if (check_weights(weights)) return 1;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail("liboake_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+                prop.minor);
+  oake_handle* h = new oake_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->w = *weights;
+  h->layers.assign(weights->layer, weights->layer + weights->layers);
+  h->w.layer = h->layers.data();
+  h->launches = 0;
+  h->profiling = false;
+  memset(h->acc_ms, 0, sizeof(h->acc_ms));
+  memset(h->acc_flops, 0, sizeof(h->acc_flops));
+  memset(h->acc_launches, 0, sizeof(h->acc_launches));
+  const int W = h->w.width;
+  int rc = 0;
+  rc |= make_tmap_act_2d(&h->tm_conv1, h->w.conv1_w, W, 3 * 32 * 32, gemm_block_n(W));
+  rc |= make_tmap_act_2d(&h->tm_proj, h->w.proj_w, h->w.out_dim, W, gemm_block_n(h->w.out_dim));
+  h->tm_layer.resize(h->w.layers);
+  for (int l = 0; l < h->w.layers && rc == 0; ++l) {
+    const oake_layer_weights& lw = h->layers[l];
+    if (!lw.qkv_w || !lw.out_w || !lw.fc1_w || !lw.fc2_w || !lw.ln1_w || !lw.ln1_b || !lw.ln2_w ||
+        !lw.ln2_b || !lw.qkv_b || !lw.out_b || !lw.fc1_b || !lw.fc2_b) {
+      delete h;
+      return fail("layer %d has a NULL weight pointer", l);
+    }
+    rc |= make_tmap_act_2d(&h->tm_layer[l].qkv, lw.qkv_w, 3 * W, W, gemm_block_n(3 * W));
+    rc |= make_tmap_act_2d(&h->tm_layer[l].out, lw.out_w, W, W, gemm_block_n(W));
+    rc |= make_tmap_act_2d(&h->tm_layer[l].fc1, lw.fc1_w, 4 * W, W, gemm_block_n(4 * W));
+    rc |= make_tmap_act_2d(&h->tm_layer[l].fc2, lw.fc2_w, W, 4 * W, gemm_block_n(W));
+  }
+  if (rc != 0) {
+    delete h;
+    return fail("cuTensorMapEncodeTiled failed for a weight tensor (rc=%d)", rc);
+  }
+  *out = h;
+  return 0;
+}
+
+void oake_destroy(oake_handle* h) {
+  if (h == nullptr) return;
+  for (auto& pe : h->events) {
+    cudaEventDestroy(pe.a);
+    cudaEventDestroy(pe.b);
+  }
+  for (auto e : h->pool) cudaEventDestroy(e);
+  delete h;
+}
+
+int oake_workspace_bytes(const oake_handle* h, int max_crops, int variant, size_t* out_bytes) {
+  if (!h || !out_bytes) return fail("NULL argument");
+  if (max_crops < 0) return fail("max_crops < 0");
+  if (variant != OAKE_VARIANT_T50 && variant != OAKE_VARIANT_T197) return fail("bad variant %d", variant);
+  *out_bytes = make_plan(h, max_crops, variant).total + kAlign;
+  return 0;
+}
+
+int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, const float* masks,
+                       void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes, void* stream) {
+  if (!h) return fail("handle is NULL");
+  if (variant != OAKE_VARIANT_T50 && variant != OAKE_VARIANT_T197) return fail("bad variant %d", variant);
+  if (B < 0) return fail("B < 0");
+  if (B == 0) return 0;
+  if (!pixels || !out_f16 || !ws) return fail("NULL buffer");
+  const bool side = variant == OAKE_VARIANT_T197;
+  if (side && !masks) return fail("variant T197 needs masks");
+  if (side && !h->w.pos_t197) return fail("handle was created without pos_t197");
+  const Plan p = make_plan(h, B, variant);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + kAlign - 1) / kAlign * kAlign);
+  if (static_cast<size_t>(base - static_cast<uint8_t*>(ws)) + p.total > ws_bytes)
+    return fail("workspace too small: need %zu bytes, got %zu", p.total + kAlign, ws_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const int W = h->w.width, L = h->w.layers, H = h->w.heads, OD = h->w.out_dim;
+  const int PC = 3 * h->w.patch * h->w.patch;
+  act_t* patches = reinterpret_cast<act_t*>(base + p.off_patches);
+  float* patch_out = reinterpret_cast<float*>(base + p.off_patch_out);
+  float* x = reinterpret_cast<float*>(base + p.off_x);
+  act_t* hbuf = reinterpret_cast<act_t*>(base + p.off_h);
+  act_t* qkv = reinterpret_cast<act_t*>(base + p.off_qkv);
+  act_t* attn = reinterpret_cast<act_t*>(base + p.off_attn);
+  act_t* mlp = reinterpret_cast<act_t*>(base + p.off_mlp);
+  act_t* head_in = reinterpret_cast<act_t*>(base + p.off_head_in);
+  float* emb_raw = out_raw_f32 ? out_raw_f32 : reinterpret_cast<float*>(base + p.off_emb_raw);
+
+  const int R = p.R, ts = p.tail_start;
+  CUtensorMap tm_patches, tm_h, tm_attn, tm_mlp, tm_h_tail, tm_attn_tail, tm_mlp_tail, tm_head;
+  int rc = 0;
+  rc |= make_tmap_act_2d(&tm_patches, patches, static_cast<uint64_t>(B) * p.P, PC, 128);
+  rc |= make_tmap_act_2d(&tm_h, hbuf, R, W, 128);
+  rc |= make_tmap_act_2d(&tm_attn, attn, R, W, 128);
+  rc |= make_tmap_act_2d(&tm_mlp, mlp, R, 4 * W, 128);
+  rc |= make_tmap_act_2d(&tm_h_tail, hbuf + static_cast<size_t>(ts) * W, B, W, 128);
+  rc |= make_tmap_act_2d(&tm_attn_tail, attn + static_cast<size_t>(ts) * W, B, W, 128);
+  rc |= make_tmap_act_2d(&tm_mlp_tail, mlp + static_cast<size_t>(ts) * 4 * W, B, 4 * W, 128);
+  rc |= make_tmap_act_2d(&tm_head, head_in, B, W, 128);
+  if (rc != 0) return fail("cuTensorMapEncodeTiled failed for an activation tensor (rc=%d)", rc);
+
+  Launcher go{h, st};
+  const int ns = h->num_sms;
+  auto gflops = [](double m, double n, double k) { return 2.0 * m * n * k; };
+
+  // K0/K1: crops -> conv1 patch matrix -> patch embedding -> tokens + ln_pre
+  go.run(K_FRONTEND, 0, [&] {
+    return launch_im2col_pixels(st, pixels, patches, B, side ? 16 : 32, side ? 15 : 0, side ? 14 : 7);
+  });
+  {
+    GemmEpilogue ep{nullptr, nullptr, patch_out, W, 0, 1, 0};
+    const int M = B * p.P;
+    go.run(K_GEMM_PATCH, gflops(M, W, PC), [&] { return launch_gemm(st, tm_patches, h->tm_conv1, M, W, PC, ep, ns); });
+  }
+  go.run(K_ASSEMBLE, 0, [&] {
+    return launch_assemble_ln_pre(st, patch_out, h->w.class_emb, side ? h->w.pos_t197 : h->w.pos_t50,
+                                  h->w.ln_pre_w, h->w.ln_pre_b, x, B, p.P, W, side ? 1 : 0);
+  });
+
+  for (int l = 0; l < L; ++l) {
+    const oake_layer_weights& lw = h->layers[l];
+    const LayerMaps& tm = h->tm_layer[l];
+    const bool last = (l == L - 1);
+    // rows that still matter after this block's attention
+    const int r0 = last ? ts : 0;
+    const int rn = last ? B : R;
+    float* xr = x + static_cast<size_t>(r0) * W;
+
+    go.run(K_LAYERNORM, 0, [&] { return launch_layernorm(st, x, lw.ln1_w, lw.ln1_b, hbuf, R, W); });
+    {
+      GemmEpilogue ep{lw.qkv_b, nullptr, qkv, 3 * W, 0, 0, 0};
+      go.run(K_GEMM_QKV, gflops(R, 3 * W, W), [&] { return launch_gemm(st, tm_h, tm.qkv, R, 3 * W, W, ep, ns); });
+    }
+    if (!(last && side))
+      go.run(K_ATTN_MAIN, 4.0 * B * p.T * p.T * W, [&] { return launch_attention_main(st, qkv, attn, B, p.P, H); });
+    if (side)
+      go.run(K_ATTN_SIDE, 4.0 * B * p.T * W, [&] { return launch_attention_side(st, qkv, masks, attn, B, p.P, H); });
+    {
+      GemmEpilogue ep{lw.out_b, xr, xr, W, W, 1, 0};
+      go.run(K_GEMM_OUT, gflops(rn, W, W),
+             [&] { return launch_gemm(st, last ? tm_attn_tail : tm_attn, tm.out, rn, W, W, ep, ns); });
+    }
+    go.run(K_LAYERNORM, 0, [&] {
+      return launch_layernorm(st, xr, lw.ln2_w, lw.ln2_b, hbuf + static_cast<size_t>(r0) * W, rn, W);
+    });
+    {
+      GemmEpilogue ep{lw.fc1_b, nullptr, mlp + static_cast<size_t>(r0) * 4 * W, 4 * W, 0, 0, 1};
+      go.run(K_GEMM_FC1, gflops(rn, 4 * W, W),
+             [&] { return launch_gemm(st, last ? tm_h_tail : tm_h, tm.fc1, rn, 4 * W, W, ep, ns); });
+    }
+    {
+      GemmEpilogue ep{lw.fc2_b, xr, xr, W, W, 1, 0};
+      go.run(K_GEMM_FC2, gflops(rn, W, 4 * W),
+             [&] { return launch_gemm(st, last ? tm_mlp_tail : tm_mlp, tm.fc2, rn, W, 4 * W, ep, ns); });
+    }
+  }
+
+  // K8: ln_post(output token) @ proj -> L2 normalise -> fp16
+  go.run(K_LAYERNORM, 0, [&] {
+    return launch_layernorm(st, x + static_cast<size_t>(ts) * W, h->w.ln_post_w, h->w.ln_post_b, head_in, B, W);
+  });
+  {
+    GemmEpilogue ep{nullptr, nullptr, emb_raw, OD, 0, 1, 0};
+    go.run(K_GEMM_PROJ, gflops(B, OD, W), [&] { return launch_gemm(st, tm_head, h->tm_proj, B, OD, W, ep, ns); });
+  }
+  go.run(K_L2NORM, 0, [&] { return launch_l2norm_half(st, emb_raw, static_cast<__half*>(out_f16), B, OD); });
+
+  if (go.err != cudaSuccess)
+    return fail("launch of %s failed: %s", go.where, cudaGetErrorString(go.err));
+  return 0;
+}
+
+int oake_launch_count(const oake_handle* h, long long* out) {
+  if (!h || !out) return fail("NULL argument");
+  *out = h->launches;
+  return 0;
+}
+
+int oake_profile_enable(oake_handle* h, int enable) {
+  if (!h) return fail("handle is NULL");
+  h->profiling = enable != 0;
+  return 0;
+}
+
+int oake_profile_collect(oake_handle* h, int cap, const char** names, double* ms, double* flops,
+                         long long* launches, int* n) {
+  if (!h || !n) return fail("NULL argument");
+  for (auto& pe : h->events) {
+    cudaError_t e = cudaEventSynchronize(pe.b);
+    if (e != cudaSuccess) return fail("cudaEventSynchronize: %s", cudaGetErrorString(e));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, pe.a, pe.b);
+    h->acc_ms[pe.cls] += t;
+    h->acc_flops[pe.cls] += pe.flops;
+    h->acc_launches[pe.cls] += 1;
+    h->pool.push_back(pe.a);
+    h->pool.push_back(pe.b);
+  }
+  h->events.clear();
+  int k = 0;
+  for (int c = 0; c < K_NUM && k < cap; ++c) {
+    if (names) names[k] = kClassNames[c];
+    if (ms) ms[k] = h->acc_ms[c];
+    if (flops) flops[k] = h->acc_flops[c];
+    if (launches) launches[k] = h->acc_launches[c];
+    ++k;
+  }
+  *n = k;
+  memset(h->acc_ms, 0, sizeof(h->acc_ms));
+  memset(h->acc_flops, 0, sizeof(h->acc_flops));
+  memset(h->acc_launches, 0, sizeof(h->acc_launches));
+  return 0;
+}
+
+// -------------------------------------------------------------------- single-kernel entry points
+int oake_test_gemm(const void* A, const void* Wt, int M, int N, int K, const float* bias, int act,
+                   const float* residual, void* out, int out_f32, int impl, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GemmEpilogue ep{bias, residual, out, N, N, out_f32, act};
+  cudaError_t e;
+  if (impl == 1) {
+    e = launch_gemm_simt(st, static_cast<const act_t*>(A), static_cast<const act_t*>(Wt), M, N, K, ep);
+  } else {
+    int dev = 0, ns = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&ns, cudaDevAttrMultiProcessorCount, dev);
+    CUtensorMap tmA, tmW;
+    if (make_tmap_act_2d(&tmA, A, M, K, 128) || make_tmap_act_2d(&tmW, Wt, N, K, gemm_block_n(N)))
+      return fail("cuTensorMapEncodeTiled failed");
+    e = launch_gemm(st, tmA, tmW, M, N, K, ep, ns);
+  }
+  if (e != cudaSuccess) return fail("gemm launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int oake_test_layernorm(const float* x, const float* w, const float* b, void* out_act, int rows,
+                        void* stream) {
+  cudaError_t e = launch_layernorm(static_cast<cudaStream_t>(stream), x, w, b, static_cast<act_t*>(out_act), rows, 768);
+  if (e != cudaSuccess) return fail("layernorm launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int oake_test_attention_main(const void* qkv, void* out_act, int B, int P, void* stream) {
+  cudaError_t e = launch_attention_main(static_cast<cudaStream_t>(stream), static_cast<const act_t*>(qkv),
+                                        static_cast<act_t*>(out_act), B, P, 12);
+  if (e != cudaSuccess) return fail("attention_main launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int oake_test_attention_side(const void* qkv, const float* mask, void* out_act, int B, int P,
+                             void* stream) {
+  cudaError_t e = launch_attention_side(static_cast<cudaStream_t>(stream), static_cast<const act_t*>(qkv),
+                                        mask, static_cast<act_t*>(out_act), B, P, 12);
+  if (e != cudaSuccess) return fail("attention_side launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int oake_test_im2col(const float* pixels, void* patches_act, int B, int variant, void* stream) {
+  const bool side = variant == OAKE_VARIANT_T197;
+  cudaError_t e = launch_im2col_pixels(static_cast<cudaStream_t>(stream), pixels, static_cast<act_t*>(patches_act),
+                                       B, side ? 16 : 32, side ? 15 : 0, side ? 14 : 7);
+  if (e != cudaSuccess) return fail("im2col launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// Internal launcher declarations shared by the OAKE translation units.
+#pragma once
+
+#include "common.cuh"
+
+namespace oake {
+
+// ---------------------------------------------------------------- gemm.cu
+struct GemmEpilogue {
+  const float* bias;      // [N] fp32 or nullptr
+  const float* residual;  // fp32 [M, ld_res] added after the activation, or nullptr
+  void* out;              // act_t or fp32 [M, ldo]; may alias `residual`
+  int ldo;
+  int ld_res;
+  int out_f32;  // 1: fp32 output, 0: act_t output
+  int act;      // 0: identity, 1: QuickGELU  u * sigmoid(1.702 u)
+};
+
+// Encodes a 2D row-major [rows, cols] act_t tensor as a TMA map with a (box_rows x 64) box and
+// 128-byte swizzle.  Returns 0 on success.
+int make_tmap_act_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                     uint32_t box_rows);
+
+// out[M,N] = epilogue(A[M,K] * W[N,K]^T).  A and W are act_t, K-contiguous.  N % 128 == 0,
+// K % 64 == 0.  tmA must have a 128-row box, tmW a `gemm_block_n(N)`-row box.
+int gemm_block_n(int N);
+cudaError_t launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M,
+                        int N, int K, const GemmEpilogue& ep, int num_sms);
+// CUDA-core reference of the same contract (debug / unit tests only; never on the product path).
+cudaError_t launch_gemm_simt(cudaStream_t st, const act_t* A, const act_t* W, int M, int N, int K,
+                             const GemmEpilogue& ep);
+
+// -------------------------------------------------------------- rowops.cu
+cudaError_t launch_layernorm(cudaStream_t st, const float* x, const float* w, const float* b,
+                             act_t* out, int rows, int width);
+// Builds the residual stream: rows [0, B*P) = LN(patch_out + pos[1 + i % P]); rows [B*P, B*P+B) =
+// LN(class_emb + pos[0]); if with_y, rows [B*P+B, B*P+2B) = copy of the class rows.
+cudaError_t launch_assemble_ln_pre(cudaStream_t st, const float* patch_out, const float* class_emb,
+                                   const float* pos, const float* w, const float* b, float* x,
+                                   int B, int P, int width, int with_y);
+cudaError_t launch_l2norm_half(cudaStream_t st, const float* e, __half* out, int rows, int dim);
+
+// ----------------------------------------------------------- attention.cu
+// qkv: act [R, 3*W] (q | k | v, head h = columns 64h..64h+63 of each third); rows ordered
+// [B*P patch rows | B class rows | (B side rows)].  Writes act [R, W] for patch + class rows.
+cudaError_t launch_attention_main(cudaStream_t st, const act_t* qkv, act_t* out, int B, int P,
+                                  int heads);
+// Side stream (objects): one query (the y row) over the P patch keys + itself with additive
+// bias -100 * mask (mask: fp32 [B, P], 1 = background).  Writes the B side rows of `out`.
+cudaError_t launch_attention_side(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out,
+                                  int B, int P, int heads);
+
+// ------------------------------------------------------------ frontend.cu
+// pixels fp32 NCHW [B,3,224,224] (already CLIP-normalised) -> act [B*P, 3*32*32] conv1 patches,
+// column order (c, ky, kx).  stride 32 / pad 0 (P=49) or stride 16 / pad 15 (P=196).
+cudaError_t launch_im2col_pixels(cudaStream_t st, const float* pixels, act_t* patches, int B,
+                                 int stride, int pad, int grid);
+
+}  // namespace oake

@@ -1,0 +1,138 @@
+// Row-wise fp32 kernels of the OAKE tower: LayerNorm, token assembly + ln_pre
+// (the tail of K1), final L2-normalise + fp16 cast (K8; reference: F.normalize(...).half() at
+// oadp/oake/globals.py:58-59, blocks.py:130-133, objects.py:331-334).
+// One warp per 768-wide row, statistics in fp32 registers, 128-bit global accesses.
+#include "kernels.cuh"
+
+namespace oake {
+
+namespace {
+
+constexpr int kWidth = 768;
+constexpr int kPerLane = kWidth / 32;  // 24 floats = 6 float4 per lane
+constexpr float kLnEps = 1e-5f;
+
+// v: 24 values of one row held by this lane as 6 float4 at float4 index lane + 32*j.
+__device__ __forceinline__ void ln_normalize(float4 (&v)[6], const float* __restrict__ w,
+                                             const float* __restrict__ b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) s += v[j].x + v[j].y + v[j].z + v[j].w;
+  const float mean = warp_sum(s) * (1.0f / kWidth);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    v[j].x -= mean;
+    v[j].y -= mean;
+    v[j].z -= mean;
+    v[j].w -= mean;
+    ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / kWidth) + kLnEps);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 g = __ldg(w4 + lane + 32 * j);
+    const float4 be = __ldg(b4 + lane + 32 * j);
+    v[j].x = v[j].x * rstd * g.x + be.x;
+    v[j].y = v[j].y * rstd * g.y + be.y;
+    v[j].z = v[j].z * rstd * g.z + be.z;
+    v[j].w = v[j].w * rstd * g.w + be.w;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                 const float* __restrict__ b, act_t* __restrict__ out, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* x4 = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * kWidth);
+  float4 v[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) v[j] = x4[lane + 32 * j];
+  ln_normalize(v, w, b, lane);
+  uint2* o2 = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * kWidth);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    uint2 u;
+    u.x = pack2(v[j].x, v[j].y);
+    u.y = pack2(v[j].z, v[j].w);
+    o2[lane + 32 * j] = u;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restrict__ class_emb,
+                       const float* __restrict__ pos, const float* __restrict__ w,
+                       const float* __restrict__ b, float* __restrict__ x, int B, int P,
+                       int with_y) {
+  const int rows = B * P + B;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bool is_cls = row >= B * P;
+  const float4* src = reinterpret_cast<const float4*>(
+      is_cls ? class_emb : patch_out + static_cast<size_t>(row) * kWidth);
+  const int tok = is_cls ? 0 : 1 + row % P;
+  const float4* p4 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(tok) * kWidth);
+  float4 v[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 a = src[lane + 32 * j];
+    const float4 p = __ldg(p4 + lane + 32 * j);
+    v[j] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+  }
+  ln_normalize(v, w, b, lane);
+  float4* o4 = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * kWidth);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) o4[lane + 32 * j] = v[j];
+  if (is_cls && with_y) {  // side token y0 = x[CLS] right after ln_pre (objects.py:216-222)
+    float4* y4 = reinterpret_cast<float4*>(x + static_cast<size_t>(row + B) * kWidth);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) y4[lane + 32 * j] = v[j];
+  }
+}
+
+// F.normalize(e, dim=1, eps=1e-12) then .half(); dim == 512 -> 16 floats per lane.
+__global__ void __launch_bounds__(256)
+l2norm_half_kernel(const float* __restrict__ e, __half* __restrict__ out, int rows, int dim) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* r = e + static_cast<size_t>(row) * dim;
+  float ss = 0.f;
+  for (int i = lane; i < dim; i += 32) ss += r[i] * r[i];
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  for (int i = lane; i < dim; i += 32) out[static_cast<size_t>(row) * dim + i] = __float2half_rn(r[i] * inv);
+}
+
+}  // namespace
+
+cudaError_t launch_layernorm(cudaStream_t st, const float* x, const float* w, const float* b,
+                             act_t* out, int rows, int width) {
+  if (width != kWidth) return cudaErrorInvalidValue;
+  if (rows <= 0) return cudaSuccess;
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, w, b, out, rows);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_assemble_ln_pre(cudaStream_t st, const float* patch_out, const float* class_emb,
+                                   const float* pos, const float* w, const float* b, float* x, int B,
+                                   int P, int width, int with_y) {
+  if (width != kWidth) return cudaErrorInvalidValue;
+  if (B <= 0) return cudaSuccess;
+  const int rows = B * P + B;
+  assemble_ln_pre_kernel<<<(rows + 7) / 8, 256, 0, st>>>(patch_out, class_emb, pos, w, b, x, B, P,
+                                                         with_y);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_l2norm_half(cudaStream_t st, const float* e, __half* out, int rows, int dim) {
+  if (rows <= 0) return cudaSuccess;
+  l2norm_half_kernel<<<(rows + 7) / 8, 256, 0, st>>>(e, out, rows, dim);
+  return cudaGetLastError();
+}
+
+}  // namespace oake

@@ -1,0 +1,174 @@
+"""GPU tier: every sm_100a kernel, through the C ABI, against a plain torch fp32 reference of the
+same op on the same (fp16-rounded) inputs.  Tolerances are written per test."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oadp_b200 import binding
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+
+
+def act_dtype():
+    return {'f16': torch.float16, 'bf16': torch.bfloat16}[binding.act_dtype_name()]
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def run_gemm(lib, A, W, bias=None, act=0, residual=None, out_f32=False, impl=0, inplace=False):
+    M, K = A.shape
+    N = W.shape[0]
+    if inplace:
+        out = residual
+    else:
+        out = torch.full((M, N), float('nan'), device=DEV, dtype=torch.float32 if out_f32 else act_dtype())
+    binding.check(lib.oake_test_gemm(A.data_ptr(), W.data_ptr(), M, N, K,
+                                     bias.data_ptr() if bias is not None else None, act,
+                                     residual.data_ptr() if residual is not None else None,
+                                     out.data_ptr(), int(out_f32), impl, stream()))
+    torch.cuda.synchronize()
+    return out
+
+
+def ref_gemm(A, W, bias=None, act=0, residual=None):
+    y = A.float() @ W.float().T
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = y * torch.sigmoid(1.702 * y)
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (128, 256, 128), (300, 768, 768), (1000, 2304, 768),
+                                   (77, 512, 768), (4097, 768, 3072), (19000, 3072, 768)])
+def test_gemm_tcgen05_plain(lib, M, N, K):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=DEV, generator=g)).to(act_dtype())
+    W = (torch.randn(N, K, device=DEV, generator=g) * K**-0.5).to(act_dtype())
+    out = run_gemm(lib, A, W, out_f32=True)
+    ref = ref_gemm(A, W)
+    # fp32 accumulation of exactly representable products: only summation order differs
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max() < 2e-3, (out - ref).abs().max()
+
+
+def test_gemm_matches_simt_reference(lib):
+    g = torch.Generator(device=DEV).manual_seed(5)
+    A = torch.randn(515, 768, device=DEV, generator=g).to(act_dtype())
+    W = (torch.randn(2304, 768, device=DEV, generator=g) * 768**-0.5).to(act_dtype())
+    bias = torch.randn(2304, device=DEV, generator=g)
+    a = run_gemm(lib, A, W, bias=bias, out_f32=True, impl=0)
+    b = run_gemm(lib, A, W, bias=bias, out_f32=True, impl=1)
+    assert (a - b).abs().max() < 2e-3
+
+
+def test_gemm_epilogues(lib):
+    g = torch.Generator(device=DEV).manual_seed(6)
+    M, K = 1030, 768
+    A = torch.randn(M, K, device=DEV, generator=g).to(act_dtype())
+    # c_fc + QuickGELU -> act output
+    W1 = (torch.randn(3072, K, device=DEV, generator=g) * K**-0.5).to(act_dtype())
+    b1 = torch.randn(3072, device=DEV, generator=g) * 0.1
+    out = run_gemm(lib, A, W1, bias=b1, act=1)
+    ref = ref_gemm(A, W1, b1, 1)
+    assert out.dtype == act_dtype()
+    assert (out.float() - ref).abs().max() < 2e-2  # one fp16/bf16 rounding of |y| <~ 8
+    # c_proj + bias + in-place fp32 residual
+    H = out
+    W2 = (torch.randn(768, 3072, device=DEV, generator=g) * 3072**-0.5).to(act_dtype())
+    b2 = torch.randn(768, device=DEV, generator=g) * 0.1
+    x = torch.randn(M, 768, device=DEV, generator=g)
+    ref2 = ref_gemm(H, W2, b2, 0, x.clone())
+    out2 = run_gemm(lib, H, W2, bias=b2, residual=x, out_f32=True, inplace=True)
+    assert out2.data_ptr() == x.data_ptr()
+    assert (out2 - ref2).abs().max() < 2e-3
+
+
+def test_layernorm(lib):
+    g = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.randn(1001, 768, device=DEV, generator=g) * 3 + 0.5
+    w = 1 + 0.1 * torch.randn(768, device=DEV, generator=g)
+    b = 0.1 * torch.randn(768, device=DEV, generator=g)
+    out = torch.empty(1001, 768, device=DEV, dtype=act_dtype())
+    binding.check(lib.oake_test_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), 1001, stream()))
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x, (768, ), w, b, 1e-5)
+    tol = 4e-3 if act_dtype() == torch.float16 else 3e-2
+    assert (out.float() - ref).abs().max() < tol
+
+
+def ref_attention(qkv, B, P, side_mask=None):
+    """rows [B*P | B | (B)] -> same-layout output; fp32 math on the rounded inputs."""
+    W = 768
+    q, k, v = qkv.float().split(W, dim=-1)
+
+    def gather(t):  # -> (B, T, 12, 64) tokens ordered patches then class
+        pat = t[:B * P].reshape(B, P, 12, 64)
+        cls = t[B * P:B * P + B].reshape(B, 1, 12, 64)
+        return torch.cat([pat, cls], 1)
+
+    Q, K, V = gather(q).transpose(1, 2), gather(k).transpose(1, 2), gather(v).transpose(1, 2)
+    o = torch.softmax(Q @ K.transpose(-1, -2) / 8, -1) @ V  # (B,12,T,64)
+    o = o.transpose(1, 2).reshape(B, P + 1, W)
+    out = torch.zeros(qkv.shape[0], W, device=qkv.device)
+    out[:B * P] = o[:, :P].reshape(B * P, W)
+    out[B * P:B * P + B] = o[:, P]
+    if side_mask is not None:
+        ys = slice(B * P + B, B * P + 2 * B)
+        qy = q[ys].reshape(B, 1, 12, 64).transpose(1, 2)
+        ky = torch.cat([k[:B * P].reshape(B, P, 12, 64), k[ys].reshape(B, 1, 12, 64)], 1).transpose(1, 2)
+        vy = torch.cat([v[:B * P].reshape(B, P, 12, 64), v[ys].reshape(B, 1, 12, 64)], 1).transpose(1, 2)
+        bias = torch.cat([side_mask * -100.0, side_mask.new_zeros(B, 1)], 1)[:, None, None, :]
+        oy = torch.softmax(qy @ ky.transpose(-1, -2) / 8 + bias, -1) @ vy
+        out[ys] = oy.transpose(1, 2).reshape(B, W)
+    return out
+
+
+@pytest.mark.parametrize('P,B', [(49, 5), (196, 3)])
+def test_attention_main(lib, P, B):
+    g = torch.Generator(device=DEV).manual_seed(P)
+    R = B * (P + 1)
+    qkv = (torch.randn(R, 2304, device=DEV, generator=g) * 1.5).to(act_dtype())
+    out = torch.zeros(R, 768, device=DEV, dtype=act_dtype())
+    binding.check(lib.oake_test_attention_main(qkv.data_ptr(), out.data_ptr(), B, P, stream()))
+    torch.cuda.synchronize()
+    ref = ref_attention(qkv, B, P)
+    tol = 6e-3 if act_dtype() == torch.float16 else 4e-2
+    assert (out.float() - ref).abs().max() < tol, (out.float() - ref).abs().max()
+
+
+def test_attention_side(lib):
+    B, P = 4, 196
+    g = torch.Generator(device=DEV).manual_seed(11)
+    R = B * (P + 2)
+    qkv = (torch.randn(R, 2304, device=DEV, generator=g) * 1.5).to(act_dtype())
+    mask = (torch.rand(B, P, device=DEV, generator=g) > 0.5).float()
+    mask[0] = 0
+    mask[1] = 1
+    out = torch.zeros(R, 768, device=DEV, dtype=act_dtype())
+    binding.check(lib.oake_test_attention_side(qkv.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, stream()))
+    torch.cuda.synchronize()
+    ref = ref_attention(qkv, B, P, mask)
+    ys = slice(B * P + B, R)
+    tol = 6e-3 if act_dtype() == torch.float16 else 4e-2
+    assert (out[ys].float() - ref[ys]).abs().max() < tol
+    assert (out[:B * P + B] == 0).all()  # side kernel writes only the side rows
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+def test_im2col(lib, variant):
+    B = 3
+    g = torch.Generator(device=DEV).manual_seed(12)
+    px = torch.randn(B, 3, 224, 224, device=DEV, generator=g)
+    stride, pad, grid = ((32, 0, 7), (16, 15, 14))[variant]
+    out = torch.empty(B * grid * grid, 3072, device=DEV, dtype=act_dtype())
+    binding.check(lib.oake_test_im2col(px.data_ptr(), out.data_ptr(), B, variant, stream()))
+    torch.cuda.synchronize()
+    ref = F.unfold(px, 32, padding=pad, stride=stride).transpose(1, 2).reshape(B * grid * grid, 3072)
+    assert torch.equal(out, ref.to(act_dtype()))  # pure data movement + one rounding: bit-exact
