@@ -37,21 +37,27 @@ typedef struct oake_handle oake_handle;
 
 /* Device pointers for one ResidualAttentionBlock (openai/CLIP model.py state-dict names).
  * "act" = the tensor-core element type reported by oake_act_dtype() ("f16" unless built with
- * -DOAKE_USE_BF16); linear weights are stored [out_features, in_features] row-major exactly as
- * in the checkpoint. */
+ * -DOAKE_USE_BF16); linear weights are stored [out_features, in_features] row-major as in the
+ * checkpoint.
+ *
+ * ln_1 and ln_2 are FOLDED into the GEMM that consumes them (the library never runs them as
+ * separate kernels).  For y = LN(x; gamma, beta) W^T + b the caller supplies
+ *     w' = W * diag(gamma)            rounded to act          (qkv_w / fc1_w)
+ *     s  = row sums of w' AS STORED   fp32 [out_features]     (qkv_s / fc1_s)
+ *     c  = W beta + b                 fp32 [out_features]     (qkv_c / fc1_c)
+ * and the kernel evaluates  y[m,n] = rstd_m * (x_m . w'_n - mean_m * s_n) + c_n  with mean/rstd of
+ * the stored residual row.  `oadp_b200.model.fold_layernorm` builds these from a checkpoint. */
 typedef struct {
-  const float* ln1_w; /* ln_1.weight              [768]        */
-  const float* ln1_b; /* ln_1.bias                [768]        */
-  const void* qkv_w;  /* attn.in_proj_weight      [2304,768] act */
-  const float* qkv_b; /* attn.in_proj_bias        [2304]       */
+  const void* qkv_w;  /* attn.in_proj_weight * diag(ln_1.weight)        [2304,768] act */
+  const float* qkv_s; /* [2304] */
+  const float* qkv_c; /* attn.in_proj_weight @ ln_1.bias + in_proj_bias [2304] */
   const void* out_w;  /* attn.out_proj.weight     [768,768] act  */
-  const float* out_b; /* attn.out_proj.bias       [768]        */
-  const float* ln2_w; /* ln_2.weight              [768]        */
-  const float* ln2_b; /* ln_2.bias                [768]        */
-  const void* fc1_w;  /* mlp.c_fc.weight          [3072,768] act */
-  const float* fc1_b; /* mlp.c_fc.bias            [3072]       */
+  const float* out_b; /* attn.out_proj.bias       [768]          */
+  const void* fc1_w;  /* mlp.c_fc.weight * diag(ln_2.weight)            [3072,768] act */
+  const float* fc1_s; /* [3072] */
+  const float* fc1_c; /* mlp.c_fc.weight @ ln_2.bias + c_fc.bias        [3072] */
   const void* fc2_w;  /* mlp.c_proj.weight        [768,3072] act */
-  const float* fc2_b; /* mlp.c_proj.bias          [768]        */
+  const float* fc2_b; /* mlp.c_proj.bias          [768]          */
 } oake_layer_weights;
 
 typedef struct {
@@ -111,11 +117,18 @@ int oake_profile_collect(oake_handle* h, int cap, const char** names, double* ms
                          long long* launches, int* n);
 
 /* ---- single-kernel entry points (unit tests; all pointers device, row-major) --------------- */
-/* out[M,N] = epi(A[M,K] * W[N,K]^T): bias fp32 [N] or NULL, act 0|1 (QuickGELU), residual fp32
- * [M,N] or NULL (may alias out when out_f32), out act or fp32.  impl 0 = tcgen05, 1 = SIMT ref. */
-int oake_test_gemm(const void* A, const void* W, int M, int N, int K, const float* bias, int act,
-                   const float* residual, void* out, int out_f32, int impl, void* stream);
-int oake_test_layernorm(const float* x, const float* w, const float* b, void* out_act, int rows,
+/* out[M,N] = epi(A[M,K] * W[N,K]^T), the tcgen05 GEMM with every epilogue feature:
+ *   bias fp32 [N] | NULL; colsum fp32 [N] + ln_stats fp32 [M,4,2] (4 partial (sum x, sum x^2)
+ *   pairs per row, added in order) enable the LayerNorm fold | NULL; act 0|1 (QuickGELU);
+ *   residual act [M,N] | NULL (may alias out); out_stats fp32 [M,4,2]: slot j receives
+ *   (sum y, sum y^2) over columns [256j, 256j+256) of the stored row | NULL;
+ *   out act or fp32 (fp32: bias/act only).
+ *   impl 0 = tcgen05, 1 = CUDA-core reference (bias/act/residual only). */
+int oake_test_gemm(const void* A, const void* W, int M, int N, int K, const float* bias,
+                   const float* colsum, const float* ln_stats, int act, const void* residual,
+                   float* out_stats, void* out, int out_f32, int impl, void* stream);
+/* Stand-alone LayerNorm of act rows [rows,768] (ln_post). */
+int oake_test_layernorm(const void* x_act, const float* w, const float* b, void* out_act, int rows,
                         void* stream);
 /* qkv act [R,2304], rows [B*P | B | (B)]; out act [R,768]. */
 int oake_test_attention_main(const void* qkv, void* out_act, int B, int P, void* stream);

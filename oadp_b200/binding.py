@@ -19,8 +19,7 @@ class OakeError(RuntimeError):
 
 class LayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        'ln1_w', 'ln1_b', 'qkv_w', 'qkv_b', 'out_w', 'out_b', 'ln2_w', 'ln2_b', 'fc1_w', 'fc1_b',
-        'fc2_w', 'fc2_b')]
+        'qkv_w', 'qkv_s', 'qkv_c', 'out_w', 'out_b', 'fc1_w', 'fc1_s', 'fc1_c', 'fc2_w', 'fc2_b')]
 
 
 class Weights(C.Structure):
@@ -44,8 +43,9 @@ SIGNATURES = {
     'oake_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
     'oake_profile_collect': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
-    'oake_test_gemm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'oake_test_gemm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p]),
     'oake_test_layernorm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'oake_test_attention_main': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'oake_test_attention_side': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

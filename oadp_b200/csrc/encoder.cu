@@ -38,20 +38,20 @@ enum KClass {
   K_FRONTEND = 0,
   K_GEMM_PATCH,
   K_ASSEMBLE,
-  K_LAYERNORM,
   K_GEMM_QKV,
   K_ATTN_MAIN,
   K_ATTN_SIDE,
   K_GEMM_OUT,
   K_GEMM_FC1,
   K_GEMM_FC2,
+  K_LN_POST,
   K_GEMM_PROJ,
   K_L2NORM,
   K_NUM
 };
-const char* kClassNames[K_NUM] = {"frontend",  "gemm_patch", "assemble_ln_pre", "layernorm",
-                                  "gemm_qkv",  "attn_main",  "attn_side",       "gemm_out",
-                                  "gemm_fc1",  "gemm_fc2",   "gemm_proj",       "l2norm_half"};
+const char* kClassNames[K_NUM] = {"frontend", "gemm_patch", "assemble_ln_pre", "gemm_qkv", "attn_main",
+                                  "attn_side", "gemm_out", "gemm_fc1", "gemm_fc2", "ln_post",
+                                  "gemm_proj", "l2norm_half"};
 
 struct LayerMaps {
   CUtensorMap qkv, out, fc1, fc2;
@@ -68,8 +68,8 @@ size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
   int B, P, T, R, tail_start;
-  size_t off_patches, off_patch_out, off_x, off_h, off_qkv, off_attn, off_mlp, off_head_in,
-      off_emb_raw, total;
+  size_t off_patches, off_patch_out, off_x, off_stats_a, off_stats_b, off_qkv, off_attn, off_mlp,
+      off_head_in, off_emb_raw, total;
 };
 
 }  // namespace
@@ -109,8 +109,9 @@ Plan make_plan(const oake_handle* h, int B, int variant) {
   };
   p.off_patches = take(static_cast<size_t>(B) * p.P * patch_cols * sizeof(act_t));
   p.off_patch_out = take(static_cast<size_t>(B) * p.P * W * sizeof(float));
-  p.off_x = take(static_cast<size_t>(p.R) * W * sizeof(float));
-  p.off_h = take(static_cast<size_t>(p.R) * W * sizeof(act_t));
+  p.off_x = take(static_cast<size_t>(p.R) * W * sizeof(act_t));
+  p.off_stats_a = take(static_cast<size_t>(p.R) * kStatSlots * sizeof(float2));
+  p.off_stats_b = take(static_cast<size_t>(p.R) * kStatSlots * sizeof(float2));
   p.off_qkv = take(static_cast<size_t>(p.R) * 3 * W * sizeof(act_t));
   p.off_attn = take(static_cast<size_t>(p.R) * W * sizeof(act_t));
   p.off_mlp = take(static_cast<size_t>(p.R) * 4 * W * sizeof(act_t));
@@ -209,8 +210,8 @@ int oake_create(oake_handle** out, int device, const oake_weights* weights) {
   h->tm_layer.resize(h->w.layers);
   for (int l = 0; l < h->w.layers && rc == 0; ++l) {
     const oake_layer_weights& lw = h->layers[l];
-    if (!lw.qkv_w || !lw.out_w || !lw.fc1_w || !lw.fc2_w || !lw.ln1_w || !lw.ln1_b || !lw.ln2_w ||
-        !lw.ln2_b || !lw.qkv_b || !lw.out_b || !lw.fc1_b || !lw.fc2_b) {
+    if (!lw.qkv_w || !lw.qkv_s || !lw.qkv_c || !lw.out_w || !lw.out_b || !lw.fc1_w || !lw.fc1_s ||
+        !lw.fc1_c || !lw.fc2_w || !lw.fc2_b) {
       delete h;
       return fail("layer %d has a NULL weight pointer", l);
     }
@@ -265,8 +266,9 @@ int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, 
   const int PC = 3 * h->w.patch * h->w.patch;
   act_t* patches = reinterpret_cast<act_t*>(base + p.off_patches);
   float* patch_out = reinterpret_cast<float*>(base + p.off_patch_out);
-  float* x = reinterpret_cast<float*>(base + p.off_x);
-  act_t* hbuf = reinterpret_cast<act_t*>(base + p.off_h);
+  act_t* x = reinterpret_cast<act_t*>(base + p.off_x);
+  float2* stats_a = reinterpret_cast<float2*>(base + p.off_stats_a);  // rows of x after out_proj
+  float2* stats_b = reinterpret_cast<float2*>(base + p.off_stats_b);  // rows of x entering a block
   act_t* qkv = reinterpret_cast<act_t*>(base + p.off_qkv);
   act_t* attn = reinterpret_cast<act_t*>(base + p.off_attn);
   act_t* mlp = reinterpret_cast<act_t*>(base + p.off_mlp);
@@ -274,13 +276,13 @@ int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, 
   float* emb_raw = out_raw_f32 ? out_raw_f32 : reinterpret_cast<float*>(base + p.off_emb_raw);
 
   const int R = p.R, ts = p.tail_start;
-  CUtensorMap tm_patches, tm_h, tm_attn, tm_mlp, tm_h_tail, tm_attn_tail, tm_mlp_tail, tm_head;
+  CUtensorMap tm_patches, tm_x, tm_attn, tm_mlp, tm_x_tail, tm_attn_tail, tm_mlp_tail, tm_head;
   int rc = 0;
   rc |= make_tmap_act_2d(&tm_patches, patches, static_cast<uint64_t>(B) * p.P, PC, 128);
-  rc |= make_tmap_act_2d(&tm_h, hbuf, R, W, 128);
+  rc |= make_tmap_act_2d(&tm_x, x, R, W, 128);
   rc |= make_tmap_act_2d(&tm_attn, attn, R, W, 128);
   rc |= make_tmap_act_2d(&tm_mlp, mlp, R, 4 * W, 128);
-  rc |= make_tmap_act_2d(&tm_h_tail, hbuf + static_cast<size_t>(ts) * W, B, W, 128);
+  rc |= make_tmap_act_2d(&tm_x_tail, x + static_cast<size_t>(ts) * W, B, W, 128);
   rc |= make_tmap_act_2d(&tm_attn_tail, attn + static_cast<size_t>(ts) * W, B, W, 128);
   rc |= make_tmap_act_2d(&tm_mlp_tail, mlp + static_cast<size_t>(ts) * 4 * W, B, 4 * W, 128);
   rc |= make_tmap_act_2d(&tm_head, head_in, B, W, 128);
@@ -288,20 +290,22 @@ int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, 
 
   Launcher go{h, st};
   const int ns = h->num_sms;
+  // slot 3 of the statistics is never written by a 768-wide producer: clear both tables once
+  go.err = cudaMemsetAsync(stats_a, 0, 2 * align_up(static_cast<size_t>(R) * kStatSlots * sizeof(float2)), st);
   auto gflops = [](double m, double n, double k) { return 2.0 * m * n * k; };
 
-  // K0/K1: crops -> conv1 patch matrix -> patch embedding -> tokens + ln_pre
+  // K0/K1: crops -> conv1 patch matrix -> patch embedding -> tokens + ln_pre (+ row statistics)
   go.run(K_FRONTEND, 0, [&] {
     return launch_im2col_pixels(st, pixels, patches, B, side ? 16 : 32, side ? 15 : 0, side ? 14 : 7);
   });
   {
-    GemmEpilogue ep{nullptr, nullptr, patch_out, W, 0, 1, 0};
+    GemmEpilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, patch_out, W, 0, 1, 0};
     const int M = B * p.P;
     go.run(K_GEMM_PATCH, gflops(M, W, PC), [&] { return launch_gemm(st, tm_patches, h->tm_conv1, M, W, PC, ep, ns); });
   }
   go.run(K_ASSEMBLE, 0, [&] {
     return launch_assemble_ln_pre(st, patch_out, h->w.class_emb, side ? h->w.pos_t197 : h->w.pos_t50,
-                                  h->w.ln_pre_w, h->w.ln_pre_b, x, B, p.P, W, side ? 1 : 0);
+                                  h->w.ln_pre_w, h->w.ln_pre_b, x, stats_b, B, p.P, W, side ? 1 : 0);
   });
 
   for (int l = 0; l < L; ++l) {
@@ -311,49 +315,46 @@ int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, 
     // rows that still matter after this block's attention
     const int r0 = last ? ts : 0;
     const int rn = last ? B : R;
-    float* xr = x + static_cast<size_t>(r0) * W;
+    act_t* xr = x + static_cast<size_t>(r0) * W;
 
-    go.run(K_LAYERNORM, 0, [&] { return launch_layernorm(st, x, lw.ln1_w, lw.ln1_b, hbuf, R, W); });
-    {
-      GemmEpilogue ep{lw.qkv_b, nullptr, qkv, 3 * W, 0, 0, 0};
-      go.run(K_GEMM_QKV, gflops(R, 3 * W, W), [&] { return launch_gemm(st, tm_h, tm.qkv, R, 3 * W, W, ep, ns); });
+    {  // q,k,v = ln_1(x) W^T + b   (LayerNorm folded, statistics from stats_b)
+      GemmEpilogue ep{lw.qkv_c, lw.qkv_s, stats_b, nullptr, nullptr, qkv, 3 * W, 0, 0, 0};
+      go.run(K_GEMM_QKV, gflops(R, 3 * W, W), [&] { return launch_gemm(st, tm_x, tm.qkv, R, 3 * W, W, ep, ns); });
     }
     if (!(last && side))
       go.run(K_ATTN_MAIN, 4.0 * B * p.T * p.T * W, [&] { return launch_attention_main(st, qkv, attn, B, p.P, H); });
     if (side)
       go.run(K_ATTN_SIDE, 4.0 * B * p.T * W, [&] { return launch_attention_side(st, qkv, masks, attn, B, p.P, H); });
-    {
-      GemmEpilogue ep{lw.out_b, xr, xr, W, W, 1, 0};
+    {  // x += attn W_o^T + b ; statistics of the new x -> stats_a
+      GemmEpilogue ep{lw.out_b, nullptr, nullptr, xr, stats_a + static_cast<size_t>(r0) * kStatSlots, xr, W, W, 0, 0};
       go.run(K_GEMM_OUT, gflops(rn, W, W),
              [&] { return launch_gemm(st, last ? tm_attn_tail : tm_attn, tm.out, rn, W, W, ep, ns); });
     }
-    go.run(K_LAYERNORM, 0, [&] {
-      return launch_layernorm(st, xr, lw.ln2_w, lw.ln2_b, hbuf + static_cast<size_t>(r0) * W, rn, W);
-    });
-    {
-      GemmEpilogue ep{lw.fc1_b, nullptr, mlp + static_cast<size_t>(r0) * 4 * W, 4 * W, 0, 0, 1};
+    {  // u = QuickGELU(ln_2(x) W_fc^T + b)   (LayerNorm folded, statistics from stats_a)
+      GemmEpilogue ep{lw.fc1_c, lw.fc1_s, stats_a + static_cast<size_t>(r0) * kStatSlots, nullptr, nullptr, mlp + static_cast<size_t>(r0) * 4 * W,
+                      4 * W, 0, 0, 1};
       go.run(K_GEMM_FC1, gflops(rn, 4 * W, W),
-             [&] { return launch_gemm(st, last ? tm_h_tail : tm_h, tm.fc1, rn, 4 * W, W, ep, ns); });
+             [&] { return launch_gemm(st, last ? tm_x_tail : tm_x, tm.fc1, rn, 4 * W, W, ep, ns); });
     }
-    {
-      GemmEpilogue ep{lw.fc2_b, xr, xr, W, W, 1, 0};
+    {  // x += u W_proj^T + b ; statistics of the new x -> stats_b (the next block's ln_1)
+      GemmEpilogue ep{lw.fc2_b, nullptr, nullptr, xr, last ? nullptr : stats_b, xr, W, W, 0, 0};
       go.run(K_GEMM_FC2, gflops(rn, W, 4 * W),
              [&] { return launch_gemm(st, last ? tm_mlp_tail : tm_mlp, tm.fc2, rn, W, 4 * W, ep, ns); });
     }
   }
 
   // K8: ln_post(output token) @ proj -> L2 normalise -> fp16
-  go.run(K_LAYERNORM, 0, [&] {
+  go.run(K_LN_POST, 0, [&] {
     return launch_layernorm(st, x + static_cast<size_t>(ts) * W, h->w.ln_post_w, h->w.ln_post_b, head_in, B, W);
   });
   {
-    GemmEpilogue ep{nullptr, nullptr, emb_raw, OD, 0, 1, 0};
+    GemmEpilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, emb_raw, OD, 0, 1, 0};
     go.run(K_GEMM_PROJ, gflops(B, OD, W), [&] { return launch_gemm(st, tm_head, h->tm_proj, B, OD, W, ep, ns); });
   }
   go.run(K_L2NORM, 0, [&] { return launch_l2norm_half(st, emb_raw, static_cast<__half*>(out_f16), B, OD); });
 
   if (go.err != cudaSuccess)
-    return fail("launch of %s failed: %s", go.where, cudaGetErrorString(go.err));
+    return fail("launch of %s failed: %s", go.where[0] ? go.where : "memset", cudaGetErrorString(go.err));
   return 0;
 }
 
@@ -400,12 +401,18 @@ int oake_profile_collect(oake_handle* h, int cap, const char** names, double* ms
 }
 
 // -------------------------------------------------------------------- single-kernel entry points
-int oake_test_gemm(const void* A, const void* Wt, int M, int N, int K, const float* bias, int act,
-                   const float* residual, void* out, int out_f32, int impl, void* stream) {
+int oake_test_gemm(const void* A, const void* Wt, int M, int N, int K, const float* bias,
+                   const float* colsum, const float* ln_stats, int act, const void* residual,
+                   float* out_stats, void* out, int out_f32, int impl, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GemmEpilogue ep{bias, residual, out, N, N, out_f32, act};
+  GemmEpilogue ep{bias, colsum, reinterpret_cast<const float2*>(ln_stats), static_cast<const act_t*>(residual),
+                  reinterpret_cast<float2*>(out_stats), out, N, N, out_f32, act};
+  if (colsum && (!ln_stats || !bias)) return fail("colsum needs ln_stats and bias (c_n)");
+  if (out_stats && (N % 256 != 0 || N > 256 * kStatSlots)) return fail("out_stats needs N %% 256 == 0, N <= 1024");
+  if (out_f32 && (colsum || residual || out_stats)) return fail("fp32 output supports bias / activation only");
   cudaError_t e;
   if (impl == 1) {
+    if (colsum || out_stats) return fail("the SIMT reference has no LayerNorm fold / statistics");
     e = launch_gemm_simt(st, static_cast<const act_t*>(A), static_cast<const act_t*>(Wt), M, N, K, ep);
   } else {
     int dev = 0, ns = 0;
@@ -420,9 +427,10 @@ int oake_test_gemm(const void* A, const void* Wt, int M, int N, int K, const flo
   return 0;
 }
 
-int oake_test_layernorm(const float* x, const float* w, const float* b, void* out_act, int rows,
+int oake_test_layernorm(const void* x_act, const float* w, const float* b, void* out_act, int rows,
                         void* stream) {
-  cudaError_t e = launch_layernorm(static_cast<cudaStream_t>(stream), x, w, b, static_cast<act_t*>(out_act), rows, 768);
+  cudaError_t e = launch_layernorm(static_cast<cudaStream_t>(stream), static_cast<const act_t*>(x_act), w, b,
+                                   static_cast<act_t*>(out_act), rows, 768);
   if (e != cudaSuccess) return fail("layernorm launch: %s", cudaGetErrorString(e));
   return 0;
 }

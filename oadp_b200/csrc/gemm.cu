@@ -38,59 +38,187 @@ struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
+  static constexpr int kStgRowBytes = 128 + 16;              // 128 B of payload + 16 B bank skew
+  static constexpr int kStgBytes = 32 * kStgRowBytes;        // one 32-row strip per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 4 * kStgBytes + 1024;
   static constexpr int kTmemCols = 2 * BN;
 };
 
-__device__ __forceinline__ float quick_gelu(float u) { return u / (1.0f + __expf(-1.702f * u)); }
+// QuickGELU u * sigmoid(1.702 u) = h + h * tanh(0.851 u), h = u / 2: one MUFU per element.
+__device__ __forceinline__ float quick_gelu(float u) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * u));
+  const float h = 0.5f * u;
+  return fmaf(h, t, h);
+}
 
-// 32 consecutive output columns of one row.
-__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, float (&v)[32], int row,
-                                               int col0) {
-  if (ep.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+__device__ __forceinline__ void add_bias32(const float* __restrict__ bias, float (&v)[32]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x;
-      v[4 * j + 1] += b.y;
-      v[4 * j + 2] += b.z;
-      v[4 * j + 3] += b.w;
-    }
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(b4 + j);
+    v[4 * j + 0] += b.x;
+    v[4 * j + 1] += b.y;
+    v[4 * j + 2] += b.z;
+    v[4 * j + 3] += b.w;
   }
-  if (ep.act == 1) {
+}
+
+// Epilogue of one warp on one 32-row strip of the accumulator.  Each thread owns a row in TMEM, but
+// a thread-per-row global access pattern touches half sectors 32 rows apart; instead every
+// 128-byte row segment goes through a per-warp shared-memory strip (144-byte row pitch:
+// conflict-free both ways) so that each global instruction moves 4 rows x 128 contiguous bytes.
+//
+// act_t output (the tower's hot epilogues), chunks of 64 columns:
+//   y = [LayerNorm fold] rstd_m * (acc - mean_m * s_n) + c_n   (W was pre-multiplied by gamma,
+//        s_n = sum_k W'[n,k], c_n = sum_k beta_k W[n,k] + b_n; mean/rstd from the row statistics
+//        the PRODUCER of the A rows accumulated) | acc + bias_n
+//   y = QuickGELU(y)                       (c_fc)
+//   y += residual (fp16, may alias out)    (out_proj, c_proj)
+//   out = fp16(y);  out_stats[m] += (sum y, sum y^2) over this tile's columns of the rounded y
+// fp32 output (patch embedding, final projection), chunks of 32 columns: bias / QuickGELU only.
+struct RowLn {
+  float rstd, nmr;  // y = rstd * acc + nmr * s_n + c_n,  nmr = -mean * rstd
+};
+
+__device__ __forceinline__ void load_residual_chunk(uint4 (&res)[8], const GemmEpilogue& ep, int row0,
+                                                    int col0, int M, int sub_r, int sub_c) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+  for (int i = 0; i < 8; ++i) {
+    const int r = row0 + 4 * i + sub_r;
+    res[i] = make_uint4(0, 0, 0, 0);
+    if (r < M)
+      res[i] = *reinterpret_cast<const uint4*>(
+          reinterpret_cast<const uint8_t*>(ep.residual + static_cast<size_t>(r) * ep.ld_res + col0) + sub_c);
   }
-  if (ep.residual != nullptr) {
-    const float4* r4 =
-        reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + col0);
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_strip_act(const GemmEpilogue& ep, uint32_t t_strip, uint8_t* stg,
+                                                   int row0, int col_base, int M, int lane, uint4 (&res)[8],
+                                                   const RowLn ln) {
+  constexpr int kPitch = Cfg<BN>::kStgRowBytes;
+  constexpr int NC = BN / 64;
+  uint8_t* my_row = stg + lane * kPitch;
+  const int sub_r = lane >> 3;        // coalesced phase: 4 rows per instruction ...
+  const int sub_c = (lane & 7) * 16;  // ... 8 lanes x 16 B per row
+  const bool has_res = ep.residual != nullptr;
+  float sum = 0.f, sumsq = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < NC; ++c) {
+    const int col0 = col_base + c * 64;
+    if (has_res) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 r = r4[j];
-      v[4 * j + 0] += r.x;
-      v[4 * j + 1] += r.y;
-      v[4 * j + 2] += r.z;
-      v[4 * j + 3] += r.w;
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stg + (4 * i + sub_r) * kPitch + sub_c) = res[i];
+      if (c + 1 < NC) load_residual_chunk(res, ep, row0, col0 + 64, M, sub_r, sub_c);  // in flight below
+      __syncwarp();
     }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r32[32];
+      tmem_ld_32x32(t_strip + c * 64 + half * 32, r32);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
+      const int cc = col0 + half * 32;
+      if (ep.colsum != nullptr) {  // y = rstd * acc + (nmr * s_n + c_n)
+        const float4* s4 = reinterpret_cast<const float4*>(ep.colsum + cc);
+        const float4* c4 = reinterpret_cast<const float4*>(ep.bias + cc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 sv = __ldg(s4 + j);
+          const float4 cv = __ldg(c4 + j);
+          v[4 * j + 0] = fmaf(ln.rstd, v[4 * j + 0], fmaf(ln.nmr, sv.x, cv.x));
+          v[4 * j + 1] = fmaf(ln.rstd, v[4 * j + 1], fmaf(ln.nmr, sv.y, cv.y));
+          v[4 * j + 2] = fmaf(ln.rstd, v[4 * j + 2], fmaf(ln.nmr, sv.z, cv.z));
+          v[4 * j + 3] = fmaf(ln.rstd, v[4 * j + 3], fmaf(ln.nmr, sv.w, cv.w));
+        }
+      } else if (ep.bias != nullptr) {
+        add_bias32(ep.bias + cc, v);
+      }
+      if (ep.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+      }
+      uint4* seg = reinterpret_cast<uint4*>(my_row + half * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (has_res) {
+          const uint4 rv = seg[j];
+          const float2 r0 = unpack2(rv.x), r1 = unpack2(rv.y), r2 = unpack2(rv.z), r3 = unpack2(rv.w);
+          v[8 * j + 0] += r0.x;
+          v[8 * j + 1] += r0.y;
+          v[8 * j + 2] += r1.x;
+          v[8 * j + 3] += r1.y;
+          v[8 * j + 4] += r2.x;
+          v[8 * j + 5] += r2.y;
+          v[8 * j + 6] += r3.x;
+          v[8 * j + 7] += r3.y;
+        }
+        uint4 u;
+        u.x = pack2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack2(v[8 * j + 6], v[8 * j + 7]);
+        seg[j] = u;
+        if (ep.out_stats != nullptr) {  // statistics of the values as stored (rounded)
+          const float2 a = unpack2(u.x), b = unpack2(u.y), cdd = unpack2(u.z), d = unpack2(u.w);
+          sum += (a.x + a.y) + (b.x + b.y) + (cdd.x + cdd.y) + (d.x + d.y);
+          sumsq += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cdd.x * cdd.x + cdd.y * cdd.y + d.x * d.x + d.y * d.y;
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + sub_r;
+      if (row0 + r < M)
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(
+            static_cast<act_t*>(ep.out) + static_cast<size_t>(row0 + r) * ep.ldo + col0) + sub_c) =
+            *reinterpret_cast<const uint4*>(stg + r * kPitch + sub_c);
+    }
+    __syncwarp();
   }
-  if (ep.out_f32) {
-    float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(ep.out) +
-                                           static_cast<size_t>(row) * ep.ldo + col0);
+  // One slot per 256-column block, summed in a fixed order by the consumer: deterministic (no atomics).
+  if (ep.out_stats != nullptr && row0 + lane < M)
+    ep.out_stats[static_cast<size_t>(row0 + lane) * kStatSlots + col_base / 256] = make_float2(sum, sumsq);
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_strip_f32(const GemmEpilogue& ep, uint32_t t_strip, uint8_t* stg,
+                                                   int row0, int col_base, int M, int lane) {
+  constexpr int kPitch = Cfg<BN>::kStgRowBytes;
+  uint8_t* my_row = stg + lane * kPitch;
+  const int sub_r = lane >> 3;
+  const int sub_c = (lane & 7) * 16;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col0 = col_base + c * 32;
+    uint32_t r32[32];
+    tmem_ld_32x32(t_strip + c * 32, r32);
+    tmem_ld_wait();
+    float v[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else {
-    uint4* o4 = reinterpret_cast<uint4*>(static_cast<act_t*>(ep.out) +
-                                         static_cast<size_t>(row) * ep.ldo + col0);
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
+    if (ep.bias != nullptr) add_bias32(ep.bias + col0, v);
+    if (ep.act == 1) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 u;
-      u.x = pack2(v[8 * j + 0], v[8 * j + 1]);
-      u.y = pack2(v[8 * j + 2], v[8 * j + 3]);
-      u.z = pack2(v[8 * j + 4], v[8 * j + 5]);
-      u.w = pack2(v[8 * j + 6], v[8 * j + 7]);
-      o4[j] = u;
+      for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(my_row + j * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + sub_r;
+      if (row0 + r < M)
+        *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(
+            static_cast<float*>(ep.out) + static_cast<size_t>(row0 + r) * ep.ldo + col0) + sub_c) =
+            *reinterpret_cast<const float4*>(stg + r * kPitch + sub_c);
+    }
+    __syncwarp();
   }
 }
 
@@ -110,6 +238,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full_bar = empty_bar + C::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* stg_base = smem + C::kStages * C::kStageBytes + C::kBarBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -203,23 +332,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n;
       const int n_blk = tile - m_blk * num_n;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
-      const uint32_t t_base =
-          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_base + c * 32, r);
-        tmem_ld_wait();
-        if (row < M) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epilogue_chunk(ep, v, row, n_blk * BN + c * 32);
+      const int row0 = m_blk * BM + q * 32;
+      uint8_t* stg = stg_base + q * C::kStgBytes;
+      // Everything that does not depend on the accumulator is fetched before waiting for it.
+      uint4 res[8];
+      RowLn ln{1.f, 0.f};
+      if (!ep.out_f32) {
+        if (ep.residual != nullptr) load_residual_chunk(res, ep, row0, n_blk * BN, M, lane >> 3, (lane & 7) * 16);
+        if (ep.colsum != nullptr && row0 + lane < M) {
+          const float4* sp = reinterpret_cast<const float4*>(ep.ln_stats + static_cast<size_t>(row0 + lane) * kStatSlots);
+          const float4 s01 = sp[0], s23 = sp[1];
+          const float sx = ((s01.x + s01.z) + s23.x) + s23.z;
+          const float sxx = ((s01.y + s01.w) + s23.y) + s23.w;
+          const float inv_k = 1.0f / static_cast<float>(K);
+          const float mean = sx * inv_k;
+          const float var = fmaxf(sxx * inv_k - mean * mean, 0.f);
+          ln.rstd = rsqrtf(var + 1e-5f);
+          ln.nmr = -mean * ln.rstd;
         }
       }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_strip =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      if (ep.out_f32)
+        epilogue_strip_f32<BN>(ep, t_strip, stg, row0, n_blk * BN, M, lane);
+      else
+        epilogue_strip_act<BN>(ep, t_strip, stg, row0, n_blk * BN, M, lane, res, ln);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -260,7 +399,7 @@ __global__ void gemm_simt_kernel(const act_t* __restrict__ A, const act_t* __res
     float v = acc;
     if (ep.bias) v += ep.bias[col];
     if (ep.act == 1) v = quick_gelu(v);
-    if (ep.residual) v += ep.residual[static_cast<size_t>(row) * ep.ld_res + col];
+    if (ep.residual) v += from_act(ep.residual[static_cast<size_t>(row) * ep.ld_res + col]);
     if (ep.out_f32)
       static_cast<float*>(ep.out)[static_cast<size_t>(row) * ep.ldo + col] = v;
     else

@@ -6,13 +6,21 @@
 namespace oake {
 
 // ---------------------------------------------------------------- gemm.cu
+// Row statistics travel as kStatSlots partial (sum, sum of squares) pairs per row: the producing
+// GEMM writes slot n_blk (one per 256 output columns, N <= 1024), the consumer adds the slots in
+// a fixed order -- deterministic, no atomics, no memset (unused slots must hold zeros).
+constexpr int kStatSlots = 4;
+
 struct GemmEpilogue {
-  const float* bias;      // [N] fp32 or nullptr
-  const float* residual;  // fp32 [M, ld_res] added after the activation, or nullptr
-  void* out;              // act_t or fp32 [M, ldo]; may alias `residual`
+  const float* bias;        // [N] fp32 (plain bias, or the folded c_n; required with colsum) or nullptr
+  const float* colsum;      // [N] fp32 s_n = sum_k W'[n,k]: enables the LayerNorm fold, or nullptr
+  const float2* ln_stats;   // [M][kStatSlots] statistics of the A rows over K; required with colsum
+  const act_t* residual;    // act_t [M, ld_res] added after the activation (act_t output only)
+  float2* out_stats;        // [M][kStatSlots] statistics of the stored rows (N % 256 == 0), or nullptr
+  void* out;                // act_t or fp32 [M, ldo]; may alias `residual`
   int ldo;
   int ld_res;
-  int out_f32;  // 1: fp32 output, 0: act_t output
+  int out_f32;  // 1: fp32 output (bias / activation only), 0: act_t output
   int act;      // 0: identity, 1: QuickGELU  u * sigmoid(1.702 u)
 };
 
@@ -31,13 +39,16 @@ cudaError_t launch_gemm_simt(cudaStream_t st, const act_t* A, const act_t* W, in
                              const GemmEpilogue& ep);
 
 // -------------------------------------------------------------- rowops.cu
-cudaError_t launch_layernorm(cudaStream_t st, const float* x, const float* w, const float* b,
+// LayerNorm of act_t rows (only ln_post uses a stand-alone LayerNorm; ln_1 / ln_2 are folded into
+// the consuming GEMM's epilogue).
+cudaError_t launch_layernorm(cudaStream_t st, const act_t* x, const float* w, const float* b,
                              act_t* out, int rows, int width);
-// Builds the residual stream: rows [0, B*P) = LN(patch_out + pos[1 + i % P]); rows [B*P, B*P+B) =
-// LN(class_emb + pos[0]); if with_y, rows [B*P+B, B*P+2B) = copy of the class rows.
+// Builds the residual stream x (act_t) and its row statistics ([rows][kStatSlots], slot 0 = sum /
+// sum of squares of the stored values, other slots zero): rows [0, B*P) = LN(patch_out + pos[1 + i % P]); rows [B*P, B*P+B) = LN(class_emb +
+// pos[0]); if with_y, rows [B*P+B, B*P+2B) = copy of the class rows.
 cudaError_t launch_assemble_ln_pre(cudaStream_t st, const float* patch_out, const float* class_emb,
-                                   const float* pos, const float* w, const float* b, float* x,
-                                   int B, int P, int width, int with_y);
+                                   const float* pos, const float* w, const float* b, act_t* x,
+                                   float2* stats, int B, int P, int width, int with_y);
 cudaError_t launch_l2norm_half(cudaStream_t st, const float* e, __half* out, int rows, int dim);
 
 // ----------------------------------------------------------- attention.cu

@@ -1,5 +1,6 @@
-// Row-wise fp32 kernels of the OAKE tower: LayerNorm, token assembly + ln_pre
-// (the tail of K1), final L2-normalise + fp16 cast (K8; reference: F.normalize(...).half() at
+// Row-wise kernels of the OAKE tower: token assembly + ln_pre (the tail of SURVEY 2.2 K1), the
+// stand-alone LayerNorm used for ln_post (K2; ln_1 / ln_2 are folded into the GEMM epilogues),
+// final L2-normalise + fp16 cast (K8; reference: F.normalize(...).half() at
 // oadp/oake/globals.py:58-59, blocks.py:130-133, objects.py:331-334).
 // One warp per 768-wide row, statistics in fp32 registers, 128-bit global accesses.
 #include "kernels.cuh"
@@ -9,7 +10,6 @@ namespace oake {
 namespace {
 
 constexpr int kWidth = 768;
-constexpr int kPerLane = kWidth / 32;  // 24 floats = 6 float4 per lane
 constexpr float kLnEps = 1e-5f;
 
 // v: 24 values of one row held by this lane as 6 float4 at float4 index lane + 32*j.
@@ -42,32 +42,46 @@ __device__ __forceinline__ void ln_normalize(float4 (&v)[6], const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                 const float* __restrict__ b, act_t* __restrict__ out, int rows) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float4* x4 = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * kWidth);
-  float4 v[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) v[j] = x4[lane + 32 * j];
-  ln_normalize(v, w, b, lane);
-  uint2* o2 = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * kWidth);
+// Packs a normalised row to act_t, stores it, and returns (sum, sum of squares) of the STORED values.
+__device__ __forceinline__ float2 store_row_act(act_t* dst, const float4 (&v)[6], int lane) {
+  uint2* o2 = reinterpret_cast<uint2*>(dst);
+  float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     uint2 u;
     u.x = pack2(v[j].x, v[j].y);
     u.y = pack2(v[j].z, v[j].w);
     o2[lane + 32 * j] = u;
+    const float2 a = unpack2(u.x), b = unpack2(u.y);
+    s += (a.x + a.y) + (b.x + b.y);
+    ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
   }
+  return make_float2(warp_sum(s), warp_sum(ss));
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const act_t* __restrict__ x, const float* __restrict__ w,
+                 const float* __restrict__ b, act_t* __restrict__ out, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint2* x2 = reinterpret_cast<const uint2*>(x + static_cast<size_t>(row) * kWidth);
+  float4 v[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const uint2 u = x2[lane + 32 * j];
+    const float2 a = unpack2(u.x), c = unpack2(u.y);
+    v[j] = make_float4(a.x, a.y, c.x, c.y);
+  }
+  ln_normalize(v, w, b, lane);
+  store_row_act(out + static_cast<size_t>(row) * kWidth, v, lane);
 }
 
 __global__ void __launch_bounds__(256)
 assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restrict__ class_emb,
                        const float* __restrict__ pos, const float* __restrict__ w,
-                       const float* __restrict__ b, float* __restrict__ x, int B, int P,
-                       int with_y) {
+                       const float* __restrict__ b, act_t* __restrict__ x, float2* __restrict__ stats,
+                       int B, int P, int with_y) {
   const int rows = B * P + B;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -85,13 +99,12 @@ assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restr
     v[j] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
   }
   ln_normalize(v, w, b, lane);
-  float4* o4 = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * kWidth);
-#pragma unroll
-  for (int j = 0; j < 6; ++j) o4[lane + 32 * j] = v[j];
+  const float2 st = store_row_act(x + static_cast<size_t>(row) * kWidth, v, lane);
+  if (lane < kStatSlots) stats[static_cast<size_t>(row) * kStatSlots + lane] = lane == 0 ? st : make_float2(0.f, 0.f);
   if (is_cls && with_y) {  // side token y0 = x[CLS] right after ln_pre (objects.py:216-222)
-    float4* y4 = reinterpret_cast<float4*>(x + static_cast<size_t>(row + B) * kWidth);
-#pragma unroll
-    for (int j = 0; j < 6; ++j) y4[lane + 32 * j] = v[j];
+    store_row_act(x + static_cast<size_t>(row + B) * kWidth, v, lane);
+    if (lane < kStatSlots)
+      stats[static_cast<size_t>(row + B) * kStatSlots + lane] = lane == 0 ? st : make_float2(0.f, 0.f);
   }
 }
 
@@ -110,7 +123,7 @@ l2norm_half_kernel(const float* __restrict__ e, __half* __restrict__ out, int ro
 
 }  // namespace
 
-cudaError_t launch_layernorm(cudaStream_t st, const float* x, const float* w, const float* b,
+cudaError_t launch_layernorm(cudaStream_t st, const act_t* x, const float* w, const float* b,
                              act_t* out, int rows, int width) {
   if (width != kWidth) return cudaErrorInvalidValue;
   if (rows <= 0) return cudaSuccess;
@@ -119,13 +132,13 @@ cudaError_t launch_layernorm(cudaStream_t st, const float* x, const float* w, co
 }
 
 cudaError_t launch_assemble_ln_pre(cudaStream_t st, const float* patch_out, const float* class_emb,
-                                   const float* pos, const float* w, const float* b, float* x, int B,
-                                   int P, int width, int with_y) {
+                                   const float* pos, const float* w, const float* b, act_t* x,
+                                   float2* stats, int B, int P, int width, int with_y) {
   if (width != kWidth) return cudaErrorInvalidValue;
   if (B <= 0) return cudaSuccess;
   const int rows = B * P + B;
-  assemble_ln_pre_kernel<<<(rows + 7) / 8, 256, 0, st>>>(patch_out, class_emb, pos, w, b, x, B, P,
-                                                         with_y);
+  assemble_ln_pre_kernel<<<(rows + 7) / 8, 256, 0, st>>>(patch_out, class_emb, pos, w, b, x, stats, B,
+                                                         P, with_y);
   return cudaGetLastError();
 }
 

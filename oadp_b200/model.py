@@ -43,6 +43,19 @@ def resample_positional_embedding(pos: torch.Tensor, grid_to: int, mode: str = '
     return torch.cat([pos[:1].float(), grid])
 
 
+def fold_layernorm(weight: torch.Tensor, bias: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                   act: torch.dtype) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """LN(x; gamma, beta) W^T + b  ==  rstd * (x W'^T - mean * s) + c   (include/oake_b200.h).
+
+    Returns (W' = W diag(gamma) rounded to `act`, s = row sums of the ROUNDED W' in fp32,
+    c = W beta + b in fp32).  Computed in fp64 so the fold itself adds no error."""
+    w64 = weight.double()
+    w_folded = (w64 * gamma.double()[None, :]).to(act)
+    s = w_folded.double().sum(dim=1).float()
+    c = (w64 @ beta.double() + bias.double()).float()
+    return w_folded, s, c
+
+
 def _act_torch_dtype() -> torch.dtype:
     return {'f16': torch.float16, 'bf16': torch.bfloat16}[binding.act_dtype_name()]
 
@@ -77,15 +90,23 @@ class _Packed:
             add(f'{n}_w', params[f'{n}.weight'], torch.float32)
             add(f'{n}_b', params[f'{n}.bias'], torch.float32)
         add('proj_w', params['proj'].T, act)
-        names = (('ln1_w', 'ln_1.weight', 0), ('ln1_b', 'ln_1.bias', 0),
-                 ('qkv_w', 'attn.in_proj_weight', 1), ('qkv_b', 'attn.in_proj_bias', 0),
-                 ('out_w', 'attn.out_proj.weight', 1), ('out_b', 'attn.out_proj.bias', 0),
-                 ('ln2_w', 'ln_2.weight', 0), ('ln2_b', 'ln_2.bias', 0),
-                 ('fc1_w', 'mlp.c_fc.weight', 1), ('fc1_b', 'mlp.c_fc.bias', 0),
-                 ('fc2_w', 'mlp.c_proj.weight', 1), ('fc2_b', 'mlp.c_proj.bias', 0))
+        fields = ('qkv_w', 'qkv_s', 'qkv_c', 'out_w', 'out_b', 'fc1_w', 'fc1_s', 'fc1_c', 'fc2_w', 'fc2_b')
         for i in range(layers):
-            for field, src, is_act in names:
-                add(f'{i}.{field}', params[f'transformer.resblocks.{i}.{src}'], act if is_act else torch.float32)
+            pre = f'transformer.resblocks.{i}.'
+            qw, qs, qc = fold_layernorm(params[pre + 'attn.in_proj_weight'].cpu(), params[pre + 'attn.in_proj_bias'].cpu(),
+                                        params[pre + 'ln_1.weight'].cpu(), params[pre + 'ln_1.bias'].cpu(), act)
+            fw, fs, fc = fold_layernorm(params[pre + 'mlp.c_fc.weight'].cpu(), params[pre + 'mlp.c_fc.bias'].cpu(),
+                                        params[pre + 'ln_2.weight'].cpu(), params[pre + 'ln_2.bias'].cpu(), act)
+            add(f'{i}.qkv_w', qw, act)
+            add(f'{i}.qkv_s', qs, torch.float32)
+            add(f'{i}.qkv_c', qc, torch.float32)
+            add(f'{i}.out_w', params[pre + 'attn.out_proj.weight'], act)
+            add(f'{i}.out_b', params[pre + 'attn.out_proj.bias'], torch.float32)
+            add(f'{i}.fc1_w', fw, act)
+            add(f'{i}.fc1_s', fs, torch.float32)
+            add(f'{i}.fc1_c', fc, torch.float32)
+            add(f'{i}.fc2_w', params[pre + 'mlp.c_proj.weight'], act)
+            add(f'{i}.fc2_b', params[pre + 'mlp.c_proj.bias'], torch.float32)
 
         offsets, total = {}, 0
         for key, t in entries:
@@ -101,7 +122,7 @@ class _Packed:
 
         self.layer_array = (binding.LayerWeights * layers)()
         for i in range(layers):
-            for field, _, _ in names:
+            for field in fields:
                 setattr(self.layer_array[i], field, ptr[f'{i}.{field}'])
         w = binding.Weights()
         w.layers, w.width, w.heads, w.patch, w.out_dim, w.image = layers, WIDTH, HEADS, PATCH, OUT_DIM, IMAGE
@@ -115,7 +136,8 @@ class _Packed:
 class OakeEngine:
     """One liboake_b200 handle bound to (device, current stream) + a growable workspace."""
 
-    MAX_CROPS = {binding.VARIANT_T50: 2048, binding.VARIANT_T197: 512}
+    # chunk sizes chosen so that ceil(rows / 128) lands on a multiple of the 148 SMs (no ragged last wave)
+    MAX_CROPS = {binding.VARIANT_T50: 1894, binding.VARIANT_T197: 478}
 
     def __init__(self, params: Params, device: torch.device | str = 'cuda', pos_mode: str = 'bilinear') -> None:
         self.lib = binding.load()

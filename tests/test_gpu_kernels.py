@@ -19,17 +19,21 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def run_gemm(lib, A, W, bias=None, act=0, residual=None, out_f32=False, impl=0, inplace=False):
+def ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def run_gemm(lib, A, W, bias=None, colsum=None, ln_stats=None, act=0, residual=None, out_stats=None,
+             out_f32=False, impl=0, inplace=False):
     M, K = A.shape
     N = W.shape[0]
     if inplace:
         out = residual
     else:
         out = torch.full((M, N), float('nan'), device=DEV, dtype=torch.float32 if out_f32 else act_dtype())
-    binding.check(lib.oake_test_gemm(A.data_ptr(), W.data_ptr(), M, N, K,
-                                     bias.data_ptr() if bias is not None else None, act,
-                                     residual.data_ptr() if residual is not None else None,
-                                     out.data_ptr(), int(out_f32), impl, stream()))
+    binding.check(lib.oake_test_gemm(A.data_ptr(), W.data_ptr(), M, N, K, ptr(bias), ptr(colsum), ptr(ln_stats),
+                                     act, ptr(residual), ptr(out_stats), out.data_ptr(), int(out_f32), impl,
+                                     stream()))
     torch.cuda.synchronize()
     return out
 
@@ -41,8 +45,13 @@ def ref_gemm(A, W, bias=None, act=0, residual=None):
     if act == 1:
         y = y * torch.sigmoid(1.702 * y)
     if residual is not None:
-        y = y + residual
+        y = y + residual.float()
     return y
+
+
+def act_tol(scale=1.0):
+    """one rounding of a value of magnitude ~scale to the activation type (+ tanh.approx slack)"""
+    return scale * (2e-3 if act_dtype() == torch.float16 else 1.6e-2)
 
 
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (128, 256, 128), (300, 768, 768), (1000, 2304, 768),
@@ -78,29 +87,60 @@ def test_gemm_epilogues(lib):
     out = run_gemm(lib, A, W1, bias=b1, act=1)
     ref = ref_gemm(A, W1, b1, 1)
     assert out.dtype == act_dtype()
-    assert (out.float() - ref).abs().max() < 2e-2  # one fp16/bf16 rounding of |y| <~ 8
-    # c_proj + bias + in-place fp32 residual
+    assert (out.float() - ref).abs().max() < act_tol(8)
+    # c_proj + bias + in-place act residual + row statistics of what was stored
     H = out
     W2 = (torch.randn(768, 3072, device=DEV, generator=g) * 3072**-0.5).to(act_dtype())
     b2 = torch.randn(768, device=DEV, generator=g) * 0.1
-    x = torch.randn(M, 768, device=DEV, generator=g)
+    x = (torch.randn(M, 768, device=DEV, generator=g) * 2).to(act_dtype())
     ref2 = ref_gemm(H, W2, b2, 0, x.clone())
-    out2 = run_gemm(lib, H, W2, bias=b2, residual=x, out_f32=True, inplace=True)
+    stats = torch.zeros(M, 4, 2, device=DEV)
+    out2 = run_gemm(lib, H, W2, bias=b2, residual=x, out_stats=stats, inplace=True)
     assert out2.data_ptr() == x.data_ptr()
-    assert (out2 - ref2).abs().max() < 2e-3
+    assert (out2.float() - ref2).abs().max() < act_tol(8)
+    assert (stats[:, 3] == 0).all()  # 768 columns fill slots 0..2 only
+    assert torch.allclose(stats[..., 0].sum(1), out2.float().sum(-1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[..., 1].sum(1), (out2.float()**2).sum(-1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:, 1, 0], out2.float()[:, 256:512].sum(-1), rtol=1e-4, atol=1e-2)
+    # the CUDA-core reference of the same contract agrees
+    x2 = (torch.randn(M, 768, device=DEV, generator=g) * 2).to(act_dtype())
+    a = run_gemm(lib, H, W2, bias=b2, residual=x2, impl=0)
+    b = run_gemm(lib, H, W2, bias=b2, residual=x2, impl=1)
+    assert (a.float() - b.float()).abs().max() < act_tol(8)
+
+
+def test_gemm_layernorm_fold(lib):
+    """y = LN(x) W^T + b evaluated as rstd * (x W'^T - mean * s) + c with statistics from a buffer."""
+    from oadp_b200.model import fold_layernorm
+    g = torch.Generator(device=DEV).manual_seed(8)
+    M, K, N = 777, 768, 2304
+    x = (torch.randn(M, K, device=DEV, generator=g) * 3 + 0.7).to(act_dtype())
+    W = torch.randn(N, K, device=DEV, generator=g) * K**-0.5
+    b = torch.randn(N, device=DEV, generator=g) * 0.1
+    gamma = 1 + 0.1 * torch.randn(K, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(K, device=DEV, generator=g)
+    Wf, s, c = fold_layernorm(W.cpu(), b.cpu(), gamma.cpu(), beta.cpu(), act_dtype())
+    Wf, s, c = Wf.to(DEV), s.to(DEV), c.to(DEV)
+    xf = x.float()
+    stats = torch.zeros(M, 4, 2, device=DEV)
+    for j in range(3):  # partial statistics, as the producing GEMM leaves them
+        stats[:, j, 0] = xf[:, 256 * j:256 * j + 256].sum(-1)
+        stats[:, j, 1] = (xf[:, 256 * j:256 * j + 256]**2).sum(-1)
+    out = run_gemm(lib, x, Wf, bias=c, colsum=s, ln_stats=stats, out_f32=False)
+    ref = F.layer_norm(xf, (K, ), gamma, beta, 1e-5) @ W.T + b
+    assert (out.float() - ref).abs().max() < act_tol(6) + 6e-3, (out.float() - ref).abs().max()
 
 
 def test_layernorm(lib):
     g = torch.Generator(device=DEV).manual_seed(7)
-    x = torch.randn(1001, 768, device=DEV, generator=g) * 3 + 0.5
+    x = (torch.randn(1001, 768, device=DEV, generator=g) * 3 + 0.5).to(act_dtype())
     w = 1 + 0.1 * torch.randn(768, device=DEV, generator=g)
     b = 0.1 * torch.randn(768, device=DEV, generator=g)
     out = torch.empty(1001, 768, device=DEV, dtype=act_dtype())
     binding.check(lib.oake_test_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), 1001, stream()))
     torch.cuda.synchronize()
-    ref = F.layer_norm(x, (768, ), w, b, 1e-5)
-    tol = 4e-3 if act_dtype() == torch.float16 else 3e-2
-    assert (out.float() - ref).abs().max() < tol
+    ref = F.layer_norm(x.float(), (768, ), w, b, 1e-5)
+    assert (out.float() - ref).abs().max() < act_tol(5)
 
 
 def ref_attention(qkv, B, P, side_mask=None):
