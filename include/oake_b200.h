@@ -118,10 +118,10 @@ int oake_profile_collect(oake_handle* h, int cap, const char** names, double* ms
 
 /* ---- single-kernel entry points (unit tests; all pointers device, row-major) --------------- */
 /* out[M,N] = epi(A[M,K] * W[N,K]^T), the tcgen05 GEMM with every epilogue feature:
- *   bias fp32 [N] | NULL; colsum fp32 [N] + ln_stats fp32 [M,4,2] (4 partial (sum x, sum x^2)
+ *   bias fp32 [N] | NULL; colsum fp32 [N] + ln_stats fp32 [M,8,2] (8 partial (sum x, sum x^2)
  *   pairs per row, added in order) enable the LayerNorm fold | NULL; act 0|1 (QuickGELU);
- *   residual act [M,N] | NULL (may alias out); out_stats fp32 [M,4,2]: slot j receives
- *   (sum y, sum y^2) over columns [256j, 256j+256) of the stored row | NULL;
+ *   residual act [M,N] | NULL (may alias out; excludes act / fold); out_stats fp32 [M,8,2]: slot j
+ *   receives (sum y, sum y^2) over columns [128j, 128j+128) of the output row (needs residual) | NULL;
  *   out act or fp32 (fp32: bias/act only).
  *   impl 0 = tcgen05, 1 = CUDA-core reference (bias/act/residual only). */
 int oake_test_gemm(const void* A, const void* W, int M, int N, int K, const float* bias,

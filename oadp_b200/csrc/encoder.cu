@@ -290,7 +290,7 @@ int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, 
 
   Launcher go{h, st};
   const int ns = h->num_sms;
-  // slot 3 of the statistics is never written by a 768-wide producer: clear both tables once
+  // a 768-wide producer fills 6 of the 8 statistic slots: clear both tables once per call
   go.err = cudaMemsetAsync(stats_a, 0, 2 * align_up(static_cast<size_t>(R) * kStatSlots * sizeof(float2)), st);
   auto gflops = [](double m, double n, double k) { return 2.0 * m * n * k; };
 
@@ -408,7 +408,9 @@ int oake_test_gemm(const void* A, const void* Wt, int M, int N, int K, const flo
   GemmEpilogue ep{bias, colsum, reinterpret_cast<const float2*>(ln_stats), static_cast<const act_t*>(residual),
                   reinterpret_cast<float2*>(out_stats), out, N, N, out_f32, act};
   if (colsum && (!ln_stats || !bias)) return fail("colsum needs ln_stats and bias (c_n)");
-  if (out_stats && (N % 256 != 0 || N > 256 * kStatSlots)) return fail("out_stats needs N %% 256 == 0, N <= 1024");
+  if (out_stats && (!residual || N % 256 != 0 || N > 128 * kStatSlots))
+    return fail("out_stats needs a residual, N %% 256 == 0 and N <= 1024");
+  if (residual && (act != 0 || colsum)) return fail("the residual epilogue has no activation / LayerNorm fold");
   if (out_f32 && (colsum || residual || out_stats)) return fail("fp32 output supports bias / activation only");
   cudaError_t e;
   if (impl == 1) {

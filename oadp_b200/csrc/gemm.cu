@@ -6,17 +6,20 @@
 // patch embedding after im2col, QKV, attention out-proj + residual, c_fc + QuickGELU,
 // c_proj + residual, final projection), replacing the cuDNN/cuBLAS calls the reference makes
 // through clip.model.VisionTransformer (call sites oadp/oake/globals.py:57, blocks.py:129,
-// objects.py:330).
+// objects.py:330), and it absorbs ln_1 / ln_2 (LayerNorm folded into the consumer's epilogue,
+// row statistics emitted by the producer's epilogue).
 //
-// Structure (one CTA per SM, 256 threads):
-//   warp 0    : TMA producer   -- cp.async.bulk.tensor 128x64 A tile + BNx64 W tile per stage,
-//                                 128B-swizzled, completion on the stage's `full` mbarrier
-//   warp 1    : MMA issuer     -- one elected thread issues 4 x tcgen05.mma (K=16) per stage into
-//                                 a TMEM accumulator, tcgen05.commit releases the stage
-//   warp 2    : TMEM allocator
-//   warps 4-7 : epilogue       -- tcgen05.ld the finished 128xBN fp32 accumulator (double buffered
-//                                 in TMEM so the next tile's MMAs overlap), bias / QuickGELU /
-//                                 fp32 residual, store fp16 or fp32
+// Structure (one CTA per SM, 384 threads):
+//   warp 0     : TMA producer   -- cp.async.bulk.tensor 128x64 A tile + BNx64 W tile per stage,
+//                                  128B-swizzled, completion on the stage's `full` mbarrier
+//   warp 1     : MMA issuer     -- one elected thread issues 4 x tcgen05.mma (K=16) per stage into
+//                                  a TMEM accumulator, tcgen05.commit releases the stage
+//   warp 2     : TMEM allocator
+//   warps 4-11 : epilogue       -- two warps per TMEM lane quarter, each owning half of the tile's
+//                                  columns; the accumulator is double buffered in TMEM so the next
+//                                  tile's MMAs overlap.  A single warp sustains only ~0.2 IPC on this
+//                                  dependent tcgen05.ld -> math -> pack -> store chain (ncu,
+//                                  profiles/), so the K=768 GEMMs need all eight to stay MMA-bound.
 // Tiles are walked n-fastest so the CTAs running concurrently share the A rows in L2; the
 // weights (<= 4.7 MB) stay L2-resident.
 #include <stdio.h>
@@ -30,6 +33,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+
+enum EpiMode {
+  EPI_F32 = 0,  // fp32 out: bias, QuickGELU
+  EPI_ACT = 1,  // act out: LayerNorm fold | bias, QuickGELU
+  EPI_RES = 2,  // act out: bias + act residual (+ row statistics)
+};
 
 template <int BN>
 struct Cfg {
@@ -38,9 +49,11 @@ struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kStgRowBytes = 128 + 16;              // 128 B of payload + 16 B bank skew
-  static constexpr int kStgBytes = 32 * kStgRowBytes;        // one 32-row strip per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 4 * kStgBytes + 1024;
+  static constexpr int kWarpCols = BN / 2;                  // columns owned by one epilogue warp
+  static constexpr int kStgBytes = 32 * 64;                 // 32 rows x 64 B, XOR-swizzled
+  static constexpr int kVecBytes = 2 * kWarpCols * 4;       // bias + colsum of the warp's columns
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kBarBytes + kEpiWarps * (kStgBytes + kVecBytes) + 1024;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -52,178 +65,183 @@ __device__ __forceinline__ float quick_gelu(float u) {
   return fmaf(h, t, h);
 }
 
-__device__ __forceinline__ void add_bias32(const float* __restrict__ bias, float (&v)[32]) {
-  const float4* b4 = reinterpret_cast<const float4*>(bias);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b = __ldg(b4 + j);
-    v[4 * j + 0] += b.x;
-    v[4 * j + 1] += b.y;
-    v[4 * j + 2] += b.z;
-    v[4 * j + 3] += b.w;
-  }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 
-// Epilogue of one warp on one 32-row strip of the accumulator.  Each thread owns a row in TMEM, but
-// a thread-per-row global access pattern touches half sectors 32 rows apart; instead every
-// 128-byte row segment goes through a per-warp shared-memory strip (144-byte row pitch:
-// conflict-free both ways) so that each global instruction moves 4 rows x 128 contiguous bytes.
-//
-// act_t output (the tower's hot epilogues), chunks of 64 columns:
-//   y = [LayerNorm fold] rstd_m * (acc - mean_m * s_n) + c_n   (W was pre-multiplied by gamma,
-//        s_n = sum_k W'[n,k], c_n = sum_k beta_k W[n,k] + b_n; mean/rstd from the row statistics
-//        the PRODUCER of the A rows accumulated) | acc + bias_n
-//   y = QuickGELU(y)                       (c_fc)
-//   y += residual (fp16, may alias out)    (out_proj, c_proj)
-//   out = fp16(y);  out_stats[m] += (sum y, sum y^2) over this tile's columns of the rounded y
-// fp32 output (patch embedding, final projection), chunks of 32 columns: bias / QuickGELU only.
+// Per-warp staging strip: 32 rows x 64 B.  16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3):
+// conflict-free both for "thread = row" accesses and for the coalesced phase in which one
+// instruction moves 8 rows x 64 contiguous bytes (lane -> row 8i + lane / 4, chunk lane % 4).
+__device__ __forceinline__ uint4* stg_chunk(uint8_t* stg, int row, int chunk) {
+  return reinterpret_cast<uint4*>(stg + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
 struct RowLn {
   float rstd, nmr;  // y = rstd * acc + nmr * s_n + c_n,  nmr = -mean * rstd
 };
 
-__device__ __forceinline__ void load_residual_chunk(uint4 (&res)[8], const GemmEpilogue& ep, int row0,
-                                                    int col0, int M, int sub_r, int sub_c) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = row0 + 4 * i + sub_r;
-    res[i] = make_uint4(0, 0, 0, 0);
-    if (r < M)
-      res[i] = *reinterpret_cast<const uint4*>(
-          reinterpret_cast<const uint8_t*>(ep.residual + static_cast<size_t>(r) * ep.ld_res + col0) + sub_c);
-  }
-}
-
-template <int BN>
-__device__ __forceinline__ void epilogue_strip_act(const GemmEpilogue& ep, uint32_t t_strip, uint8_t* stg,
-                                                   int row0, int col_base, int M, int lane, uint4 (&res)[8],
-                                                   const RowLn ln) {
-  constexpr int kPitch = Cfg<BN>::kStgRowBytes;
-  constexpr int NC = BN / 64;
-  uint8_t* my_row = stg + lane * kPitch;
-  const int sub_r = lane >> 3;        // coalesced phase: 4 rows per instruction ...
-  const int sub_c = (lane & 7) * 16;  // ... 8 lanes x 16 B per row
-  const bool has_res = ep.residual != nullptr;
+// act_t output.  One call = the warp's 32 rows x kWarpCols columns, in pieces of 32 columns:
+//   y = [fold] rstd_m * acc + (nmr_m * s_n + c_n)   |   acc + bias_n
+//   y = QuickGELU(y)                 (c_fc)
+//   y += residual (act_t, may alias out), statistics (sum y, sum y^2)   (out_proj, c_proj)
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_warp, uint8_t* stg,
+                                             const float* vec, int row0, int col_base, int M, int lane,
+                                             uint4 (&res)[4], const RowLn ln) {
+  constexpr int WC = Cfg<BN>::kWarpCols;
+  constexpr int NP = WC / 32;
+  const int sub_r = lane >> 2;  // coalesced phase: 8 rows per instruction, 4 lanes x 16 B per row
+  const int sub_c = lane & 3;
+  const bool fold = MODE == EPI_ACT && ep.colsum != nullptr;
+  const bool has_bias = ep.bias != nullptr;
+  const bool gelu = MODE == EPI_ACT && ep.act == 1;
   float sum = 0.f, sumsq = 0.f;
+  uint32_t r32[32];
+  tmem_ld_32x32(t_warp, r32);
 #pragma unroll 1
-  for (int c = 0; c < NC; ++c) {
-    const int col0 = col_base + c * 64;
-    if (has_res) {
+  for (int pc = 0; pc < NP; ++pc) {
+    const int col0 = col_base + pc * 32;
+    if (MODE == EPI_RES) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stg + (4 * i + sub_r) * kPitch + sub_c) = res[i];
-      if (c + 1 < NC) load_residual_chunk(res, ep, row0, col0 + 64, M, sub_r, sub_c);  // in flight below
+      for (int i = 0; i < 4; ++i) *stg_chunk(stg, 8 * i + sub_r, sub_c) = res[i];
+      if (pc + 1 < NP) {  // next piece's residual, in flight during the math below
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row0 + 8 * i + sub_r;
+          res[i] = make_uint4(0, 0, 0, 0);
+          if (r < M)
+            res[i] = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(r) * ep.ld_res + col0 + 32 +
+                                                     sub_c * 8);
+        }
+      }
       __syncwarp();
     }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t r32[32];
-      tmem_ld_32x32(t_strip + c * 64 + half * 32, r32);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
-      const int cc = col0 + half * 32;
-      if (ep.colsum != nullptr) {  // y = rstd * acc + (nmr * s_n + c_n)
-        const float4* s4 = reinterpret_cast<const float4*>(ep.colsum + cc);
-        const float4* c4 = reinterpret_cast<const float4*>(ep.bias + cc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 sv = __ldg(s4 + j);
-          const float4 cv = __ldg(c4 + j);
-          v[4 * j + 0] = fmaf(ln.rstd, v[4 * j + 0], fmaf(ln.nmr, sv.x, cv.x));
-          v[4 * j + 1] = fmaf(ln.rstd, v[4 * j + 1], fmaf(ln.nmr, sv.y, cv.y));
-          v[4 * j + 2] = fmaf(ln.rstd, v[4 * j + 2], fmaf(ln.nmr, sv.z, cv.z));
-          v[4 * j + 3] = fmaf(ln.rstd, v[4 * j + 3], fmaf(ln.nmr, sv.w, cv.w));
-        }
-      } else if (ep.bias != nullptr) {
-        add_bias32(ep.bias + cc, v);
-      }
-      if (ep.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-      }
-      uint4* seg = reinterpret_cast<uint4*>(my_row + half * 64);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (has_res) {
-          const uint4 rv = seg[j];
-          const float2 r0 = unpack2(rv.x), r1 = unpack2(rv.y), r2 = unpack2(rv.z), r3 = unpack2(rv.w);
-          v[8 * j + 0] += r0.x;
-          v[8 * j + 1] += r0.y;
-          v[8 * j + 2] += r1.x;
-          v[8 * j + 3] += r1.y;
-          v[8 * j + 4] += r2.x;
-          v[8 * j + 5] += r2.y;
-          v[8 * j + 6] += r3.x;
-          v[8 * j + 7] += r3.y;
-        }
-        uint4 u;
-        u.x = pack2(v[8 * j + 0], v[8 * j + 1]);
-        u.y = pack2(v[8 * j + 2], v[8 * j + 3]);
-        u.z = pack2(v[8 * j + 4], v[8 * j + 5]);
-        u.w = pack2(v[8 * j + 6], v[8 * j + 7]);
-        seg[j] = u;
-        if (ep.out_stats != nullptr) {  // statistics of the values as stored (rounded)
-          const float2 a = unpack2(u.x), b = unpack2(u.y), cdd = unpack2(u.z), d = unpack2(u.w);
-          sum += (a.x + a.y) + (b.x + b.y) + (cdd.x + cdd.y) + (d.x + d.y);
-          sumsq += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cdd.x * cdd.x + cdd.y * cdd.y + d.x * d.x + d.y * d.y;
-        }
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = 4 * i + sub_r;
-      if (row0 + r < M)
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(
-            static_cast<act_t*>(ep.out) + static_cast<size_t>(row0 + r) * ep.ldo + col0) + sub_c) =
-            *reinterpret_cast<const uint4*>(stg + r * kPitch + sub_c);
-    }
-    __syncwarp();
-  }
-  // One slot per 256-column block, summed in a fixed order by the consumer: deterministic (no atomics).
-  if (ep.out_stats != nullptr && row0 + lane < M)
-    ep.out_stats[static_cast<size_t>(row0 + lane) * kStatSlots + col_base / 256] = make_float2(sum, sumsq);
-}
-
-template <int BN>
-__device__ __forceinline__ void epilogue_strip_f32(const GemmEpilogue& ep, uint32_t t_strip, uint8_t* stg,
-                                                   int row0, int col_base, int M, int lane) {
-  constexpr int kPitch = Cfg<BN>::kStgRowBytes;
-  uint8_t* my_row = stg + lane * kPitch;
-  const int sub_r = lane >> 3;
-  const int sub_c = (lane & 7) * 16;
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    const int col0 = col_base + c * 32;
-    uint32_t r32[32];
-    tmem_ld_32x32(t_strip + c * 32, r32);
     tmem_ld_wait();
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
-    if (ep.bias != nullptr) add_bias32(ep.bias + col0, v);
-    if (ep.act == 1) {
+    if (pc + 1 < NP) tmem_ld_32x32(t_warp + (pc + 1) * 32, r32);  // next piece, in flight during the math
+    const float4* c4 = reinterpret_cast<const float4*>(vec + pc * 32);
+    const float4* s4 = reinterpret_cast<const float4*>(vec + WC + pc * 32);
+    if (fold) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 sv = s4[j];
+        const float4 cv = c4[j];
+        v[4 * j + 0] = fmaf(ln.rstd, v[4 * j + 0], fmaf(ln.nmr, sv.x, cv.x));
+        v[4 * j + 1] = fmaf(ln.rstd, v[4 * j + 1], fmaf(ln.nmr, sv.y, cv.y));
+        v[4 * j + 2] = fmaf(ln.rstd, v[4 * j + 2], fmaf(ln.nmr, sv.z, cv.z));
+        v[4 * j + 3] = fmaf(ln.rstd, v[4 * j + 3], fmaf(ln.nmr, sv.w, cv.w));
+      }
+    } else if (has_bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 cv = c4[j];
+        v[4 * j + 0] += cv.x;
+        v[4 * j + 1] += cv.y;
+        v[4 * j + 2] += cv.z;
+        v[4 * j + 3] += cv.w;
+      }
+    }
+    if (gelu) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(my_row + j * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < 4; ++j) {
+      uint4* slot = stg_chunk(stg, lane, j);
+      if (MODE == EPI_RES) {
+        const uint4 rv = *slot;
+        const float2 r0 = unpack2(rv.x), r1 = unpack2(rv.y), r2 = unpack2(rv.z), r3 = unpack2(rv.w);
+        v[8 * j + 0] += r0.x;
+        v[8 * j + 1] += r0.y;
+        v[8 * j + 2] += r1.x;
+        v[8 * j + 3] += r1.y;
+        v[8 * j + 4] += r2.x;
+        v[8 * j + 5] += r2.y;
+        v[8 * j + 6] += r3.x;
+        v[8 * j + 7] += r3.y;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sum += v[8 * j + e];
+          sumsq = fmaf(v[8 * j + e], v[8 * j + e], sumsq);
+        }
+      }
+      uint4 u;
+      u.x = pack2(v[8 * j + 0], v[8 * j + 1]);
+      u.y = pack2(v[8 * j + 2], v[8 * j + 3]);
+      u.z = pack2(v[8 * j + 4], v[8 * j + 5]);
+      u.w = pack2(v[8 * j + 6], v[8 * j + 7]);
+      *slot = u;
+    }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = 4 * i + sub_r;
-      if (row0 + r < M)
-        *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(
-            static_cast<float*>(ep.out) + static_cast<size_t>(row0 + r) * ep.ldo + col0) + sub_c) =
-            *reinterpret_cast<const float4*>(stg + r * kPitch + sub_c);
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + 8 * i + sub_r;
+      if (r < M)
+        *reinterpret_cast<uint4*>(static_cast<act_t*>(ep.out) + static_cast<size_t>(r) * ep.ldo + col0 + sub_c * 8) =
+            *stg_chunk(stg, 8 * i + sub_r, sub_c);
+    }
+    __syncwarp();
+  }
+  // One slot per 128-column block, summed in a fixed order by the consumer: deterministic, no
+  // atomics.  (Statistics of the fp32 values before the final rounding to act_t.)
+  if (MODE == EPI_RES && ep.out_stats != nullptr && row0 + lane < M)
+    ep.out_stats[static_cast<size_t>(row0 + lane) * kStatSlots + col_base / 128] = make_float2(sum, sumsq);
+}
+
+// fp32 output (patch embedding, final projection): bias / QuickGELU, pieces of 16 columns.
+template <int BN>
+__device__ __forceinline__ void epilogue_f32(const GemmEpilogue& ep, uint32_t t_warp, uint8_t* stg,
+                                             const float* vec, int row0, int col_base, int M, int lane) {
+  constexpr int WC = Cfg<BN>::kWarpCols;
+  const int sub_r = lane >> 2;
+  const int sub_c = lane & 3;
+#pragma unroll 1
+  for (int pc = 0; pc < WC / 16; ++pc) {
+    const int col0 = col_base + pc * 16;
+    uint32_t r16[16];
+    tmem_ld_32x16(t_warp + pc * 16, r16);
+    tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r16[j]);
+    if (ep.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += vec[pc * 16 + j];
+    }
+    if (ep.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = quick_gelu(v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(stg_chunk(stg, lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = row0 + 8 * i + sub_r;
+      if (r < M)
+        *reinterpret_cast<uint4*>(static_cast<float*>(ep.out) + static_cast<size_t>(r) * ep.ldo + col0 + sub_c * 4) =
+            *stg_chunk(stg, 8 * i + sub_r, sub_c);
     }
     __syncwarp();
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     int M, int N, int K, GemmEpilogue ep) {
   using C = Cfg<BN>;
@@ -239,6 +257,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint8_t* stg_base = smem + C::kStages * C::kStageBytes + C::kBarBytes;
+  uint8_t* vec_base = stg_base + kEpiWarps * C::kStgBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -258,7 +277,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -326,41 +345,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------------- epilogue
-    const int q = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int e = warp - 4;
+    const int q = e & 3;    // == warp % 4: the TMEM lane quarter this warp may read
+    const int ch = e >> 2;  // which half of the tile's columns
+    uint8_t* stg = stg_base + e * C::kStgBytes;
+    float* vec = reinterpret_cast<float*>(vec_base + e * C::kVecBytes);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n;
       const int n_blk = tile - m_blk * num_n;
       const int row0 = m_blk * BM + q * 32;
-      uint8_t* stg = stg_base + q * C::kStgBytes;
+      const int col_base = n_blk * BN + ch * C::kWarpCols;
       // Everything that does not depend on the accumulator is fetched before waiting for it.
-      uint4 res[8];
+      if (lane * 4 < C::kWarpCols) {
+        if (ep.bias != nullptr) cp_async16(vec + lane * 4, ep.bias + col_base + lane * 4);
+        if (MODE == EPI_ACT && ep.colsum != nullptr)
+          cp_async16(vec + C::kWarpCols + lane * 4, ep.colsum + col_base + lane * 4);
+      }
+      uint4 res[4];
       RowLn ln{1.f, 0.f};
-      if (!ep.out_f32) {
-        if (ep.residual != nullptr) load_residual_chunk(res, ep, row0, n_blk * BN, M, lane >> 3, (lane & 7) * 16);
-        if (ep.colsum != nullptr && row0 + lane < M) {
-          const float4* sp = reinterpret_cast<const float4*>(ep.ln_stats + static_cast<size_t>(row0 + lane) * kStatSlots);
-          const float4 s01 = sp[0], s23 = sp[1];
-          const float sx = ((s01.x + s01.z) + s23.x) + s23.z;
-          const float sxx = ((s01.y + s01.w) + s23.y) + s23.w;
-          const float inv_k = 1.0f / static_cast<float>(K);
-          const float mean = sx * inv_k;
-          const float var = fmaxf(sxx * inv_k - mean * mean, 0.f);
-          ln.rstd = rsqrtf(var + 1e-5f);
-          ln.nmr = -mean * ln.rstd;
+      if (MODE == EPI_RES) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row0 + 8 * i + (lane >> 2);
+          res[i] = make_uint4(0, 0, 0, 0);
+          if (r < M)
+            res[i] = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(r) * ep.ld_res + col_base +
+                                                     (lane & 3) * 8);
         }
+      }
+      if (MODE == EPI_ACT && ep.colsum != nullptr && row0 + lane < M) {
+        const float4* sp = reinterpret_cast<const float4*>(ep.ln_stats + static_cast<size_t>(row0 + lane) * kStatSlots);
+        float sx = 0.f, sxx = 0.f;
+#pragma unroll
+        for (int i = 0; i < kStatSlots / 2; ++i) {
+          const float4 t = sp[i];
+          sx += t.x;
+          sx += t.z;
+          sxx += t.y;
+          sxx += t.w;
+        }
+        const float inv_k = 1.0f / static_cast<float>(K);
+        const float mean = sx * inv_k;
+        const float var = fmaxf(sxx * inv_k - mean * mean, 0.f);
+        ln.rstd = rsqrtf(var + 1e-5f);
+        ln.nmr = -mean * ln.rstd;
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_strip =
-          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      if (ep.out_f32)
-        epilogue_strip_f32<BN>(ep, t_strip, stg, row0, n_blk * BN, M, lane);
-      else
-        epilogue_strip_act<BN>(ep, t_strip, stg, row0, n_blk * BN, M, lane, res, ln);
-      tc_fence_before();
+      cp_async_wait_all();
       __syncwarp();
+      const uint32_t t_warp = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                              static_cast<uint32_t>(acc * BN + ch * C::kWarpCols);
+      if (MODE == EPI_F32)
+        epilogue_f32<BN>(ep, t_warp, stg, vec, row0, col_base, M, lane);
+      else
+        epilogue_act<BN, MODE>(ep, t_warp, stg, vec, row0, col_base, M, lane, res, ln);
+      tc_fence_before();
+      __syncwarp();  // every lane is done with TMEM and with `vec` before they are handed back
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) {
         acc = 0;
@@ -423,6 +466,31 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+template <int BN, int MODE>
+cudaError_t launch_gemm_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N,
+                             int K, const GemmEpilogue& ep, int num_sms) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_tcgen05_kernel<BN, MODE><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmW, M, N, K, ep);
+  return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t launch_gemm_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N, int K,
+                           const GemmEpilogue& ep, int num_sms) {
+  if (ep.out_f32) return launch_gemm_inst<BN, EPI_F32>(st, tmA, tmW, M, N, K, ep, num_sms);
+  if (ep.residual != nullptr) return launch_gemm_inst<BN, EPI_RES>(st, tmA, tmW, M, N, K, ep, num_sms);
+  return launch_gemm_inst<BN, EPI_ACT>(st, tmA, tmW, M, N, K, ep, num_sms);
+}
+
 }  // namespace
 
 int make_tmap_act_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
@@ -446,27 +514,15 @@ int make_tmap_act_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 
-template <int BN>
-static cudaError_t launch_gemm_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW,
-                                  int M, int N, int K, const GemmEpilogue& ep, int num_sms) {
-  using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  const int tiles = ((M + BM - 1) / BM) * (N / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tcgen05_kernel<BN><<<grid, 256, C::kSmemBytes, st>>>(tmA, tmW, M, N, K, ep);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N,
                         int K, const GemmEpilogue& ep, int num_sms) {
   if (M <= 0) return cudaSuccess;
   if (N % 128 != 0 || K % BK != 0) return cudaErrorInvalidValue;
+  // combinations the epilogue modes do not implement
+  if (ep.out_f32 && (ep.colsum || ep.residual || ep.out_stats)) return cudaErrorInvalidValue;
+  if (ep.colsum && (!ep.ln_stats || !ep.bias || ep.residual)) return cudaErrorInvalidValue;
+  if (ep.residual && ep.act != 0) return cudaErrorInvalidValue;
+  if (ep.out_stats && (!ep.residual || N % 256 != 0 || N > 128 * kStatSlots)) return cudaErrorInvalidValue;
   if (gemm_block_n(N) == 256) return launch_gemm_bn<256>(st, tmA, tmW, M, N, K, ep, num_sms);
   return launch_gemm_bn<128>(st, tmA, tmW, M, N, K, ep, num_sms);
 }

@@ -7,16 +7,16 @@ namespace oake {
 
 // ---------------------------------------------------------------- gemm.cu
 // Row statistics travel as kStatSlots partial (sum, sum of squares) pairs per row: the producing
-// GEMM writes slot n_blk (one per 256 output columns, N <= 1024), the consumer adds the slots in
-// a fixed order -- deterministic, no atomics, no memset (unused slots must hold zeros).
-constexpr int kStatSlots = 4;
+// GEMM writes one slot per 128 output columns (N <= 1024), the consumer adds the slots in a fixed
+// order -- deterministic, no atomics (unused slots must hold zeros).
+constexpr int kStatSlots = 8;
 
 struct GemmEpilogue {
   const float* bias;        // [N] fp32 (plain bias, or the folded c_n; required with colsum) or nullptr
   const float* colsum;      // [N] fp32 s_n = sum_k W'[n,k]: enables the LayerNorm fold, or nullptr
   const float2* ln_stats;   // [M][kStatSlots] statistics of the A rows over K; required with colsum
   const act_t* residual;    // act_t [M, ld_res] added after the activation (act_t output only)
-  float2* out_stats;        // [M][kStatSlots] statistics of the stored rows (N % 256 == 0), or nullptr
+  float2* out_stats;        // [M][kStatSlots] statistics of the output rows (needs residual, N % 256 == 0), or nullptr
   void* out;                // act_t or fp32 [M, ldo]; may alias `residual`
   int ldo;
   int ld_res;

@@ -94,14 +94,15 @@ def test_gemm_epilogues(lib):
     b2 = torch.randn(768, device=DEV, generator=g) * 0.1
     x = (torch.randn(M, 768, device=DEV, generator=g) * 2).to(act_dtype())
     ref2 = ref_gemm(H, W2, b2, 0, x.clone())
-    stats = torch.zeros(M, 4, 2, device=DEV)
+    stats = torch.zeros(M, 8, 2, device=DEV)
     out2 = run_gemm(lib, H, W2, bias=b2, residual=x, out_stats=stats, inplace=True)
     assert out2.data_ptr() == x.data_ptr()
     assert (out2.float() - ref2).abs().max() < act_tol(8)
-    assert (stats[:, 3] == 0).all()  # 768 columns fill slots 0..2 only
-    assert torch.allclose(stats[..., 0].sum(1), out2.float().sum(-1), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(stats[..., 1].sum(1), (out2.float()**2).sum(-1), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(stats[:, 1, 0], out2.float()[:, 256:512].sum(-1), rtol=1e-4, atol=1e-2)
+    assert (stats[:, 6:] == 0).all()  # 768 columns fill slots 0..5 only
+    # statistics are taken on the fp32 values just before the rounding to the activation type
+    assert torch.allclose(stats[..., 0].sum(1), ref2.sum(-1), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(stats[..., 1].sum(1), (ref2**2).sum(-1), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(stats[:, 3, 0], ref2[:, 384:512].sum(-1), rtol=1e-3, atol=5e-2)
     # the CUDA-core reference of the same contract agrees
     x2 = (torch.randn(M, 768, device=DEV, generator=g) * 2).to(act_dtype())
     a = run_gemm(lib, H, W2, bias=b2, residual=x2, impl=0)
@@ -122,10 +123,10 @@ def test_gemm_layernorm_fold(lib):
     Wf, s, c = fold_layernorm(W.cpu(), b.cpu(), gamma.cpu(), beta.cpu(), act_dtype())
     Wf, s, c = Wf.to(DEV), s.to(DEV), c.to(DEV)
     xf = x.float()
-    stats = torch.zeros(M, 4, 2, device=DEV)
-    for j in range(3):  # partial statistics, as the producing GEMM leaves them
-        stats[:, j, 0] = xf[:, 256 * j:256 * j + 256].sum(-1)
-        stats[:, j, 1] = (xf[:, 256 * j:256 * j + 256]**2).sum(-1)
+    stats = torch.zeros(M, 8, 2, device=DEV)
+    for j in range(6):  # partial statistics, as the producing GEMM leaves them
+        stats[:, j, 0] = xf[:, 128 * j:128 * j + 128].sum(-1)
+        stats[:, j, 1] = (xf[:, 128 * j:128 * j + 128]**2).sum(-1)
     out = run_gemm(lib, x, Wf, bias=c, colsum=s, ln_stats=stats, out_f32=False)
     ref = F.layer_norm(xf, (K, ), gamma, beta, 1e-5) @ W.T + b
     assert (out.float() - ref).abs().max() < act_tol(6) + 6e-3, (out.float() - ref).abs().max()
