@@ -99,6 +99,50 @@ int oake_workspace_bytes(const oake_handle* h, int max_crops, int variant, size_
 int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, const float* masks,
                        void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- GPU front end: the work the reference does in DataLoader workers with PIL -------------- */
+
+/* One crop-and-resize: Pillow `image.crop(box).resize((out_w, out_h), BICUBIC)` restricted to the
+ * window [win_x, win_x+win_w) x [win_y, win_y+win_h) of the resized image (torchvision CenterCrop),
+ * bit-exact on uint8.  Stands where the reference calls PIL through torchvision
+ * Resize(224, BICUBIC) + CenterCrop(224) (oadp/oake/globals.py:32, blocks.py:80-81,95,
+ * objects.py:116-127) and `image.resize((int(w/1.5), int(h/1.5)))` (blocks.py:73-77).
+ * Images are uint8 HWC, 3 channels.  The rectangle may leave the image: outside reads 0, like
+ * PIL's crop.  Limits: box_w/out_w and box_h/out_h <= 11 (oake_resize_u8 reports an error above). */
+typedef struct {
+  int64_t src_off;      /* byte offset of the source image inside the source arena */
+  int64_t dst_off;      /* byte offset of the output window inside the destination arena */
+  int32_t src_w, src_h; /* source image size, pixels */
+  int32_t src_pitch_px; /* source row pitch, pixels */
+  int32_t box_x0, box_y0, box_w, box_h; /* crop rectangle in source pixels (after PIL's rounding) */
+  int32_t out_w, out_h; /* size the crop is resized to */
+  int32_t win_x, win_y, win_w, win_h; /* window of the resized crop that is written */
+  int32_t dst_pitch_px; /* destination row pitch, pixels */
+} oake_resize_job;
+
+/* jobs: DEVICE array.  max_tiles = max over jobs of ceil(win_w/32)*ceil(win_h/32).  err_flag: device
+ * int, set to 1 if a job exceeded the kernel's limits (caller clears and checks it). */
+int oake_resize_u8(const uint8_t* src_arena, uint8_t* dst_arena, const oake_resize_job* jobs, int n_jobs,
+                   int max_tiles, int* err_flag, void* stream);
+
+/* Where a 224x224 uint8 HWC crop lives: arena + off, rows pitch_px pixels apart.  Block crops of
+ * oadp/oake/blocks.py:79-81 need no copy at all: they are windows into the pyramid level. */
+typedef struct {
+  int64_t off;
+  int32_t pitch_px;
+  int32_t reserved;
+} oake_crop_src;
+
+/* oake_encode_pixels for crops that are still uint8: ToTensor + Normalize (CLIP mean/std, exact
+ * fp32 table) are fused into the patch gather.  crops: DEVICE array of B entries. */
+int oake_encode_crops_u8(oake_handle* h, const uint8_t* arena, const oake_crop_src* crops, int B, int variant,
+                         const float* masks, void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes,
+                         void* stream);
+
+/* The 14x14 foreground masks of oadp/oake/objects.py:129-155 for B crops.  box_xyxy: the expanded
+ * squares (float, before PIL's rounding), fg_xyxy: proposal - box.lt; masks: fp32 [B,1,14,14], 1 =
+ * background.  All device pointers. */
+int oake_object_masks(const float* fg_xyxy, const float* box_xyxy, int B, float* masks, void* stream);
+
 /* Error string of the last failing call on this thread ("" if none). */
 const char* oake_last_error(void);
 /* "f16" or "bf16": element type of `act` tensors. */

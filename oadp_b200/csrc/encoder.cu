@@ -81,6 +81,7 @@ struct oake_handle {
   std::vector<oake_layer_weights> layers;
   CUtensorMap tm_conv1, tm_proj;
   std::vector<LayerMaps> tm_layer;
+  act_t* pixel_lut;  // [3*256] ToTensor + Normalize of every byte value, rounded to act_t
   long long launches;
   bool profiling;
   std::vector<ProfEvent> events;
@@ -198,6 +199,7 @@ int oake_create(oake_handle** out, int device, const oake_weights* weights) {
   h->w = *weights;
   h->layers.assign(weights->layer, weights->layer + weights->layers);
   h->w.layer = h->layers.data();
+  h->pixel_lut = nullptr;
   h->launches = 0;
   h->profiling = false;
   memset(h->acc_ms, 0, sizeof(h->acc_ms));
@@ -224,6 +226,29 @@ int oake_create(oake_handle** out, int device, const oake_weights* weights) {
     delete h;
     return fail("cuTensorMapEncodeTiled failed for a weight tensor (rc=%d)", rc);
   }
+  {
+    // torchvision ToTensor (v / 255) then Normalize ((t - mean) / std), all in fp32 like the
+    // reference's transform (clip `_transform`), then the one rounding to the tensor-core type.
+    const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+    const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+    std::vector<act_t> lut(768);
+    for (int c = 0; c < 3; ++c)
+      for (int v = 0; v < 256; ++v) {
+        const float t = static_cast<float>(v) / 255.0f;
+        const float n = (t - mean[c]) / stdv[c];
+#ifdef OAKE_USE_BF16
+        lut[c * 256 + v] = __float2bfloat16_rn(n);
+#else
+        lut[c * 256 + v] = __float2half_rn(n);
+#endif
+      }
+    e = cudaMalloc(&h->pixel_lut, 768 * sizeof(act_t));
+    if (e == cudaSuccess) e = cudaMemcpy(h->pixel_lut, lut.data(), 768 * sizeof(act_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      delete h;
+      return fail("pixel table upload: %s", cudaGetErrorString(e));
+    }
+  }
   *out = h;
   return 0;
 }
@@ -235,6 +260,7 @@ void oake_destroy(oake_handle* h) {
     cudaEventDestroy(pe.b);
   }
   for (auto e : h->pool) cudaEventDestroy(e);
+  if (h->pixel_lut) cudaFree(h->pixel_lut);
   delete h;
 }
 
@@ -246,13 +272,19 @@ int oake_workspace_bytes(const oake_handle* h, int max_crops, int variant, size_
   return 0;
 }
 
-int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, const float* masks,
-                       void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes, void* stream) {
+}  // extern "C"
+
+namespace {
+
+// The tower.  Exactly one of `pixels` (fp32 NCHW crops) or (`arena`, `crops`) (uint8 crops) is given.
+int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const oake_crop_src* crops, int B,
+                int variant, const float* masks, void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes,
+                void* stream) {
   if (!h) return fail("handle is NULL");
   if (variant != OAKE_VARIANT_T50 && variant != OAKE_VARIANT_T197) return fail("bad variant %d", variant);
   if (B < 0) return fail("B < 0");
   if (B == 0) return 0;
-  if (!pixels || !out_f16 || !ws) return fail("NULL buffer");
+  if ((!pixels && !(arena && crops)) || !out_f16 || !ws) return fail("NULL buffer");
   const bool side = variant == OAKE_VARIANT_T197;
   if (side && !masks) return fail("variant T197 needs masks");
   if (side && !h->w.pos_t197) return fail("handle was created without pos_t197");
@@ -296,7 +328,9 @@ int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, 
 
   // K0/K1: crops -> conv1 patch matrix -> patch embedding -> tokens + ln_pre (+ row statistics)
   go.run(K_FRONTEND, 0, [&] {
-    return launch_im2col_pixels(st, pixels, patches, B, side ? 16 : 32, side ? 15 : 0, side ? 14 : 7);
+    if (pixels) return launch_im2col_pixels(st, pixels, patches, B, side ? 16 : 32, side ? 15 : 0, side ? 14 : 7);
+    return launch_im2col_u8(st, arena, crops, h->pixel_lut, patches, B, side ? 16 : 32, side ? 15 : 0,
+                            side ? 14 : 7);
   });
   {
     GemmEpilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, patch_out, W, 0, 1, 0};
@@ -355,6 +389,44 @@ int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, 
 
   if (go.err != cudaSuccess)
     return fail("launch of %s failed: %s", go.where[0] ? go.where : "memset", cudaGetErrorString(go.err));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oake_encode_pixels(oake_handle* h, const float* pixels, int B, int variant, const float* masks,
+                       void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes, void* stream) {
+  if (B > 0 && !pixels) return fail("pixels is NULL");
+  return encode_impl(h, pixels, nullptr, nullptr, B, variant, masks, out_f16, out_raw_f32, ws, ws_bytes, stream);
+}
+
+int oake_encode_crops_u8(oake_handle* h, const uint8_t* arena, const oake_crop_src* crops, int B, int variant,
+                         const float* masks, void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes,
+                         void* stream) {
+  if (B > 0 && (!arena || !crops)) return fail("arena / crops is NULL");
+  return encode_impl(h, nullptr, arena, crops, B, variant, masks, out_f16, out_raw_f32, ws, ws_bytes, stream);
+}
+
+int oake_resize_u8(const uint8_t* src_arena, uint8_t* dst_arena, const oake_resize_job* jobs, int n_jobs,
+                   int max_tiles, int* err_flag, void* stream) {
+  if (n_jobs < 0 || max_tiles < 0) return fail("negative count");
+  if (n_jobs == 0) return 0;
+  if (!src_arena || !dst_arena || !jobs || !err_flag) return fail("NULL buffer");
+  if (max_tiles > 65535 * 16) return fail("max_tiles too large");
+  cudaError_t e = launch_resize_u8(static_cast<cudaStream_t>(stream), src_arena, dst_arena, jobs, n_jobs, max_tiles,
+                                   err_flag);
+  if (e != cudaSuccess) return fail("resize_u8 launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int oake_object_masks(const float* fg_xyxy, const float* box_xyxy, int B, float* masks, void* stream) {
+  if (B < 0) return fail("B < 0");
+  if (B == 0) return 0;
+  if (!fg_xyxy || !box_xyxy || !masks) return fail("NULL buffer");
+  cudaError_t e = launch_object_masks(static_cast<cudaStream_t>(stream), fg_xyxy, box_xyxy, masks, B, 14);
+  if (e != cudaSuccess) return fail("object_masks launch: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -1,10 +1,19 @@
-// Front end of the OAKE tower: turns crops into the conv1 patch matrix (im2col) that the tcgen05
-// GEMM consumes.
+// Front end of the OAKE tower: turns images + crop rectangles into the conv1
+// patch matrix the tcgen05 GEMM consumes, entirely on the GPU.
 //
-//  * im2col_pixels: (B,3,224,224) fp32 CLIP-normalised crops, the tensor the reference feeds to
-//    `model.encode_image` / `model.visual` (oadp/oake/globals.py:54-57, blocks.py:126-129,
-//    objects.py:319-330) -> act_t [B*P, 3072].  stride 32 / pad 0 (P = 49) is CLIP's conv1;
-//    stride 16 / pad 15 (P = 196) is the objects surgery of objects.py:299-301.
+//  * resize_u8: Pillow's antialiased separable bicubic (`Image.crop(box).resize(size, BICUBIC)`,
+//    libImaging/Resample.c: double-precision coefficients, 22-bit fixed point, horizontal pass then
+//    vertical pass with a uint8 intermediate), bit-exact on uint8.  It stands where the reference's
+//    DataLoader workers call PIL through torchvision `Resize(224, BICUBIC)` + `CenterCrop(224)`
+//    (clip `_transform`; oadp/oake/globals.py:32, blocks.py:73-81,95, objects.py:116-127), and the
+//    pyramid `image.resize((int(w / 1.5), int(h / 1.5)))` of blocks.py:73-77.
+//  * im2col_u8: uint8 224x224 crops (anywhere in a byte arena) -> ToTensor + Normalize (exact fp32
+//    table) -> act_t [B*P, 3072] patch rows, column order (c, ky, kx).  stride 32 / pad 0 (P = 49)
+//    is CLIP's conv1; stride 16 / pad 15 (P = 196) is the objects surgery of objects.py:299-301.
+//  * im2col_pixels: the same patch matrix from (B,3,224,224) fp32 crops that were preprocessed on
+//    the host, i.e. the tensor the reference hands to `encode_image` / `visual`.
+//  * object_masks: the 14x14 foreground masks of objects.py:129-155.
+#include "../../include/oake_b200.h"
 #include "kernels.cuh"
 
 namespace oake {
@@ -16,6 +25,9 @@ constexpr int kPatch = 32;
 constexpr int kCols = 3 * kPatch * kPatch;  // 3072
 constexpr int kChunks = kCols / 8;          // 16-byte output chunks per patch row
 
+// ------------------------------------------------------------------------------------------------
+// im2col from fp32 NCHW crops
+// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 im2col_pixels_kernel(const float* __restrict__ pixels, act_t* __restrict__ patches, long long total,
                      int stride, int pad, int grid) {
@@ -52,6 +64,237 @@ im2col_pixels_kernel(const float* __restrict__ pixels, act_t* __restrict__ patch
   *reinterpret_cast<uint4*>(patches + prow * kCols + chunk * 8) = u;
 }
 
+// ------------------------------------------------------------------------------------------------
+// im2col from uint8 HWC crops + ToTensor/Normalize table
+// ------------------------------------------------------------------------------------------------
+// One thread = 8 consecutive kx of one (crop, patch, ky) for all three channels: reads 24
+// contiguous bytes, writes three 16-byte chunks.  lut[c * 256 + v] = act_t((v / 255 - mean_c) / std_c);
+// padded (out-of-crop) pixels are exact zeros, as conv2d's zero padding acts AFTER Normalize.
+__global__ void __launch_bounds__(256)
+im2col_u8_kernel(const uint8_t* __restrict__ arena, const oake_crop_src* __restrict__ crops,
+                 const act_t* __restrict__ lut, act_t* __restrict__ patches, long long total, int stride,
+                 int pad, int grid) {
+  __shared__ act_t s_lut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int per_row = kPatch * kPatch / 8;  // (ky, kx0) pairs per patch
+  const int sub = static_cast<int>(idx % per_row);
+  const long long prow = idx / per_row;
+  const int P = grid * grid;
+  const int b = static_cast<int>(prow / P);
+  const int g = static_cast<int>(prow - static_cast<long long>(b) * P);
+  const int gy = g / grid, gx = g - gy * grid;
+  const int ky = sub / (kPatch / 8);
+  const int kx0 = (sub - ky * (kPatch / 8)) * 8;
+  const int y = gy * stride - pad + ky;
+  const int x0 = gx * stride - pad + kx0;
+  const oake_crop_src cs = crops[b];
+  uint32_t out[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[c][j] = 0u;
+  if (y >= 0 && y < kImg) {
+    const uint8_t* src = arena + cs.off + (static_cast<long long>(y) * cs.pitch_px + x0) * 3;
+    unsigned short h[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int x = x0 + j;
+      const bool ok = x >= 0 && x < kImg;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        act_t val = to_act(0.f);
+        if (ok) val = s_lut[c * 256 + src[j * 3 + c]];
+        h[c][j] = *reinterpret_cast<unsigned short*>(&val);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        out[c][j] = static_cast<uint32_t>(h[c][2 * j]) | (static_cast<uint32_t>(h[c][2 * j + 1]) << 16);
+  }
+  act_t* dst = patches + prow * kCols + ky * kPatch + kx0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    *reinterpret_cast<uint4*>(dst + c * kPatch * kPatch) = make_uint4(out[c][0], out[c][1], out[c][2], out[c][3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pillow-exact antialiased bicubic resize of a crop rectangle, uint8 HWC
+// ------------------------------------------------------------------------------------------------
+constexpr int kTile = 32;       // output tile (pixels)
+constexpr int kMaxTaps = 48;    // filter taps per output sample: scale factors up to ~11.5
+constexpr int kMaxRows = 448;   // intermediate rows per tile kept in shared memory
+constexpr int kPrecBits = 32 - 8 - 2;
+
+// libImaging bicubic_filter, a = -0.5, evaluated with explicit roundings (no FMA contraction).
+__device__ __forceinline__ double pil_bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) {
+    const double t = __dadd_rn(__dmul_rn(a + 2.0, x), -(a + 3.0));
+    return __dadd_rn(__dmul_rn(__dmul_rn(t, x), x), 1.0);
+  }
+  if (x < 2.0) {
+    double t = __dmul_rn(__dadd_rn(x, -5.0), x);
+    t = __dmul_rn(__dadd_rn(t, 8.0), x);
+    return __dmul_rn(__dadd_rn(t, -4.0), a);
+  }
+  return 0.0;
+}
+
+// libImaging precompute_coeffs + normalize_coeffs_8bpc for ONE output sample `xx`.
+// Writes taps to k[0..*count) and the first source index to *first.
+__device__ void pil_coeffs(int in_size, int out_size, int xx, int* first, int* count, int* k) {
+  const double scale = static_cast<double>(in_size) / static_cast<double>(out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = __dmul_rn(2.0, filterscale);
+  const double center = __dmul_rn(static_cast<double>(xx) + 0.5, scale);
+  const double ss = 1.0 / filterscale;
+  int xmin = static_cast<int>(__dadd_rn(__dadd_rn(center, -support), 0.5));
+  if (xmin < 0) xmin = 0;
+  int xmax = static_cast<int>(__dadd_rn(__dadd_rn(center, support), 0.5));
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  if (xmax > kMaxTaps) xmax = kMaxTaps;  // guarded by the host-side scale check
+  double w[kMaxTaps];
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) {
+    const double arg = __dmul_rn(__dadd_rn(__dadd_rn(static_cast<double>(x + xmin), -center), 0.5), ss);
+    w[x] = pil_bicubic(arg);
+    ww = __dadd_rn(ww, w[x]);
+  }
+  for (int x = 0; x < xmax; ++x) {
+    double v = w[x];
+    if (ww != 0.0) v = __ddiv_rn(v, ww);
+    const double f = __dmul_rn(v, static_cast<double>(1 << kPrecBits));
+    k[x] = v < 0.0 ? static_cast<int>(__dadd_rn(-0.5, f)) : static_cast<int>(__dadd_rn(0.5, f));
+  }
+  *first = xmin;
+  *count = xmax;
+}
+
+__device__ __forceinline__ uint8_t pil_clip8(int ss) {
+  const int v = ss >> kPrecBits;
+  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+struct ResizeSmem {
+  int kh[kTile][kMaxTaps];
+  int kv[kTile][kMaxTaps];
+  int h_first[kTile], h_count[kTile], v_first[kTile], v_count[kTile];
+  int r_lo, r_hi;
+  uint8_t tmp[kMaxRows][kTile][3];
+};
+
+__global__ void __launch_bounds__(256)
+resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ dst_arena,
+                 const oake_resize_job* __restrict__ jobs, int* __restrict__ err) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  ResizeSmem& sm = *reinterpret_cast<ResizeSmem*>(smem_raw);
+  const oake_resize_job job = jobs[blockIdx.y];
+  const int tiles_x = (job.win_w + kTile - 1) / kTile;
+  const int tiles_y = (job.win_h + kTile - 1) / kTile;
+  if (static_cast<int>(blockIdx.x) >= tiles_x * tiles_y) return;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int ox0 = job.win_x + tx * kTile, oy0 = job.win_y + ty * kTile;
+  const int tw = min(kTile, job.win_x + job.win_w - ox0);
+  const int th = min(kTile, job.win_y + job.win_h - oy0);
+  const int tid = threadIdx.x;
+
+  if (tid < kTile) {
+    if (tid < tw) pil_coeffs(job.box_w, job.out_w, ox0 + tid, &sm.h_first[tid], &sm.h_count[tid], sm.kh[tid]);
+  } else if (tid < 2 * kTile) {
+    const int r = tid - kTile;
+    if (r < th) pil_coeffs(job.box_h, job.out_h, oy0 + r, &sm.v_first[r], &sm.v_count[r], sm.kv[r]);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int lo = sm.v_first[0], hi = 0;
+    for (int r = 0; r < th; ++r) hi = max(hi, sm.v_first[r] + sm.v_count[r]);
+    sm.r_lo = lo;
+    sm.r_hi = hi;
+    if (hi - lo > kMaxRows) atomicExch(err, 1);
+  }
+  __syncthreads();
+  const int r_lo = sm.r_lo;
+  const int nr = min(sm.r_hi - r_lo, kMaxRows);
+  const uint8_t* src = src_arena + job.src_off;
+
+  // horizontal pass: crop rows [r_lo, r_lo + nr) -> tmp (uint8, like Pillow's intermediate image)
+  const int row_elems = tw * 3;
+  for (int idx = tid; idx < nr * row_elems; idx += blockDim.x) {
+    const int r = idx / row_elems;
+    const int rem = idx - r * row_elems;
+    const int j = rem / 3, c = rem - j * 3;
+    const int y = job.box_y0 + r_lo + r;
+    int ss = 1 << (kPrecBits - 1);
+    if (y >= 0 && y < job.src_h) {
+      const uint8_t* line = src + static_cast<long long>(y) * job.src_pitch_px * 3;
+      const int first = job.box_x0 + sm.h_first[j];
+      const int n = sm.h_count[j];
+      const int* k = sm.kh[j];
+      for (int t = 0; t < n; ++t) {
+        const int x = first + t;
+        if (x >= 0 && x < job.src_w) ss += static_cast<int>(line[x * 3 + c]) * k[t];
+      }
+    }
+    sm.tmp[r][j][c] = pil_clip8(ss);
+  }
+  __syncthreads();
+
+  // vertical pass
+  uint8_t* dst = dst_arena + job.dst_off;
+  for (int idx = tid; idx < th * row_elems; idx += blockDim.x) {
+    const int r = idx / row_elems;
+    const int rem = idx - r * row_elems;
+    const int j = rem / 3, c = rem - j * 3;
+    const int first = sm.v_first[r] - r_lo;
+    const int n = sm.v_count[r];
+    const int* k = sm.kv[r];
+    int ss = 1 << (kPrecBits - 1);
+    for (int t = 0; t < n; ++t) {
+      const int rr = first + t;
+      if (rr < nr) ss += static_cast<int>(sm.tmp[rr][j][c]) * k[t];
+    }
+    const int oy = oy0 - job.win_y + r, ox = ox0 - job.win_x + j;
+    dst[(static_cast<long long>(oy) * job.dst_pitch_px + ox) * 3 + c] = pil_clip8(ss);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// objects.py:129-155 masks.  box = the expanded square (float xyxy), fg = proposal - box.lt.
+// x = arange(x2 - x1) (ceil(double width) float samples), inside iff fg0 <= x <= fg2; the bool mask
+// is resampled to 14x14 by F.interpolate(mode='nearest'): src = min(floor(dst * (n / 14.f)), n - 1).
+// Output 1 = background.
+// ------------------------------------------------------------------------------------------------
+__global__ void object_masks_kernel(const float* __restrict__ fg, const float* __restrict__ box,
+                                    float* __restrict__ masks, int B, int grid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * grid * grid) return;
+  const int b = idx / (grid * grid);
+  const int cell = idx - b * grid * grid;
+  const int gy = cell / grid, gx = cell - gy * grid;
+  const float* bb = box + b * 4;
+  const float* f = fg + b * 4;
+  const int nx = static_cast<int>(ceil(static_cast<double>(bb[2]) - static_cast<double>(bb[0])));
+  const int ny = static_cast<int>(ceil(static_cast<double>(bb[3]) - static_cast<double>(bb[1])));
+  float bg = 1.f;
+  if (nx > 0 && ny > 0) {
+    const float sx = static_cast<float>(nx) / static_cast<float>(grid);
+    const float sy = static_cast<float>(ny) / static_cast<float>(grid);
+    const int ix = min(static_cast<int>(floorf(gx * sx)), nx - 1);
+    const int iy = min(static_cast<int>(floorf(gy * sy)), ny - 1);
+    const float x = static_cast<float>(ix), y = static_cast<float>(iy);
+    const bool inside = (f[0] <= x) && (x <= f[2]) && (f[1] <= y) && (y <= f[3]);
+    bg = inside ? 0.f : 1.f;
+  }
+  masks[idx] = bg;
+}
+
 }  // namespace
 
 cudaError_t launch_im2col_pixels(cudaStream_t st, const float* pixels, act_t* patches, int B,
@@ -63,5 +306,40 @@ cudaError_t launch_im2col_pixels(cudaStream_t st, const float* pixels, act_t* pa
                                                                       pad, grid);
   return cudaGetLastError();
 }
+
+cudaError_t launch_im2col_u8(cudaStream_t st, const uint8_t* arena, const oake_crop_src* crops,
+                             const act_t* lut, act_t* patches, int B, int stride, int pad, int grid) {
+  if (B <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(B) * grid * grid * (kPatch * kPatch / 8);
+  const long long blocks = (total + 255) / 256;
+  im2col_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(arena, crops, lut, patches, total, stride, pad,
+                                                                  grid);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs,
+                             int n_jobs, int max_tiles, int* err_flag) {
+  if (n_jobs <= 0 || max_tiles <= 0) return cudaSuccess;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(resize_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sizeof(ResizeSmem)));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(max_tiles, n_jobs);
+  resize_u8_kernel<<<grid, 256, sizeof(ResizeSmem), st>>>(src, dst, jobs, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_object_masks(cudaStream_t st, const float* fg, const float* box, float* masks, int B,
+                                int grid) {
+  if (B <= 0) return cudaSuccess;
+  const int total = B * grid * grid;
+  object_masks_kernel<<<(total + 255) / 256, 256, 0, st>>>(fg, box, masks, B, grid);
+  return cudaGetLastError();
+}
+
+int resize_max_taps() { return kMaxTaps; }
 
 }  // namespace oake

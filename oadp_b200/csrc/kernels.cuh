@@ -1,6 +1,7 @@
 // Internal launcher declarations shared by the OAKE translation units.
 #pragma once
 
+#include "../../include/oake_b200.h"
 #include "common.cuh"
 
 namespace oake {
@@ -66,5 +67,15 @@ cudaError_t launch_attention_side(cudaStream_t st, const act_t* qkv, const float
 // column order (c, ky, kx).  stride 32 / pad 0 (P=49) or stride 16 / pad 15 (P=196).
 cudaError_t launch_im2col_pixels(cudaStream_t st, const float* pixels, act_t* patches, int B,
                                  int stride, int pad, int grid);
+// Same patch matrix from uint8 HWC 224x224 crops living anywhere in `arena`; lut[c*256+v] is the
+// ToTensor+Normalize value of byte v in channel c, already rounded to act_t.
+cudaError_t launch_im2col_u8(cudaStream_t st, const uint8_t* arena, const oake_crop_src* crops,
+                             const act_t* lut, act_t* patches, int B, int stride, int pad, int grid);
+// Pillow-exact crop + antialiased bicubic resize, one job per (source rectangle -> output window).
+cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs,
+                             int n_jobs, int max_tiles, int* err_flag);
+cudaError_t launch_object_masks(cudaStream_t st, const float* fg, const float* box, float* masks, int B,
+                                int grid);
+int resize_max_taps();
 
 }  // namespace oake

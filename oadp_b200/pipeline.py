@@ -1,0 +1,285 @@
+"""Image-level OAKE pipeline: uint8 images (+ proposals) in, the tensors the reference stores out.
+
+This is the public API the `oadp.oake.*` validators and `bench.py` call.  Per batch of images it
+  1. copies the raw uint8 images and a few KB of job descriptors to the GPU (one pinned staging
+     buffer each, async H2D),
+  2. runs the Pillow-exact resize kernel for every crop / pyramid level (`oake_resize_u8`),
+  3. runs the tower on the uint8 crops in SM-friendly chunks (`oake_encode_crops_u8`),
+  4. copies the fp16 embeddings back.
+Results per image have exactly the reference's layouts:
+  globals: f16 (512,)                                     oadp/oake/globals.py:57-59
+  blocks : {'embeddings': f16 (Nb,512), 'bboxes': f16 (Nb,4)}              blocks.py:125-134
+  objects: {'embeddings': f16 (No,512), 'bboxes': f16 (No,4), 'objectness': f16 (No,1)}  objects.py:316-338
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import binding, frontend
+from .model import OUT_DIM, OakeEngine
+
+CROP_BYTES = frontend.SIZE * frontend.SIZE * 3
+
+
+def _align(v: int, a: int = 256) -> int:
+    return (v + a - 1) // a * a
+
+
+class _Staging:
+    """Growable pinned host buffer + matching device buffer."""
+
+    def __init__(self, device: torch.device) -> None:
+        self.device = device
+        self.host: Optional[torch.Tensor] = None
+        self.dev: Optional[torch.Tensor] = None
+
+    def reserve(self, host_bytes: int, dev_bytes: Optional[int] = None) -> None:
+        dev_bytes = host_bytes if dev_bytes is None else dev_bytes
+        if self.host is None or self.host.numel() < host_bytes:
+            self.host = torch.empty(max(host_bytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        if self.dev is None or self.dev.numel() < dev_bytes:
+            self.dev = None
+            self.dev = torch.empty(max(dev_bytes, 1 << 20), dtype=torch.uint8, device=self.device)
+
+    def upload(self, nbytes: int) -> None:
+        self.dev[:nbytes].copy_(self.host[:nbytes], non_blocking=True)
+
+
+class OakePipeline:
+
+    def __init__(self, engine: OakeEngine) -> None:
+        self.engine = engine
+        self.lib = engine.lib
+        self.device = engine.device
+        self._arena = _Staging(self.device)  # images | pyramid levels | resized crops
+        self._meta = _Staging(self.device)  # resize jobs | crop descriptors | fg | box
+        self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._out_host: Optional[torch.Tensor] = None
+        self.h2d_bytes = 0  # of the last call
+        self.d2h_bytes = 0
+        self.frontend_launches = 0  # resize / mask kernels launched so far
+
+    # ------------------------------------------------------------------------------ internals
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _place_images(self, images: Sequence[np.ndarray]) -> Tuple[List[int], int]:
+        offs, off = [], 0
+        for im in images:
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError('images must be uint8 HWC RGB arrays')
+            offs.append(off)
+            off += _align(im.shape[0] * im.shape[1] * 3)
+        return offs, off
+
+    def _run(self, images: Sequence[np.ndarray], img_offs: List[int], img_bytes: int, arena_bytes: int,
+             stages: List[np.ndarray], crops: np.ndarray, variant: int,
+             fg: Optional[np.ndarray] = None, box: Optional[np.ndarray] = None) -> torch.Tensor:
+        """Uploads, launches every stage, encodes, returns the HOST fp16 (n_crops, 512) tensor."""
+        job = self.stage(images, img_offs, img_bytes, arena_bytes, stages, crops, variant, fg, box)
+        self.upload(job)
+        out = self.launch(job)
+        return self.download(out)
+
+    # The three phases are public so that bench.py can time the device-resident part alone.
+    def stage(self, images, img_offs, img_bytes, arena_bytes, stages, crops, variant, fg=None, box=None) -> dict:
+        """Host only: lays the images and descriptors out in the pinned staging buffers."""
+        n = crops.shape[0]
+        parts, off, stage_offs = [], 0, []
+        for jobs in stages:
+            stage_offs.append(off)
+            parts.append((off, jobs.view(np.uint8).reshape(-1)))
+            off = _align(off + jobs.nbytes)
+        crops_off = off
+        parts.append((off, crops.view(np.uint8).reshape(-1)))
+        off = _align(off + crops.nbytes)
+        fg_off = box_off = masks_off = 0
+        if variant == binding.VARIANT_T197:
+            fg_off = off
+            parts.append((off, np.ascontiguousarray(fg, dtype=np.float32).view(np.uint8).reshape(-1)))
+            off = _align(off + n * 16)
+            box_off = off
+            parts.append((off, np.ascontiguousarray(box, dtype=np.float32).view(np.uint8).reshape(-1)))
+            off = _align(off + n * 16)
+            masks_off = off  # device only
+        meta_host_bytes = off
+        meta_dev_bytes = off + (n * 196 * 4 if variant == binding.VARIANT_T197 else 0)
+        self._meta.reserve(meta_host_bytes, meta_dev_bytes)
+        self._arena.reserve(img_bytes, arena_bytes)
+        mh = self._meta.host.numpy()
+        for o, b in parts:
+            mh[o:o + b.size] = b
+        ah = self._arena.host.numpy()
+        for im, o in zip(images, img_offs):
+            ah[o:o + im.size] = im.reshape(-1)
+        return dict(n=n, variant=variant, img_bytes=img_bytes, meta_host_bytes=meta_host_bytes,
+                    stages=[(j.size, frontend.max_tiles(j), o) for j, o in zip(stages, stage_offs)],
+                    crops_off=crops_off, fg_off=fg_off, box_off=box_off, masks_off=masks_off)
+
+    def upload(self, job: dict) -> None:
+        self._arena.upload(job['img_bytes'])
+        self._meta.upload(job['meta_host_bytes'])
+        self.h2d_bytes = job['img_bytes'] + job['meta_host_bytes']
+
+    def launch(self, job: dict) -> torch.Tensor:
+        """Device only: resize stages, masks, tower.  Returns the DEVICE fp16 (n, 512) tensor."""
+        n, variant = job['n'], job['variant']
+        st = self._stream()
+        arena_ptr = self._arena.dev.data_ptr()
+        meta_ptr = self._meta.dev.data_ptr()
+        for count, tiles, o in job['stages']:
+            if count:
+                binding.check(self.lib.oake_resize_u8(arena_ptr, arena_ptr, meta_ptr + o, count, tiles,
+                                                      self._err.data_ptr(), st))
+                self.frontend_launches += 1
+        masks_ptr = None
+        if variant == binding.VARIANT_T197 and n:
+            masks_ptr = meta_ptr + job['masks_off']
+            binding.check(self.lib.oake_object_masks(meta_ptr + job['fg_off'], meta_ptr + job['box_off'], n,
+                                                     masks_ptr, st))
+            self.frontend_launches += 1
+        out = torch.empty(n, OUT_DIM, dtype=torch.float16, device=self.device)
+        step = self.engine.MAX_CROPS[variant]
+        if n:
+            ws = self.engine._workspace(min(n, step), variant)
+            for s in range(0, n, step):
+                b = min(step, n - s)
+                binding.check(self.lib.oake_encode_crops_u8(
+                    self.engine._handle, arena_ptr, meta_ptr + job['crops_off'] + s * frontend.CROP_SRC.itemsize, b,
+                    variant, (masks_ptr + s * 196 * 4) if masks_ptr else None, out[s:].data_ptr(), None,
+                    ws.data_ptr(), ws.numel(), st))
+        return out
+
+    def download(self, out: torch.Tensor) -> torch.Tensor:
+        n = out.shape[0]
+        if self._out_host is None or self._out_host.shape[0] < n:
+            self._out_host = torch.empty(max(n, 4096), OUT_DIM, dtype=torch.float16, pin_memory=True)
+        host = self._out_host[:n]
+        host.copy_(out, non_blocking=True)
+        err = self._err.to('cpu', non_blocking=False)  # synchronises the stream
+        self.d2h_bytes = n * OUT_DIM * 2 + 4
+        if int(err.item()) != 0:
+            self._err.zero_()
+            raise binding.OakeError('oake_resize_u8: a crop exceeded the resize kernel limits')
+        return host.clone()
+
+    # ------------------------------------------------------------------------------ public API
+    def encode_globals(self, images: Sequence[np.ndarray]) -> List[torch.Tensor]:
+        emb = self._run(*self.plan_globals(images))
+        return [emb[i] for i in range(len(images))]
+
+    def plan_globals(self, images: Sequence[np.ndarray]) -> tuple:
+        offs, img_bytes = self._place_images(images)
+        jobs = []
+        for k, (im, o) in enumerate(zip(images, offs)):
+            h, w = im.shape[:2]
+            jobs.append(frontend.crop_jobs(o, w, h, np.array([[0, 0, w, h]], dtype=np.int64),
+                                           img_bytes + k * CROP_BYTES))
+        jobs = np.concatenate(jobs) if jobs else np.zeros(0, frontend.RESIZE_JOB)
+        crops = np.zeros(len(images), dtype=frontend.CROP_SRC)
+        crops['off'] = jobs['dst_off']
+        crops['pitch_px'] = frontend.SIZE
+        return (images, offs, img_bytes, img_bytes + len(images) * CROP_BYTES, [jobs], crops, binding.VARIANT_T50)
+
+    def encode_blocks(self, images: Sequence[np.ndarray]) -> List[Dict[str, torch.Tensor]]:
+        args, plans, counts = self.plan_blocks(images)
+        emb = self._run(*args)
+        out, s = [], 0
+        for plan, n in zip(plans, counts):
+            out.append(dict(embeddings=emb[s:s + n], bboxes=torch.tensor(plan.bboxes, dtype=torch.float32).half()))
+            s += n
+        return out
+
+    def plan_blocks(self, images: Sequence[np.ndarray]):
+        offs, img_bytes = self._place_images(images)
+        plans = [frontend.blocks_plan(im.shape[1], im.shape[0]) for im in images]
+        off = img_bytes
+        # global crops (packed) first
+        glob_off = off
+        off += len(images) * CROP_BYTES
+        stage_jobs: List[List[np.ndarray]] = [[]]
+        crops_all = []
+        counts = []
+        for k, (im, o, plan) in enumerate(zip(images, offs, plans)):
+            h, w = im.shape[:2]
+            stage_jobs[0].append(frontend.crop_jobs(o, w, h, np.array([[0, 0, w, h]], dtype=np.int64),
+                                                    glob_off + k * CROP_BYTES))
+            level_off = [o]
+            for lv in range(1, len(plan.levels)):
+                lw, lh = plan.levels[lv]
+                pw, ph = plan.levels[lv - 1]
+                level_off.append(off)
+                while len(stage_jobs) < lv:
+                    stage_jobs.append([])
+                stage_jobs[lv - 1].append(frontend.level_job(level_off[lv - 1], pw, ph, off, lw, lh))
+                off += _align(lw * lh * 3)
+            c = np.zeros(1 + len(plan.cells), dtype=frontend.CROP_SRC)
+            c['off'][0] = glob_off + k * CROP_BYTES
+            c['pitch_px'][0] = frontend.SIZE
+            for i, (lv, x, y) in enumerate(plan.cells):
+                lw = plan.levels[lv][0]
+                c['off'][1 + i] = level_off[lv] + (y * lw + x) * 3
+                c['pitch_px'][1 + i] = lw
+            crops_all.append(c)
+            counts.append(c.shape[0])
+        stages = [np.concatenate(s) if s else np.zeros(0, frontend.RESIZE_JOB) for s in stage_jobs]
+        crops = np.concatenate(crops_all) if crops_all else np.zeros(0, frontend.CROP_SRC)
+        return (images, offs, img_bytes, off, stages, crops, binding.VARIANT_T50), plans, counts
+
+    def encode_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray],
+                       dry_run: bool = False) -> List[Dict[str, torch.Tensor]]:
+        args, plans = self.plan_objects(images, proposals, dry_run)
+        emb = self._run(*args)
+        out, s = [], 0
+        for plan in plans:
+            n = plan.bboxes.shape[0]
+            out.append(dict(embeddings=emb[s:s + n], bboxes=torch.from_numpy(plan.bboxes).half(),
+                            objectness=torch.from_numpy(plan.objectness).half()))
+            s += n
+        return out
+
+    def plan_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray], dry_run: bool = False):
+        offs, img_bytes = self._place_images(images)
+        plans = [frontend.objects_plan(p, (im.shape[1], im.shape[0]), dry_run) for im, p in zip(images, proposals)]
+        total = sum(p.bboxes.shape[0] for p in plans)
+        jobs, s = [], 0
+        for im, o, plan in zip(images, offs, plans):
+            h, w = im.shape[:2]
+            jobs.append(frontend.crop_jobs(o, w, h, plan.boxes_int, img_bytes + s * CROP_BYTES))
+            s += plan.bboxes.shape[0]
+        jobs = np.concatenate(jobs) if jobs else np.zeros(0, frontend.RESIZE_JOB)
+        crops = np.zeros(total, dtype=frontend.CROP_SRC)
+        crops['off'] = jobs['dst_off']
+        crops['pitch_px'] = frontend.SIZE
+        fg = np.concatenate([p.foregrounds for p in plans]) if plans else np.zeros((0, 4), np.float32)
+        box = np.concatenate([p.expanded for p in plans]) if plans else np.zeros((0, 4), np.float32)
+        return (images, offs, img_bytes, img_bytes + total * CROP_BYTES, [jobs], crops, binding.VARIANT_T197, fg,
+                box), plans
+
+    # --------------------------------------------------------------- test hooks (uint8 crops)
+    def debug_crops_u8(self, images: Sequence[np.ndarray], jobs: np.ndarray) -> np.ndarray:
+        """Runs only the resize stage; returns the packed (n,224,224,3) uint8 crops (tests)."""
+        offs, img_bytes = self._place_images(images)
+        n = jobs.shape[0]
+        hi = int(jobs['dst_off'].max()) + CROP_BYTES if n else img_bytes
+        self._arena.reserve(img_bytes, max(hi, img_bytes))
+        self._meta.reserve(_align(jobs.nbytes))
+        ah = self._arena.host.numpy()
+        for im, o in zip(images, offs):
+            ah[o:o + im.size] = im.reshape(-1)
+        self._meta.host.numpy()[:jobs.nbytes] = jobs.view(np.uint8).reshape(-1)
+        self._arena.upload(img_bytes)
+        self._meta.upload(jobs.nbytes)
+        p = self._arena.dev.data_ptr()
+        binding.check(self.lib.oake_resize_u8(p, p, self._meta.dev.data_ptr(), n, frontend.max_tiles(jobs),
+                                              self._err.data_ptr(), self._stream()))
+        torch.cuda.synchronize(self.device)
+        if int(self._err.item()) != 0:
+            self._err.zero_()
+            raise binding.OakeError('oake_resize_u8: a crop exceeded the resize kernel limits')
+        lo = int(jobs['dst_off'].min()) if n else 0
+        return self._arena.dev[lo:lo + n * CROP_BYTES].cpu().numpy().reshape(n, 224, 224, 3)
