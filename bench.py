@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""OAKE crops/sec benchmark (BASELINE.json metric) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload oake|globals|blocks|objects] [--images I]
+
+A step = one pass of the OAKE hot path over one batch of I synthetic COCO-shaped images per GPU:
+`oake` runs what the north star names -- globals (1 crop/image) + blocks (pyramid grid, 17..39
+crops/image) + objects (300 proposals/image, ~294 survive the min_wh filter) -- on the same images.
+
+  value     whole-job crops/s, inputs (uint8 images + descriptors) already resident in HBM; timed
+            with CUDA events around exactly K steps, max over ranks.
+  e2e       the same metric through the public API (`OakePipeline.encode_*`) with HOST images:
+            pinned staging, H2D, kernels, D2H of the fp16 embeddings all inside the timed region.
+  roofline  dominant kernel class (tcgen05 GEMM, c_fc instantiation): algorithmic FLOPs per launch /
+            mean launch duration from CUDA events on the launch stream, against MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference: the CPU oracle (oracle/: PIL + torch fp32, all host threads),
+            the only stand-in for the reference's CPU path that can run here, on a
+            bounded sample of the same workload.
+Multi-GPU: one process per GPU (torchrun), images sharded by rank, no data-path collective
+(the reference's OAKE issues none either, oadp/oake/base.py:84-88); weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+GFLOP_T50 = 8.818  # algorithmic GFLOP per crop, T=50
+GFLOP_T197 = 33.552  # T=197 + side stream with shared K/V
+WEIGHT_SEED = 1234
+PROPOSALS_PER_IMAGE = 300
+
+
+def peaks():
+    f = ROOT / 'MEASURED_PEAKS.json'
+    if f.exists():
+        d = json.loads(f.read_text())
+        return dict(tflops_sustained=d['bf16_tflops_sustained'], tflops_burst=d['bf16_tflops'], hbm_gbs=d['hbm_gbs'],
+                    source='measured')
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm_gbs=6650.0, source='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int) -> None:
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        sm = [float(r[1]) for r in rows]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[5 + i].lower().startswith('active') for r in rows)]
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=float(rows[0][2]), reasons=reasons,
+                    power_w_max=max(float(r[3]) for r in rows), samples=len(rows))
+
+
+def make_inputs(n_images: int, rank: int):
+    from oadp_b200 import synth
+    imgs = synth.images(n_images, seed=1000 + rank)
+    props = [synth.proposals(im.shape[1], im.shape[0], PROPOSALS_PER_IMAGE, seed=7000 + 97 * rank + i)
+             for i, im in enumerate(imgs)]
+    return imgs, props
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(workload: str, n_images: int, steps: int, warmup: int, sample_objects: int = 24):
+    import PIL.Image
+    import torch
+    from oracle import frontend as ofe
+    from oracle import vit
+    torch.set_num_threads(os.cpu_count() or 1)
+    imgs, props = make_inputs(n_images, 0)
+    counts = workload_counts(imgs, props)
+    p = vit.init_visual_params(WEIGHT_SEED)
+    p197 = vit.objects_surgery(p)
+    img = PIL.Image.fromarray(imgs[0])
+    prop = torch.from_numpy(props[0][:sample_objects + 4])
+
+    def one_step():
+        t = {}
+        n = {}
+        t0 = time.perf_counter()
+        px = ofe.globals_preprocess(img).unsqueeze(0)  # B=1 as globals.py:54
+        vit.normalize_half(vit.encode_image(p, px))
+        t['globals'], n['globals'] = time.perf_counter() - t0, 1
+        t0 = time.perf_counter()
+        b = ofe.blocks_preprocess(img)  # whole image batch as blocks.py:126-129
+        vit.normalize_half(vit.encode_image(p, b.blocks))
+        t['blocks'], n['blocks'] = time.perf_counter() - t0, b.blocks.shape[0]
+        t0 = time.perf_counter()
+        o = ofe.objects_preprocess(img, prop)
+        vit.normalize_half(vit.encode_objects(p197, o.objects, o.masks))
+        t['objects'], n['objects'] = time.perf_counter() - t0, o.objects.shape[0]
+        return t, n
+
+    kinds = ['globals', 'blocks', 'objects'] if workload == 'oake' else [workload]
+    for _ in range(warmup):
+        one_step()
+    per_crop = {k: [] for k in kinds}
+    t_all0 = time.perf_counter()
+    for _ in range(steps):
+        t, n = one_step()
+        for k in kinds:
+            per_crop[k].append(t[k] / n[k])
+    wall = time.perf_counter() - t_all0
+    sec_per_crop = {k: statistics.median(v) for k, v in per_crop.items()}
+    total_crops = sum(counts[k] for k in kinds)
+    total_sec = sum(counts[k] * sec_per_crop[k] for k in kinds)
+    value = total_crops / total_sec
+    sample = (f'1 image 640x480 per step: 1 global (B=1) + {n["blocks"]} blocks (one batch) + {n["objects"]} '
+              f'objects (one batch), PIL front end in-process; per-kind sec/crop (median of {steps}) re-weighted to '
+              f'the step mix {counts}')
+    return dict(value=value, sec_per_crop=sec_per_crop, sample=sample, cores=torch.get_num_threads(), wall_s=wall,
+                ms_per_step=wall / max(steps, 1) * 1e3)
+
+
+def workload_counts(imgs, props):
+    from oadp_b200 import frontend
+    blocks = sum(1 + len(frontend.blocks_plan(im.shape[1], im.shape[0]).cells) for im in imgs)
+    objects = sum(frontend.objects_plan(p, (im.shape[1], im.shape[0])).bboxes.shape[0] for im, p in zip(imgs, props))
+    return dict(globals=len(imgs), blocks=blocks, objects=objects)
+
+
+# ------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='oake', choices=['oake', 'globals', 'blocks', 'objects'])
+    ap.add_argument('--images', type=int, default=8, help='images per step per GPU')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    pk = peaks()
+    cfg = dict(workload=(f'{args.workload}: globals+blocks+objects over the same images' if args.workload == 'oake'
+                         else args.workload), images_per_step_per_gpu=args.images,
+               proposals_per_image=PROPOSALS_PER_IMAGE, image_sizes='COCO-train2017-like mix (SURVEY 8d)',
+               tower='CLIP ViT-B/32 visual, 224^2, seeded random weights', parallelism=f'image-sharded x{world}')
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        ref = cpu_reference(args.workload, args.images, steps, min(args.warmup, 1))
+        line = dict(metric='OAKE crops/sec (ViT-B/32, 224^2, synthetic COCO proposals)', impl='reference',
+                    value=ref['value'], unit='crops/s', n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 1),
+                    ms_per_step=ref['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f32', data='synthetic', config=cfg,
+                    cpu_baseline=dict(value=ref['value'], unit='crops/s', cores=ref['cores'], kind='port',
+                                      sample=ref['sample'], sec_per_crop=ref['sec_per_crop']),
+                    e2e=dict(value=ref['value'], unit='crops/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device: the OAKE hot path has no CPU fallback')
+    torch.cuda.set_device(local_rank % torch.cuda.device_count())
+    if world > 1:
+        dist.init_process_group('nccl')
+    from oadp_b200 import build, synth
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    from oadp_b200.model import OakeEngine
+    from oadp_b200.pipeline import OakePipeline
+
+    dev = torch.device('cuda', torch.cuda.current_device())
+    engine = OakeEngine(synth.visual_params(WEIGHT_SEED), dev)
+    imgs, props = make_inputs(args.images, rank)
+    counts = workload_counts(imgs, props)
+    kinds = ['globals', 'blocks', 'objects'] if args.workload == 'oake' else [args.workload]
+    crops_per_step = sum(counts[k] for k in kinds)
+    gflop_per_step = sum(counts[k] * (GFLOP_T197 if k == 'objects' else GFLOP_T50) for k in kinds)
+    cfg['crops_per_step_per_gpu'] = {k: counts[k] for k in kinds}
+    cfg['l2_policy'] = ('no flush needed: every step streams > 2 GB of activations through HBM, far above the '
+                        '126 MB L2')
+
+    # one pipeline per kind so that each keeps its inputs resident in HBM
+    pipes = {k: OakePipeline(engine) for k in kinds}
+
+    def plan(k):
+        if k == 'globals':
+            return pipes[k].plan_globals(imgs)
+        if k == 'blocks':
+            return pipes[k].plan_blocks(imgs)[0]
+        return pipes[k].plan_objects(imgs, props)[0]
+
+    jobs = {}
+    for k in kinds:
+        jobs[k] = pipes[k].stage(*plan(k))
+        pipes[k].upload(jobs[k])
+    torch.cuda.synchronize()
+
+    def device_step():
+        return [pipes[k].launch(jobs[k]) for k in kinds]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- value: device-resident
+    for _ in range(warmup):
+        device_step()
+    barrier()
+    launches0 = engine.launch_count() + sum(p.frontend_launches for p in pipes.values())
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    launches = engine.launch_count() + sum(p.frontend_launches for p in pipes.values()) - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = crops_per_step * world * args.steps / (ms * 1e-3)
+
+    # ---------------------------------------------------------------- e2e: public API, host buffers
+    def api_step():
+        for k in kinds:
+            if k == 'globals':
+                pipes[k].encode_globals(imgs)
+            elif k == 'blocks':
+                pipes[k].encode_blocks(imgs)
+            else:
+                pipes[k].encode_objects(imgs, props)
+
+    h2d = d2h = 0
+    for _ in range(2):
+        api_step()
+    for k in kinds:
+        h2d += pipes[k].h2d_bytes
+        d2h += pipes[k].d2h_bytes
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        api_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = crops_per_step * world * e2e_steps / float(t.item())
+
+    # ---------------------------------------------------------------- roofline: per-class CUDA events
+    engine.profile(True)
+    for _ in range(2):
+        device_step()
+    prof = engine.profile_collect()
+    engine.profile(False)
+    gemm = {k: v for k, v in prof.items() if k.startswith('gemm_') and v['launches']}
+    dom = max(gemm, key=lambda k: gemm[k]['ms']) if gemm else None
+    tot_ms = sum(v['ms'] for v in prof.values()) or 1.0
+    roof = None
+    if dom:
+        d = gemm[dom]
+        achieved = d['flops'] / (d['ms'] * 1e-3) / 1e12
+        all_ach = sum(v['flops'] for v in gemm.values()) / (sum(v['ms'] for v in gemm.values()) * 1e-3) / 1e12
+        roof = dict(bound='tensor', kernel=f'gemm_tcgen05_kernel ({dom})', achieved=achieved, peak=pk['tflops_sustained'],
+                    unit='TFLOP/s', frac=achieved / pk['tflops_sustained'], traffic=None,
+                    peak_source=f"{pk['source']} bf16 cuBLAS, sustained (kernel timed inside a long step)",
+                    flops_per_launch=d['flops'] / d['launches'], us_per_launch=d['ms'] / d['launches'] * 1e3,
+                    share_of_step=d['ms'] / tot_ms,
+                    all_gemm=dict(achieved=all_ach, frac=all_ach / pk['tflops_sustained'],
+                                  share_of_step=sum(v['ms'] for v in gemm.values()) / tot_ms),
+                    step=dict(achieved=value / world * (gflop_per_step / crops_per_step) / 1e3,
+                              frac=value / world * (gflop_per_step / crops_per_step) / 1e3 / pk['tflops_sustained'],
+                              note='whole step: crops/s x algorithmic GFLOP/crop (8.818 T50, 33.552 T197)'),
+                    classes={k: dict(ms_per_step=v['ms'] / 2, share=v['ms'] / tot_ms,
+                                     tflops=(v['flops'] / (v['ms'] * 1e-3) / 1e12) if v['flops'] and v['ms'] else 0.0)
+                             for k, v in prof.items() if v['launches']})
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        ref = cpu_reference(args.workload, args.images, 2, 1)
+        cpu = dict(value=ref['value'], unit='crops/s', cores=ref['cores'], kind='port', sample=ref['sample'],
+                   sec_per_crop=ref['sec_per_crop'])
+
+    line = dict(metric='OAKE crops/sec (ViT-B/32, 224^2, synthetic COCO proposals)', value=value, unit='crops/s',
+                n_gpus=world, steps=args.steps, warmup=warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f16', data='synthetic', config=cfg, roofline=roof,
+                cpu_baseline=cpu,
+                e2e=dict(value=e2e_value, unit='crops/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         steps=e2e_steps),
+                gpu_launches=launches, clocks=clocks)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

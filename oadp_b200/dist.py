@@ -1,0 +1,61 @@
+"""Multi-GPU plumbing of OAKE: one process per GPU, images sharded by rank, no data-path collective.
+
+The reference shards with `DistributedSampler(dataset, shuffle=False)` (oadp/oake/base.py:84-88):
+rank r gets images r, r+W, ... and the index list is padded by wrap-around, so up to W-1 images are
+encoded twice and ranks finish at different times because crops per image
+vary.  Here the shard is balanced by *crop count* (known before any GPU work from the proposal
+file / image sizes) and nothing is duplicated.  NCCL is only used to collate outputs when the
+caller asks for a single gathered tensor (`all_gather_embeddings`); writing per-image .pth files
+needs no communication at all.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def rank_world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+
+
+def balanced_partition(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Longest-processing-time greedy: indices sorted by decreasing cost, each to the lightest rank.
+    Deterministic (ties by index), every index assigned exactly once, each shard sorted ascending."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    load = [0.0] * world
+    shards: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        shards[r].append(i)
+        load[r] += float(costs[i])
+    return [sorted(s) for s in shards]
+
+
+def all_gather_embeddings(emb: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Collates per-rank (n_r, 512) fp16 embeddings and their int64 row ids on every rank.
+
+    One all_gather of the counts, then one all_gather_into_tensor of the padded payload: 1 KiB per
+    crop, so even 8 GPUs x 20k crops/s is < 0.2 GB/s of NVLink traffic."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return emb, ids
+    world = dist.get_world_size()
+    n = torch.tensor([emb.shape[0]], device=emb.device, dtype=torch.int64)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    m = max(counts)
+    pad_e = torch.zeros(m, emb.shape[1], dtype=emb.dtype, device=emb.device)
+    pad_i = torch.full((m, ), -1, dtype=torch.int64, device=emb.device)
+    pad_e[:emb.shape[0]] = emb
+    pad_i[:ids.shape[0]] = ids
+    out_e = torch.empty(world * m, emb.shape[1], dtype=emb.dtype, device=emb.device)
+    out_i = torch.empty(world * m, dtype=torch.int64, device=emb.device)
+    dist.all_gather_into_tensor(out_e, pad_e)
+    dist.all_gather_into_tensor(out_i, pad_i)
+    keep = torch.cat([torch.arange(c, device=emb.device) + r * m for r, c in enumerate(counts)])
+    return out_e[keep], out_i[keep]

@@ -1,0 +1,202 @@
+"""Shared skeleton of the three OAKE extractors -- the counterpart of oadp/oake/base.py.
+
+Kept from the reference (the drop-in contract):
+  * CLI `python|torchrun -m oadp.oake.<task> NAME CONFIG [--override .k.k:v ...]` (base.py:66-72)
+  * `BaseDataset`: COCO image ids, output `{output_dir}/{id:012d}.pth`, items already on disk are
+    skipped, `auto_fix=True` re-loads them to detect truncated files (base.py:28-54)
+  * `BaseValidator.main()`: build the model once, run the `val` split, then `train` (base.py:115-152)
+  * `torch.save(result, output)` per image (base.py:106-113)
+Changed on purpose (B200-first):
+  * the dataset item is the decoded uint8 image (+ proposals); cropping / resizing / normalising
+    happen on the GPU (`oadp_b200.pipeline`), not with PIL in DataLoader workers
+  * images are grouped into batches of `batch_images` so that the tower always sees SM-filling
+    crop counts, and sharded across ranks by crop count (`oadp_b200.dist`) without duplicates
+  * files are written by a small thread pool while the GPU works on the next batch
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures
+import pathlib
+import time
+from abc import ABC, abstractmethod
+from typing import Any, Dict, Generic, Iterator, List, NamedTuple, Optional, Sequence, Tuple, TypeVar
+
+import numpy as np
+import torch
+
+from .. import dist as oake_dist
+from ..compat import CocoImages, Config, DictAction, Store
+from ..model import OakeModel
+from ..pipeline import OakePipeline
+
+
+class Item(NamedTuple):
+    id_: int
+    output: pathlib.Path
+    image: np.ndarray  # uint8 HWC RGB
+    extra: Any = None
+
+
+T = TypeVar('T')
+
+
+class BaseDataset(CocoImages, ABC, Generic[T]):
+
+    def __init__(self, *args, auto_fix: bool = False, output_dir: str, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self._auto_fix = auto_fix
+        self._output_dir = pathlib.Path(output_dir)
+        self._output_dir.mkdir(parents=True, exist_ok=True)
+
+    def output_path(self, id_: int) -> pathlib.Path:
+        return self._output_dir / f'{id_:012d}.pth'
+
+    def is_done(self, id_: int) -> bool:
+        output = self.output_path(id_)
+        if not output.exists():
+            return False
+        if not self._auto_fix:
+            return True
+        try:
+            torch.load(output, 'cpu')
+            return True
+        except Exception:
+            print(f'Fixing {output}', flush=True)
+            return False
+
+    def __getitem__(self, index: int) -> Optional[Item]:
+        id_ = self.ids[index]
+        if self.is_done(id_):
+            return None
+        image = np.asarray(self._load_image(id_), dtype=np.uint8)
+        return Item(id_, self.output_path(id_), image, self._extra(id_))
+
+    def _extra(self, id_: int) -> Any:
+        return None
+
+    def cost(self, index: int) -> float:
+        """Relative amount of GPU work of item `index` (for the balanced shard)."""
+        return 1.0
+
+
+def parse_args(argv: Optional[Sequence[str]] = None) -> argparse.Namespace:
+    parser = argparse.ArgumentParser(description='OAKE feature extraction')
+    parser.add_argument('name', type=str)
+    parser.add_argument('config', type=Config.load)
+    parser.add_argument('--override', action=DictAction, nargs='+')
+    return parser.parse_args(argv)
+
+
+def default_params() -> Dict[str, torch.Tensor]:
+    """Stand-in for `clip.load_default`: a ViT-B/32 state dict named by $OAKE_CLIP_WEIGHTS
+    (OpenAI `visual.*` names, e.g. exported from the official checkpoint), else seeded random
+    weights -- no CLIP checkpoint exists in this offline environment."""
+    import os
+    path = os.environ.get('OAKE_CLIP_WEIGHTS')
+    if path:
+        sd = torch.load(path, 'cpu')
+        sd = sd.get('state_dict', sd)
+        return {k[len('visual.'):] if k.startswith('visual.') else k: v.float() for k, v in sd.items()
+                if k.startswith('visual.') or k in ('proj', 'class_embedding', 'positional_embedding') or
+                k.startswith(('conv1.', 'ln_pre.', 'ln_post.', 'transformer.'))}
+    from .. import synth
+    print('OAKE_CLIP_WEIGHTS is not set: using seeded random ViT-B/32 weights', flush=True)
+    return synth.visual_params(0)
+
+
+class BaseValidator(ABC, Generic[T]):
+    """One split of one task: iterate images, encode on the GPU, write `.pth` files."""
+
+    DATASET = BaseDataset
+
+    def __init__(self, name: str, model: OakeModel, *, dataloader: Config, log: Optional[Config] = None,
+                 batch_images: int = 8, **_: Any) -> None:
+        self._name = name
+        self._model = model
+        self._pipeline = OakePipeline(model.engine)
+        self._log_interval = int((log or {}).get('interval', 50))
+        self._batch_images = 1 if Store.DRY_RUN else int(batch_images)
+        self._dataset = self._build_dataset(Config(dataloader.dataset))
+        self._writer = concurrent.futures.ThreadPoolExecutor(max_workers=int(dataloader.get('num_workers', 2)) or 1)
+
+    # ------------------------------------------------------------------ to be provided per task
+    @classmethod
+    def _build_model(cls) -> Tuple[OakeModel, Any]:
+        """(model, preprocess) like the reference; preprocess is None: it lives on the GPU."""
+        return OakeModel(default_params(), 'cuda'), None
+
+    def _build_dataset(self, config: Config) -> BaseDataset:
+        config.pop('transform', None)
+        return self.DATASET(**config)
+
+    @abstractmethod
+    def _encode(self, items: List[Item]) -> List[Any]:
+        """-> one result per item, in the exact layout the reference stores."""
+
+    # ---------------------------------------------------------------------------------- the loop
+    def _shard(self) -> List[int]:
+        rank, world = oake_dist.rank_world()
+        todo = list(range(len(self._dataset)))
+        if world == 1:
+            return todo
+        costs = [self._dataset.cost(i) for i in todo]
+        return oake_dist.balanced_partition(costs, world)[rank]
+
+    def _batches(self, indices: List[int]) -> Iterator[List[Item]]:
+        batch: List[Item] = []
+        for i in indices:
+            item = self._dataset[i]
+            if item is None:  # already on disk (base.py:45-47)
+                continue
+            batch.append(item)
+            if len(batch) == self._batch_images:
+                yield batch
+                batch = []
+        if batch:
+            yield batch
+
+    def run(self) -> int:
+        indices = self._shard()
+        if Store.DRY_RUN:
+            indices = indices[:3]
+        done, crops, t0, pending = 0, 0, time.perf_counter(), []
+        for batch in self._batches(indices):
+            results = self._encode(batch)
+            for item, result in zip(batch, results):
+                pending.append(self._writer.submit(torch.save, result, item.output))
+            done += len(batch)
+            if done % max(self._log_interval, 1) < len(batch):
+                dt = time.perf_counter() - t0
+                print(f'[{self._name}] {done}/{len(indices)} images, {done / dt:.1f} img/s', flush=True)
+            still = []
+            for f in pending:
+                if f.done():
+                    f.result()  # surface write errors
+                else:
+                    still.append(f)
+            pending = still
+        for f in pending:
+            f.result()
+        self._writer.shutdown(wait=True)
+        return done
+
+    @classmethod
+    def main(cls, argv: Optional[Sequence[str]] = None) -> None:
+        args = parse_args(argv)
+        config: Config = args.config
+        if args.override:
+            config.override(args.override)
+        if not Store.CUDA:
+            raise RuntimeError('oadp_b200 OAKE needs a CUDA (sm_100a) device; there is no CPU path')
+        import os
+        if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not torch.distributed.is_initialized():
+            torch.distributed.init_process_group(backend='nccl')
+        local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local_rank % torch.cuda.device_count())
+
+        model, _ = cls._build_model()
+        train = config.pop('train')
+        val = config.pop('val')
+        for split in (val, train):  # val first, then train (base.py:136-152)
+            cls(args.name, model, **split, **config).run()

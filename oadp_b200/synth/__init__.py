@@ -102,3 +102,45 @@ def visual_params(seed: int = 0, layers: int = 12) -> Dict[str, 'np.ndarray']:
         p[pre + 'mlp.c_proj.bias'] = rn(w, std=0.02)
     p['proj'] = rn(w, 512, std=scale)
     return p
+
+
+def write_coco_dataset(root, n_images: int, seed: int = 0, n_proposals: int = 40, sizes=COCO_SIZES,
+                       first_id: int = 101) -> dict:
+    """Materialises a tiny COCO-format dataset (lossless PNG images, instances json, proposal pickle
+    in image-id order) plus an OAKE config for each task.  Returns the paths."""
+    import json
+    import pathlib
+    import pickle
+
+    import PIL.Image
+    root = pathlib.Path(root)
+    (root / 'images').mkdir(parents=True, exist_ok=True)
+    infos, props = [], []
+    for i in range(n_images):
+        w, h = sizes[i % len(sizes)]
+        id_ = first_id + 7 * i
+        arr = image(w, h, seed * 100003 + i)
+        name = f'{id_:012d}.png'
+        PIL.Image.fromarray(arr).save(root / 'images' / name)
+        infos.append(dict(id=id_, file_name=name, width=w, height=h))
+        props.append(proposals(w, h, n_proposals, seed=seed * 7919 + i))
+    ann = root / 'instances.json'
+    ann.write_text(json.dumps(dict(images=infos, annotations=[], categories=[])))
+    pkl = root / 'proposals.pkl'
+    with open(pkl, 'wb') as f:
+        pickle.dump(props, f)
+    cfgs = {}
+    for task in ('globals', 'blocks', 'objects'):
+        ds = dict(root=str(root / 'images'), annFile=str(ann))
+        extra = ''
+        if task == 'objects':
+            ds.update(type='COCODataset', proposal_file=str(pkl), proposal_sorted=True)
+            extra = 'mini_batch_size = 512\n'
+        body = ''
+        for split in ('train', 'val'):
+            d = dict(ds, output_dir=str(root / 'oake' / task / split))
+            body += f'{split} = dict(dataloader=dict(dataset=dict({", ".join(f"{k}={v!r}" for k, v in d.items())}), num_workers=2))\n'
+        cfg = root / f'{task}.py'
+        cfg.write_text(body + 'log = dict(interval=2)\n' + extra)
+        cfgs[task] = str(cfg)
+    return dict(root=str(root), ann=str(ann), proposals=str(pkl), configs=cfgs, ids=[i['id'] for i in infos])

@@ -1,0 +1,80 @@
+"""GPU tier: the reference-facing entry points end to end -- `oadp.oake.{globals,blocks,objects}`
+Validator.main on a synthetic COCO-format dataset: output files, layouts, resume, oracle parity."""
+import pathlib
+
+import numpy as np
+import PIL.Image
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oadp_b200 import synth
+from oracle import frontend as ofe
+from oracle import vit
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dataset(tmp_path_factory, lib):
+    return synth.write_coco_dataset(tmp_path_factory.mktemp('coco'), 5, seed=2, n_proposals=20)
+
+
+def cos_ok(got, want):
+    return float((1 - F.cosine_similarity(got.float(), want.float(), dim=-1)).max()) < 1e-3
+
+
+def test_cli_all_tasks(dataset, monkeypatch):
+    monkeypatch.delenv('DRY_RUN', raising=False)
+    monkeypatch.delenv('OAKE_CLIP_WEIGHTS', raising=False)
+    import oadp.oake.blocks as cli_blocks
+    import oadp.oake.globals as cli_globals
+    import oadp.oake.objects as cli_objects
+    root = pathlib.Path(dataset['root'])
+    p = vit.init_visual_params(0)  # what default_params() falls back to (seeded random ViT-B/32)
+    p197 = vit.objects_surgery(p)
+    id0 = dataset['ids'][0]
+    pil = PIL.Image.open(root / 'images' / f'{id0:012d}.png').convert('RGB')
+    props = torch.from_numpy(synth.proposals(*pil.size, 20, seed=2 * 7919 + 0))
+
+    cli_globals.Validator.main(['t', dataset['configs']['globals'], '--override', '.batch_images:4'])
+    for split in ('train', 'val'):
+        files = sorted((root / 'oake' / 'globals' / split).glob('*.pth'))
+        assert [f.stem for f in files] == [f'{i:012d}' for i in dataset['ids']]
+    g = torch.load(root / 'oake' / 'globals' / 'val' / f'{id0:012d}.pth')
+    assert g.shape == (512, ) and g.dtype == torch.float16
+    assert cos_ok(g[None], vit.normalize_half(vit.encode_image(p, ofe.globals_preprocess(pil)[None])))
+
+    cli_blocks.Validator.main(['t', dataset['configs']['blocks']])
+    b = torch.load(root / 'oake' / 'blocks' / 'train' / f'{id0:012d}.pth')
+    rb = ofe.blocks_preprocess(pil)
+    assert set(b) == {'embeddings', 'bboxes'} and b['embeddings'].dtype == torch.float16
+    assert torch.equal(b['bboxes'], rb.bboxes.half())
+    assert cos_ok(b['embeddings'], vit.normalize_half(vit.encode_image(p, rb.blocks)))
+
+    cli_objects.Validator.main(['t', dataset['configs']['objects']])
+    o = torch.load(root / 'oake' / 'objects' / 'val' / f'{id0:012d}.pth')
+    ro = ofe.objects_preprocess(pil, props)
+    assert set(o) == {'embeddings', 'bboxes', 'objectness'}
+    assert o['objectness'].shape == (ro.objectness.shape[0], 1) and torch.equal(o['bboxes'], ro.bboxes.half())
+    assert cos_ok(o['embeddings'], vit.normalize_half(vit.encode_objects(p197, ro.objects, ro.masks)))
+
+    # resume: everything is on disk, a second run must not rewrite a single file
+    victim = root / 'oake' / 'objects' / 'val' / f'{dataset["ids"][2]:012d}.pth'
+    before = {f: f.stat().st_mtime_ns for f in (root / 'oake' / 'objects' / 'val').glob('*.pth')}
+    victim.unlink()
+    cli_objects.Validator.main(['t', dataset['configs']['objects']])
+    after = {f: f.stat().st_mtime_ns for f in (root / 'oake' / 'objects' / 'val').glob('*.pth')}
+    assert victim in after and all(after[f] == t for f, t in before.items() if f != victim)
+
+
+def test_cli_dry_run(dataset, monkeypatch, tmp_path):
+    monkeypatch.setenv('DRY_RUN', 'True')
+    import oadp.oake.objects as cli_objects
+    out = tmp_path / 'dry'
+    cli_objects.Validator.main(['t', dataset['configs']['objects'], '--override',
+                                f'.val.dataloader.dataset.output_dir::{out}/val',
+                                f'.train.dataloader.dataset.output_dir::{out}/train'])
+    files = sorted((out / 'val').glob('*.pth'))
+    assert 1 <= len(files) <= 3
+    assert torch.load(files[0])['embeddings'].shape[0] <= 5  # objects.py:166-167
