@@ -176,7 +176,9 @@ int oake_test_layernorm(const void* x_act, const float* w, const float* b, void*
                         void* stream);
 /* qkv act [R,2304], rows [B*P | B | (B)]; out act [R,768]. */
 int oake_test_attention_main(const void* qkv, void* out_act, int B, int P, void* stream);
-int oake_test_attention_side(const void* qkv, const float* mask, void* out_act, int B, int P,
+/* Objects attention: main stream + the side token y in one kernel (side_only = 0), or only the B
+ * side rows (side_only = 1, last block).  qkv act [B*(P+2),2304], mask fp32 [B,P]. */
+int oake_test_attention_side(const void* qkv, const float* mask, void* out_act, int B, int P, int side_only,
                              void* stream);
 int oake_test_im2col(const float* pixels, void* patches_act, int B, int variant, void* stream);
 

@@ -50,7 +50,7 @@ enum KClass {
   K_NUM
 };
 const char* kClassNames[K_NUM] = {"frontend", "gemm_patch", "assemble_ln_pre", "gemm_qkv", "attn_main",
-                                  "attn_side", "gemm_out", "gemm_fc1", "gemm_fc2", "ln_post",
+                                  "attn_side_only", "gemm_out", "gemm_fc1", "gemm_fc2", "ln_post",
                                   "gemm_proj", "l2norm_half"};
 
 struct LayerMaps {
@@ -355,10 +355,11 @@ int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const
       GemmEpilogue ep{lw.qkv_c, lw.qkv_s, stats_b, nullptr, nullptr, qkv, 3 * W, 0, 0, 0};
       go.run(K_GEMM_QKV, gflops(R, 3 * W, W), [&] { return launch_gemm(st, tm_x, tm.qkv, R, 3 * W, W, ep, ns); });
     }
-    if (!(last && side))
-      go.run(K_ATTN_MAIN, 4.0 * B * p.T * p.T * W, [&] { return launch_attention_main(st, qkv, attn, B, p.P, H); });
-    if (side)
-      go.run(K_ATTN_SIDE, 4.0 * B * p.T * W, [&] { return launch_attention_side(st, qkv, masks, attn, B, p.P, H); });
+    if (side && last)  // only the y row of the last block is alive (objects.py:249-258)
+      go.run(K_ATTN_SIDE, 4.0 * B * p.T * W, [&] { return launch_attention(st, qkv, masks, attn, B, p.P, H, 1, 1); });
+    else
+      go.run(K_ATTN_MAIN, 4.0 * B * p.T * p.T * W + (side ? 4.0 * B * p.T * W : 0.0),
+             [&] { return launch_attention(st, qkv, masks, attn, B, p.P, H, side ? 1 : 0, 0); });
     {  // x += attn W_o^T + b ; statistics of the new x -> stats_a
       GemmEpilogue ep{lw.out_b, nullptr, nullptr, xr, stats_a + static_cast<size_t>(r0) * kStatSlots, xr, W, W, 0, 0};
       go.run(K_GEMM_OUT, gflops(rn, W, W),
@@ -510,17 +511,17 @@ int oake_test_layernorm(const void* x_act, const float* w, const float* b, void*
 }
 
 int oake_test_attention_main(const void* qkv, void* out_act, int B, int P, void* stream) {
-  cudaError_t e = launch_attention_main(static_cast<cudaStream_t>(stream), static_cast<const act_t*>(qkv),
-                                        static_cast<act_t*>(out_act), B, P, 12);
+  cudaError_t e = launch_attention(static_cast<cudaStream_t>(stream), static_cast<const act_t*>(qkv), nullptr,
+                                   static_cast<act_t*>(out_act), B, P, 12, 0, 0);
   if (e != cudaSuccess) return fail("attention_main launch: %s", cudaGetErrorString(e));
   return 0;
 }
 
-int oake_test_attention_side(const void* qkv, const float* mask, void* out_act, int B, int P,
+int oake_test_attention_side(const void* qkv, const float* mask, void* out_act, int B, int P, int side_only,
                              void* stream) {
-  cudaError_t e = launch_attention_side(static_cast<cudaStream_t>(stream), static_cast<const act_t*>(qkv),
-                                        mask, static_cast<act_t*>(out_act), B, P, 12);
-  if (e != cudaSuccess) return fail("attention_side launch: %s", cudaGetErrorString(e));
+  cudaError_t e = launch_attention(static_cast<cudaStream_t>(stream), static_cast<const act_t*>(qkv), mask,
+                                   static_cast<act_t*>(out_act), B, P, 12, 1, side_only);
+  if (e != cudaSuccess) return fail("attention (side) launch: %s", cudaGetErrorString(e));
   return 0;
 }
 

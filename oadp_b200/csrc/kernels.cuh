@@ -54,13 +54,13 @@ cudaError_t launch_l2norm_half(cudaStream_t st, const float* e, __half* out, int
 
 // ----------------------------------------------------------- attention.cu
 // qkv: act [R, 3*W] (q | k | v, head h = columns 64h..64h+63 of each third); rows ordered
-// [B*P patch rows | B class rows | (B side rows)].  Writes act [R, W] for patch + class rows.
-cudaError_t launch_attention_main(cudaStream_t st, const act_t* qkv, act_t* out, int B, int P,
-                                  int heads);
-// Side stream (objects): one query (the y row) over the P patch keys + itself with additive
-// bias -100 * mask (mask: fp32 [B, P], 1 = background).  Writes the B side rows of `out`.
-cudaError_t launch_attention_side(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out,
-                                  int B, int P, int heads);
+// [B*P patch rows | B class rows | (B side rows)].  Writes act [R, W].
+//   with_side = 0: main stream only (patch + class rows).
+//   with_side = 1: objects; the side token y (one query over the P patch keys + itself, additive
+//                  bias -100 * mask, mask fp32 [B, P] with 1 = background) rides in the same tile.
+//                  side_only = 1 writes just the B side rows (last block of the objects tower).
+cudaError_t launch_attention(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
+                             int heads, int with_side, int side_only);
 
 // ------------------------------------------------------------ frontend.cu
 // pixels fp32 NCHW [B,3,224,224] (already CLIP-normalised) -> act [B*P, 3*32*32] conv1 patches,

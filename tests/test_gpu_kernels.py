@@ -184,8 +184,9 @@ def test_attention_main(lib, P, B):
     assert (out.float() - ref).abs().max() < tol, (out.float() - ref).abs().max()
 
 
-def test_attention_side(lib):
-    B, P = 4, 196
+@pytest.mark.parametrize('side_only', [1, 0])
+def test_attention_side(lib, side_only):
+    B, P = 5, 196
     g = torch.Generator(device=DEV).manual_seed(11)
     R = B * (P + 2)
     qkv = (torch.randn(R, 2304, device=DEV, generator=g) * 1.5).to(act_dtype())
@@ -193,13 +194,17 @@ def test_attention_side(lib):
     mask[0] = 0
     mask[1] = 1
     out = torch.zeros(R, 768, device=DEV, dtype=act_dtype())
-    binding.check(lib.oake_test_attention_side(qkv.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, stream()))
+    binding.check(lib.oake_test_attention_side(qkv.data_ptr(), mask.data_ptr(), out.data_ptr(), B, P, side_only,
+                                               stream()))
     torch.cuda.synchronize()
     ref = ref_attention(qkv, B, P, mask)
     ys = slice(B * P + B, R)
     tol = 6e-3 if act_dtype() == torch.float16 else 4e-2
     assert (out[ys].float() - ref[ys]).abs().max() < tol
-    assert (out[:B * P + B] == 0).all()  # side kernel writes only the side rows
+    if side_only:
+        assert (out[:B * P + B] == 0).all()  # only the side rows are written
+    else:
+        assert (out.float() - ref).abs().max() < tol  # main stream and side token from one kernel
 
 
 @pytest.mark.parametrize('variant', [0, 1])
