@@ -31,7 +31,7 @@ struct ACfg {
   static constexpr int TP = ((TQ + 15) / 16) * 16;
   static constexpr int MT = TP / 16;
   static constexpr int WPH = (MT + 1) / 2;    // warps per head (two m-tiles each)
-  static constexpr int HPC = 1;               // heads per CTA
+  static constexpr int HPC = 1;               // heads per CTA (the async load below assumes 1)
   static constexpr int kMinCtas = (P == 49) ? 8 : 2;
   static constexpr int kThreads = WPH * HPC * 32;
   static constexpr int kHeadSmem = 3 * TP * kLds * 2;
@@ -66,6 +66,26 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const int bytes = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+// waits until at most `n` of this thread's most recent groups are still in flight (n is a small
+// compile-time-known value after unrolling; the switch keeps the immediate operand form)
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;
+  }
+}
+
 // local token i of crop b -> row of the activation matrix [B*P patches | B class rows | B side rows]
 __device__ __forceinline__ int token_row(int i, int b, int B, int P) {
   return i < P ? b * P + i : (i == P ? B * P + b : B * P + B + b);
@@ -87,34 +107,39 @@ attention_kernel(const act_t* __restrict__ qkv, const float* __restrict__ mask, 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- cooperative load of Q/K/V of the CTA's heads (rows >= TQ zero-filled)
-  for (int idx = threadIdx.x; idx < C::HPC * C::TP * 8; idx += C::kThreads) {
-    const int hl = idx / (C::TP * 8);
-    const int rem = idx - hl * (C::TP * 8);
-    const int i = rem >> 3;
-    const int c = rem & 7;
-    act_t* sQ = reinterpret_cast<act_t*>(smem_raw + hl * C::kHeadSmem);
-    act_t* sK = sQ + C::TP * kLds;
-    act_t* sV = sK + C::TP * kLds;
-    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
-    if (i < C::TQ) {
-      const act_t* src =
-          qkv + static_cast<size_t>(token_row(i, b, B, P)) * ld + (hg * C::HPC + hl) * kDh + c * 8;
-      q = *reinterpret_cast<const uint4*>(src);
-      k = *reinterpret_cast<const uint4*>(src + W);
-      v = *reinterpret_cast<const uint4*>(src + 2 * W);
+  // ---- asynchronous load of Q/K/V (rows >= TQ zero-filled), one cp.async group per 32-key chunk:
+  //      group 0 = Q + keys [0,32), group c = keys [32c, 32c+32).  The chunk loop below waits for
+  //      exactly the group it is about to consume, so the rest of K/V streams in under the math.
+  {
+    act_t* sQw = reinterpret_cast<act_t*>(smem_raw);
+    act_t* sKw = sQw + C::TP * kLds;
+    act_t* sVw = sKw + C::TP * kLds;
+    const act_t* base = qkv + (hg * C::HPC) * kDh;
+    for (int idx = threadIdx.x; idx < C::TP * 8; idx += C::kThreads) {
+      const int i = idx >> 3, c = idx & 7;
+      const bool ok = i < C::TQ;
+      const act_t* src = base + static_cast<size_t>(token_row(ok ? i : 0, b, B, P)) * ld + c * 8;
+      cp_async16_zfill(sQw + i * kLds + c * 8, src, ok);
     }
-    *reinterpret_cast<uint4*>(sQ + i * kLds + c * 8) = q;
-    *reinterpret_cast<uint4*>(sK + i * kLds + c * 8) = k;
-    *reinterpret_cast<uint4*>(sV + i * kLds + c * 8) = v;
+#pragma unroll 1
+    for (int ch = 0; ch < C::NCH; ++ch) {
+      const int rows = min(32, C::TP - ch * 32);
+      for (int idx = threadIdx.x; idx < rows * 8; idx += C::kThreads) {
+        const int i = ch * 32 + (idx >> 3), c = idx & 7;
+        const bool ok = i < C::TQ;
+        const act_t* src = base + static_cast<size_t>(token_row(ok ? i : 0, b, B, P)) * ld + c * 8;
+        cp_async16_zfill(sKw + i * kLds + c * 8, src + W, ok);
+        cp_async16_zfill(sVw + i * kLds + c * 8, src + 2 * W, ok);
+      }
+      cp_async_commit();
+    }
   }
-  __syncthreads();
 
   const int hl = warp / C::WPH;
   const int wq = warp - hl * C::WPH;
   const int h = hg * C::HPC + hl;
   const int row_base = wq * 32;  // this warp's 32 query rows: m-tiles 2wq and 2wq+1
-  if (SIDE && side_only && !(row_base <= C::T && C::T < row_base + 32)) return;
+  const bool idle = SIDE && side_only && !(row_base <= C::T && C::T < row_base + 32);  // keeps hitting the barriers
   const act_t* sQ = reinterpret_cast<const act_t*>(smem_raw + hl * C::kHeadSmem);
   const act_t* sK = sQ + C::TP * kLds;
   const act_t* sV = sK + C::TP * kLds;
@@ -145,6 +170,9 @@ attention_kernel(const act_t* __restrict__ qkv, const float* __restrict__ mask, 
 #pragma unroll
   for (int c = 0; c < C::NCH; ++c) {
     const int key0 = c * 32;
+    cp_async_wait_pending(C::NCH - 1 - c);  // this thread's copies of chunk c (and Q) have landed ...
+    __syncthreads();                        // ... and so have everyone else's
+    if (idle) continue;
     float s[2][4][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -260,7 +288,7 @@ attention_kernel(const act_t* __restrict__ qkv, const float* __restrict__ mask, 
       l += __shfl_xor_sync(0xffffffffu, l, 1);
       l += __shfl_xor_sync(0xffffffffu, l, 2);
       const int i = row_base + mt * 16 + (lane >> 2) + hh * 8;
-      const bool want = side_only ? (SIDE && i == C::T) : (i < C::TQ);
+      const bool want = !idle && (side_only ? (SIDE && i == C::T) : (i < C::TQ));
       if (want && (mt == 0 || second)) {
         const float inv = 1.0f / l;
         act_t* dst = out + static_cast<size_t>(token_row(i, b, B, P)) * W + h * kDh + 2 * (lane & 3);
