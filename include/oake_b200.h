@@ -143,6 +143,30 @@ int oake_encode_crops_u8(oake_handle* h, const uint8_t* arena, const oake_crop_s
  * background.  All device pointers. */
 int oake_object_masks(const float* fg_xyxy, const float* box_xyxy, int B, float* masks, void* stream);
 
+/* ---- cosine classifier of oadp.dp (oadp/dp/classifiers.py:19-112, oadp/dp/utils.py:47-51) -----
+ * Two ops, split where the reference splits its modules, because the todd distiller hooks capture
+ * the OUTPUT of `fc_cls._linear` (configs/dp/models/ *.py): h must exist as a tensor and receives
+ * gradient from both the logits and the distillation loss.  All pointers device, fp32, row-major.
+ *   h      = F.normalize(x W^T + b)                                     NormalizedLinear.forward
+ *   logits = alpha * (h E^T) - shift, columns [ninf_lo, ninf_hi) = -inf BaseClassifier/Classifier/
+ *            E = [text (num_all,512) as stored ; F.normalize(bg) if bg != NULL]   ViLDClassifier.forward
+ * logits has row pitch k_pad (multiple of 128, >= K = num_all + (bg != NULL)); columns >= K are
+ * padding.  in_features must be a multiple of 64 (256 / 1024 in the reference configs). */
+int oake_classifier_workspace_bytes(int N, int in_features, int k_pad, size_t* out_bytes);
+int oake_normalized_linear_fwd(const float* x, const float* w, const float* b, int N, int in_features, float* h,
+                               float* inv_norm, void* ws, size_t ws_bytes, void* stream);
+/* dx [N,in], dw [512,in], db [512] may each be NULL. */
+int oake_normalized_linear_bwd(const float* x, const float* w, const float* h, const float* inv_norm,
+                               const float* dh, int N, int in_features, float* dx, float* dw, float* db, void* ws,
+                               size_t ws_bytes, void* stream);
+int oake_cosine_logits_fwd(const float* h, const float* text, const float* bg, int N, int num_all, int k_pad,
+                           float alpha, float shift, int ninf_lo, int ninf_hi, float* logits, void* ws,
+                           size_t ws_bytes, void* stream);
+/* dlogits [N,k_pad] (entries of -inf / padding columns are ignored); dh [N,512]; dbg [512] or NULL. */
+int oake_cosine_logits_bwd(const float* h, const float* text, const float* bg, const float* dlogits, int N,
+                           int num_all, int k_pad, float alpha, int ninf_lo, int ninf_hi, float* dh, float* dbg,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* Error string of the last failing call on this thread ("" if none). */
 const char* oake_last_error(void);
 /* "f16" or "bf16": element type of `act` tensors. */

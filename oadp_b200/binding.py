@@ -40,6 +40,18 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'oake_resize_u8': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'oake_object_masks': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'oake_classifier_workspace_bytes': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    'oake_normalized_linear_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'oake_normalized_linear_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                             C.c_void_p]),
+    'oake_cosine_logits_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                         C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.c_void_p]),
+    'oake_cosine_logits_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_void_p]),
     'oake_last_error': (C.c_char_p, []),
     'oake_act_dtype': (C.c_char_p, []),
     'oake_abi_version': (C.c_int, []),

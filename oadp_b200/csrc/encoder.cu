@@ -34,6 +34,23 @@ int fail(const char* fmt, ...) {
   return 1;
 }
 
+}  // namespace
+
+namespace oake {
+// shared with classifier.cu: records the thread-local error string, returns 1
+int fail_msg(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+}  // namespace oake
+
+namespace {
+
 enum KClass {
   K_FRONTEND = 0,
   K_GEMM_PATCH,

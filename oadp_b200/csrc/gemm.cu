@@ -226,6 +226,11 @@ __device__ __forceinline__ void epilogue_f32(const GemmEpilogue& ep, uint32_t t_
       for (int j = 0; j < 16; ++j) v[j] = quick_gelu(v[j]);
     }
 #pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + j;
+      v[j] = (col >= ep.ninf_lo && col < ep.ninf_hi) ? -INFINITY : fmaf(ep.alpha, v[j], -ep.shift);
+    }
+#pragma unroll
     for (int j = 0; j < 4; ++j)
       *reinterpret_cast<float4*>(stg_chunk(stg, lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();

@@ -23,6 +23,11 @@ struct GemmEpilogue {
   int ld_res;
   int out_f32;  // 1: fp32 output (bias / activation only), 0: act_t output
   int act;      // 0: identity, 1: QuickGELU  u * sigmoid(1.702 u)
+  // fp32 output only (cosine classifier): y = alpha * y - shift; columns [ninf_lo, ninf_hi) = -inf
+  float alpha = 1.f;
+  float shift = 0.f;
+  int ninf_lo = 0;
+  int ninf_hi = 0;
 };
 
 // Encodes a 2D row-major [rows, cols] act_t tensor as a TMA map with a (box_rows x 64) box and

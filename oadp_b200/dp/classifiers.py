@@ -1,0 +1,236 @@
+"""Cosine classifier -- counterpart of oadp/dp/classifiers.py + `NormalizedLinear` (utils.py:47-51).
+
+Same names, constructor signature (`prompts`, `in_features`, `out_features`[, `scaler`]), attribute
+names the rest of the reference reaches into (`_linear`, `_bg_embedding`, `_embeddings`,
+`_scaler`) and call-time reads of `Globals.training` / `Globals.categories`.  `_linear` stays an
+`nn.Module` invoked through `__call__` whose output is the L2-normalised (N,512) tensor, so the todd
+distiller forward hooks of configs/dp/models/*.py keep working unchanged.
+
+On a CUDA device both halves run on liboake_b200 (tcgen05 GEMMs + fused row kernels, forward and
+backward); there is no PyTorch fallback on CUDA.  CPU tensors raise: the reference's CPU debug mode
+is out of scope for this library (use the oracle in tests).
+Registered in mmdet's `LINEAR_LAYERS` when mmdet is importable, else in a local registry with the
+same decorator form.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import binding
+from .categories import Globals
+
+try:  # pragma: no cover - mmdet is not installed in this environment
+    from mmdet.models.utils.builder import LINEAR_LAYERS
+except Exception:
+
+    class _Registry:
+
+        def __init__(self) -> None:
+            self.module_dict: Dict[str, type] = {}
+
+        def register_module(self, name: Optional[str] = None, force: bool = False, module: Optional[type] = None):
+            def deco(cls: type) -> type:
+                self.module_dict[name or cls.__name__] = cls
+                return cls
+            return deco(module) if module is not None else deco
+
+        def build(self, cfg: Dict[str, Any], **default_args: Any) -> Any:
+            cfg = dict(default_args, **cfg)
+            return self.module_dict[cfg.pop('type')](**cfg)
+
+    LINEAR_LAYERS = _Registry()
+
+DIM = 512
+
+
+def _kpad(k: int) -> int:
+    return (k + 127) // 128 * 128
+
+
+class _Workspace:
+    _cache: Dict[int, torch.Tensor] = {}
+
+    @classmethod
+    def get(cls, device: torch.device, n: int, in_features: int, k_pad: int) -> torch.Tensor:
+        need = C.c_size_t()
+        binding.check(binding.load().oake_classifier_workspace_bytes(n, in_features, k_pad, C.byref(need)))
+        key = device.index or 0
+        buf = cls._cache.get(key)
+        if buf is None or buf.numel() < need.value:
+            buf = torch.empty(need.value, dtype=torch.uint8, device=device)
+            cls._cache[key] = buf
+        return buf
+
+
+def _require_cuda(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise binding.OakeError('oadp_b200 classifier kernels need CUDA tensors (sm_100a); there is no CPU path')
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _NormalizedLinearFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x)
+        lib = binding.load()
+        x32 = x.detach().float().contiguous()
+        w32 = weight.detach().float().contiguous()
+        b32 = bias.detach().float().contiguous()
+        n, in_f = x32.shape
+        h = torch.empty(n, DIM, device=x.device, dtype=torch.float32)
+        inv = torch.empty(n, device=x.device, dtype=torch.float32)
+        ws = _Workspace.get(x.device, n, in_f, 128)
+        binding.check(lib.oake_normalized_linear_fwd(x32.data_ptr(), w32.data_ptr(), b32.data_ptr(), n, in_f,
+                                                     h.data_ptr(), inv.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     _stream(x)))
+        ctx.save_for_backward(x32, w32, h, inv)
+        ctx.in_dtype = x.dtype
+        return h
+
+    @staticmethod
+    def backward(ctx, dh: torch.Tensor):
+        x32, w32, h, inv = ctx.saved_tensors
+        lib = binding.load()
+        n, in_f = x32.shape
+        dh = dh.float().contiguous()
+        need_x, need_w, need_b = ctx.needs_input_grad
+        dx = torch.empty_like(x32) if need_x else None
+        dw = torch.empty_like(w32) if need_w else None
+        db = torch.empty(DIM, device=x32.device) if need_b else None
+        ws = _Workspace.get(x32.device, n, in_f, 128)
+        binding.check(lib.oake_normalized_linear_bwd(
+            x32.data_ptr(), w32.data_ptr(), h.data_ptr(), inv.data_ptr(), dh.data_ptr(), n, in_f,
+            dx.data_ptr() if need_x else None, dw.data_ptr() if need_w else None, db.data_ptr() if need_b else None,
+            ws.data_ptr(), ws.numel(), _stream(dh)))
+        return (dx.to(ctx.in_dtype) if need_x else None), dw, db
+
+
+class _CosineLogitsFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, h: torch.Tensor, text: torch.Tensor, bg: Optional[torch.Tensor], alpha: float, shift: float,
+                ninf_lo: int, ninf_hi: int) -> torch.Tensor:
+        _require_cuda(h)
+        lib = binding.load()
+        h32 = h.detach().float().contiguous()
+        text32 = text.detach().float().contiguous()
+        bg32 = bg.detach().float().contiguous().reshape(-1) if bg is not None else None
+        n, num_all = h32.shape[0], text32.shape[0]
+        k = num_all + (1 if bg is not None else 0)
+        k_pad = _kpad(k)
+        logits = torch.empty(n, k_pad, device=h.device, dtype=torch.float32)
+        ws = _Workspace.get(h.device, n, 1024, k_pad)
+        binding.check(lib.oake_cosine_logits_fwd(h32.data_ptr(), text32.data_ptr(),
+                                                 bg32.data_ptr() if bg32 is not None else None, n, num_all, k_pad,
+                                                 alpha, shift, ninf_lo, ninf_hi, logits.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), _stream(h)))
+        ctx.save_for_backward(h32, text32, bg32 if bg32 is not None else torch.empty(0, device=h.device))
+        ctx.meta = (bg is not None, alpha, ninf_lo, ninf_hi, k, k_pad, bg.shape if bg is not None else None)
+        return logits[:, :k].contiguous()  # callers write -inf into it in place (bbox_heads.py:59)
+
+    @staticmethod
+    def backward(ctx, dlogits: torch.Tensor):
+        h32, text32, bg32 = ctx.saved_tensors
+        has_bg, alpha, ninf_lo, ninf_hi, k, k_pad, bg_shape = ctx.meta
+        lib = binding.load()
+        n, num_all = h32.shape[0], text32.shape[0]
+        dl = torch.zeros(n, k_pad, device=h32.device, dtype=torch.float32)
+        dl[:, :k] = dlogits
+        dh = torch.empty(n, DIM, device=h32.device, dtype=torch.float32)
+        want_bg = has_bg and ctx.needs_input_grad[2]
+        dbg = torch.empty(DIM, device=h32.device) if want_bg else None
+        ws = _Workspace.get(h32.device, n, 1024, k_pad)
+        binding.check(lib.oake_cosine_logits_bwd(h32.data_ptr(), text32.data_ptr(),
+                                                 bg32.data_ptr() if has_bg else None, dl.data_ptr(), n, num_all,
+                                                 k_pad, alpha, ninf_lo, ninf_hi, dh.data_ptr(),
+                                                 dbg.data_ptr() if want_bg else None, ws.data_ptr(), ws.numel(),
+                                                 _stream(dl)))
+        return dh, None, (dbg.reshape(bg_shape) if want_bg else None), None, None, None, None
+
+
+class NormalizedLinear(nn.Linear):
+    """F.normalize(Linear(x)) (utils.py:47-51); the hooked module."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return _NormalizedLinearFn.apply(x, self.weight, self.bias)
+
+
+@LINEAR_LAYERS.register_module()
+class BaseClassifier(nn.Module):
+
+    def __init__(self, *args, prompts: str, in_features: int, out_features: int, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        prompts_ = torch.load(prompts, 'cpu')
+        names = list(prompts_['names'])
+        embeddings: torch.Tensor = prompts_['embeddings']
+        indices = [names.index(name) for name in Globals.categories.all_]
+        embeddings = embeddings[indices].float()
+        num_all = Globals.categories.num_all
+        if out_features == num_all + 1:  # with a learnable background row
+            bg_embedding = nn.Parameter(torch.zeros(1, embeddings.shape[1]))
+            nn.init.xavier_uniform_(bg_embedding)
+        elif out_features == num_all:
+            bg_embedding = None
+        else:
+            raise RuntimeError(str(out_features))
+        self._prompts = prompts_
+        self.register_buffer('_embeddings', embeddings, persistent=False)
+        self._bg_embedding = bg_embedding
+        self._linear = NormalizedLinear(in_features, embeddings.shape[1])
+
+    @property
+    def embeddings(self) -> torch.Tensor:
+        """Materialised (K,512) table, for code that reads it; the kernels build it on the fly."""
+        if self._bg_embedding is None:
+            return self._embeddings
+        return torch.cat([self._embeddings, nn.functional.normalize(self._bg_embedding)])
+
+    def _affine(self) -> tuple:
+        return 1.0, 0.0
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        h = self._linear(x)  # through __call__: forward hooks see the normalised tensor
+        lo = hi = 0
+        if Globals.training:  # novel categories are invisible while training (classifiers.py:62-67)
+            lo, hi = Globals.categories.num_bases, Globals.categories.num_all
+        alpha, shift = self._affine()
+        return _CosineLogitsFn.apply(h, self._embeddings, self._bg_embedding, alpha, shift, lo, hi)
+
+
+@LINEAR_LAYERS.register_module()
+class Classifier(BaseClassifier):
+    """logits * scaler - bias, both read once from the prompts file (classifiers.py:71-83)."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self._scaler = self._prompts['scaler'].item()
+        self._bias = self._prompts['bias'].item()
+
+    def _affine(self) -> tuple:
+        return float(self._scaler), float(self._bias)
+
+
+@LINEAR_LAYERS.register_module()
+class ViLDClassifier(BaseClassifier):
+    """logits / scaler, scaler chosen by Globals.training at call time (classifiers.py:91-112)."""
+
+    def __init__(self, *args, scaler: Optional[Dict[str, float]] = None, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        if scaler is None:
+            scaler = dict(train=0.007, val=0.01)  # the reference's defaults (inverse of its configs)
+        self._scaler = scaler
+
+    @property
+    def scaler(self) -> float:
+        return self._scaler['train'] if Globals.training else self._scaler['val']
+
+    def _affine(self) -> tuple:
+        return 1.0 / float(self.scaler), 0.0
