@@ -201,7 +201,11 @@ attention_kernel(const act_t* __restrict__ qkv, const float* __restrict__ mask, 
       }
     }
 
-    // ---- scale, mask, online softmax (base 2)
+    // ---- scale, mask, online softmax (base 2).  Chunks that hold only patch keys need no masking
+    //      (decided at compile time after unrolling); the running maximum is only advanced -- and
+    //      O / l rescaled -- when some row of the warp outgrew it by more than 2^8, so that in the
+    //      steady state a chunk costs one FMUL + one FADD + one EX2 per score.
+    const bool interior = (key0 + 32 <= P);
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       float mx[2] = {-INFINITY, -INFINITY};
@@ -212,33 +216,44 @@ attention_kernel(const act_t* __restrict__ qkv, const float* __restrict__ mask, 
           const int col = key0 + n * 8 + 2 * (lane & 3) + (e & 1);
           const int hh = e >> 1;
           float v = s[mt][n][e] * scale;
-          bool valid = col < C::T;  // main rows see the P patches and the class token
-          if (SIDE && is_y[mt][hh]) {
-            // objects.py:204-247: y sees the patches (bias -100 * mask) and itself (bias 0), not CLS
-            valid = col < P || col == C::T;
-            if (col < P) v += -100.0f * kLog2e * __ldg(mask + static_cast<size_t>(b) * P + col);
+          if (interior) {
+            if (SIDE && is_y[mt][hh]) v += -100.0f * kLog2e * __ldg(mask + static_cast<size_t>(b) * P + col);
+          } else {
+            bool valid = col < C::T;  // main rows see the P patches and the class token
+            if (SIDE && is_y[mt][hh]) {
+              // objects.py:204-247: y sees the patches (bias -100 * mask) and itself (bias 0), not CLS
+              valid = col < P || col == C::T;
+              if (col < P) v += -100.0f * kLog2e * __ldg(mask + static_cast<size_t>(b) * P + col);
+            }
+            v = valid ? v : -INFINITY;
           }
-          v = valid ? v : -INFINITY;
           s[mt][n][e] = v;
           mx[hh] = fmaxf(mx[hh], v);
         }
       }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        float m = mx[hh];
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        const float m_new = fmaxf(mrow[mt][hh], m);
-        // a chunk may be fully masked for the side row (m_new stays -inf only before any valid key)
-        const float m_use = m_new == -INFINITY ? 0.f : m_new;
-        const float corr = exp2f(mrow[mt][hh] - m_use);
-        mrow[mt][hh] = m_new;
-        lrow[mt][hh] *= corr;
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+        mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+      }
+      const bool grow = (mx[0] > mrow[mt][0] + 8.f) || (mx[1] > mrow[mt][1] + 8.f);
+      if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll
-        for (int n = 0; n < kDh / 8; ++n) {
-          o[mt][n][2 * hh] *= corr;
-          o[mt][n][2 * hh + 1] *= corr;
+        for (int hh = 0; hh < 2; ++hh) {
+          const float m_new = fmaxf(mrow[mt][hh], mx[hh]);
+          const float corr = exp2f(mrow[mt][hh] - m_new);  // first chunk: exp2(-inf) = 0
+          mrow[mt][hh] = m_new;
+          lrow[mt][hh] *= corr;
+#pragma unroll
+          for (int n = 0; n < kDh / 8; ++n) {
+            o[mt][n][2 * hh] *= corr;
+            o[mt][n][2 * hh + 1] *= corr;
+          }
         }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const float m_use = mrow[mt][hh];
         float part = 0.f;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {

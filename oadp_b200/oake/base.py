@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import argparse
 import concurrent.futures
+import itertools
 import pathlib
 import time
 from abc import ABC, abstractmethod
@@ -131,8 +132,8 @@ class BaseValidator(ABC, Generic[T]):
         return self.DATASET(**config)
 
     @abstractmethod
-    def _encode(self, items: List[Item]) -> List[Any]:
-        """-> one result per item, in the exact layout the reference stores."""
+    def _submit(self, items: List[Item]):
+        """-> a `Pending` whose result() is one entry per item, in the layout the reference stores."""
 
     # ---------------------------------------------------------------------------------- the loop
     def _shard(self) -> List[int]:
@@ -160,11 +161,21 @@ class BaseValidator(ABC, Generic[T]):
         indices = self._shard()
         if Store.DRY_RUN:
             indices = indices[:3]
-        done, crops, t0, pending = 0, 0, time.perf_counter(), []
-        for batch in self._batches(indices):
-            results = self._encode(batch)
-            for item, result in zip(batch, results):
+        done, t0, pending = 0, time.perf_counter(), []
+        in_flight = None  # (batch, Pending): the GPU works on it while the next batch is decoded / staged
+
+        def drain(entry):
+            batch_, ticket = entry
+            for item, result in zip(batch_, ticket.result()):
                 pending.append(self._writer.submit(torch.save, result, item.output))
+
+        for batch in itertools.chain(self._batches(indices), [None]):
+            nxt = (batch, self._submit(batch)) if batch is not None else None
+            if in_flight is not None:
+                drain(in_flight)
+            in_flight = nxt
+            if batch is None:
+                break
             done += len(batch)
             if done % max(self._log_interval, 1) < len(batch):
                 dt = time.perf_counter() - t0

@@ -17,8 +17,8 @@ class Dataset(BaseDataset):
 class Validator(BaseValidator):
     DATASET = Dataset
 
-    def _encode(self, items: List[Item]) -> List[Any]:
-        return self._pipeline.encode_globals([it.image for it in items])
+    def _submit(self, items: List[Item]):
+        return self._pipeline.submit_globals([it.image for it in items])
 
 
 if __name__ == '__main__':

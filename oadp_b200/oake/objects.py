@@ -92,8 +92,8 @@ class Validator(BaseValidator):
         config.pop('transform', None)
         return DatasetRegistry.build(config, default_config=dict(grid=self._model.visual.grid))
 
-    def _encode(self, items: List[Item]) -> List[Any]:
-        return self._pipeline.encode_objects([it.image for it in items], [it.extra for it in items],
+    def _submit(self, items: List[Item]):
+        return self._pipeline.submit_objects([it.image for it in items], [it.extra for it in items],
                                              dry_run=Store.DRY_RUN)
 
 

@@ -49,19 +49,54 @@ class _Staging:
         self.dev[:nbytes].copy_(self.host[:nbytes], non_blocking=True)
 
 
+class _Slot:
+    """One in-flight batch: its staging buffers, its result buffer and the event that ends it."""
+
+    def __init__(self, device: torch.device) -> None:
+        self.arena = _Staging(device)  # images | pyramid levels | resized crops
+        self.meta = _Staging(device)  # resize jobs | crop descriptors | fg | box
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.out_host: Optional[torch.Tensor] = None
+        self.event = torch.cuda.Event()
+        self.busy = False
+
+
+class Pending:
+    """Handle of a submitted batch; `result()` waits for the GPU and returns what `encode_*` returns."""
+
+    def __init__(self, pipe: 'OakePipeline', slot: _Slot, host: torch.Tensor, finish) -> None:
+        self._pipe, self._slot, self._host, self._finish = pipe, slot, host, finish
+        self._done = None
+
+    def result(self):
+        if self._done is None:
+            self._slot.event.synchronize()
+            self._slot.busy = False
+            if int(self._slot.err_host.item()) != 0:
+                self._slot.err.zero_()
+                raise binding.OakeError('oake_resize_u8: a crop exceeded the resize kernel limits')
+            self._done = self._finish(self._host.clone())
+        return self._done
+
+
 class OakePipeline:
+    """Two slots: while the GPU works on one batch the host stages (and uploads) the next one."""
 
     def __init__(self, engine: OakeEngine) -> None:
         self.engine = engine
         self.lib = engine.lib
         self.device = engine.device
-        self._arena = _Staging(self.device)  # images | pyramid levels | resized crops
-        self._meta = _Staging(self.device)  # resize jobs | crop descriptors | fg | box
-        self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._out_host: Optional[torch.Tensor] = None
+        self._slots = [_Slot(self.device), _Slot(self.device)]
+        self._cur = 0
         self.h2d_bytes = 0  # of the last call
         self.d2h_bytes = 0
         self.frontend_launches = 0  # resize / mask kernels launched so far
+
+    # the slot being filled
+    _arena = property(lambda self: self._slots[self._cur].arena)
+    _meta = property(lambda self: self._slots[self._cur].meta)
+    _err = property(lambda self: self._slots[self._cur].err)
 
     # ------------------------------------------------------------------------------ internals
     def _stream(self) -> int:
@@ -76,14 +111,30 @@ class OakePipeline:
             off += _align(im.shape[0] * im.shape[1] * 3)
         return offs, off
 
-    def _run(self, images: Sequence[np.ndarray], img_offs: List[int], img_bytes: int, arena_bytes: int,
-             stages: List[np.ndarray], crops: np.ndarray, variant: int,
-             fg: Optional[np.ndarray] = None, box: Optional[np.ndarray] = None) -> torch.Tensor:
-        """Uploads, launches every stage, encodes, returns the HOST fp16 (n_crops, 512) tensor."""
-        job = self.stage(images, img_offs, img_bytes, arena_bytes, stages, crops, variant, fg, box)
+    def _submit(self, plan_args: tuple, finish) -> Pending:
+        """stage -> H2D -> kernels -> D2H, all asynchronous on the current stream."""
+        nxt = self._cur ^ 1
+        slot = self._slots[nxt]
+        if slot.busy:  # its previous batch has not been collected yet: wait for the GPU side of it
+            slot.event.synchronize()
+        self._cur = nxt
+        job = self.stage(*plan_args)
         self.upload(job)
         out = self.launch(job)
-        return self.download(out)
+        n = out.shape[0]
+        if slot.out_host is None or slot.out_host.shape[0] < n:
+            slot.out_host = torch.empty(max(n, 4096), OUT_DIM, dtype=torch.float16, pin_memory=True)
+        host = slot.out_host[:n]
+        host.copy_(out, non_blocking=True)
+        slot.err_host.copy_(slot.err, non_blocking=True)
+        slot.event.record(torch.cuda.current_stream(self.device))
+        slot.busy = True
+        self.d2h_bytes = n * OUT_DIM * 2 + 4
+        return Pending(self, slot, host, finish)
+
+    def _run(self, *plan_args) -> torch.Tensor:
+        """Synchronous form: returns the HOST fp16 (n_crops, 512) tensor."""
+        return self._submit(plan_args, lambda emb: emb).result()
 
     # The three phases are public so that bench.py can time the device-resident part alone.
     def stage(self, images, img_offs, img_bytes, arena_bytes, stages, crops, variant, fg=None, box=None) -> dict:
@@ -154,23 +205,15 @@ class OakePipeline:
                     ws.data_ptr(), ws.numel(), st))
         return out
 
-    def download(self, out: torch.Tensor) -> torch.Tensor:
-        n = out.shape[0]
-        if self._out_host is None or self._out_host.shape[0] < n:
-            self._out_host = torch.empty(max(n, 4096), OUT_DIM, dtype=torch.float16, pin_memory=True)
-        host = self._out_host[:n]
-        host.copy_(out, non_blocking=True)
-        err = self._err.to('cpu', non_blocking=False)  # synchronises the stream
-        self.d2h_bytes = n * OUT_DIM * 2 + 4
-        if int(err.item()) != 0:
-            self._err.zero_()
-            raise binding.OakeError('oake_resize_u8: a crop exceeded the resize kernel limits')
-        return host.clone()
-
     # ------------------------------------------------------------------------------ public API
+    # `encode_*` block until the result is on the host; `submit_*` return a `Pending` at once so that
+    # the caller can prepare / submit the next batch while the GPU works (validators, bench e2e).
     def encode_globals(self, images: Sequence[np.ndarray]) -> List[torch.Tensor]:
-        emb = self._run(*self.plan_globals(images))
-        return [emb[i] for i in range(len(images))]
+        return self.submit_globals(images).result()
+
+    def submit_globals(self, images: Sequence[np.ndarray]) -> Pending:
+        n = len(images)
+        return self._submit(self.plan_globals(images), lambda emb: [emb[i] for i in range(n)])
 
     def plan_globals(self, images: Sequence[np.ndarray]) -> tuple:
         offs, img_bytes = self._place_images(images)
@@ -186,13 +229,20 @@ class OakePipeline:
         return (images, offs, img_bytes, img_bytes + len(images) * CROP_BYTES, [jobs], crops, binding.VARIANT_T50)
 
     def encode_blocks(self, images: Sequence[np.ndarray]) -> List[Dict[str, torch.Tensor]]:
+        return self.submit_blocks(images).result()
+
+    def submit_blocks(self, images: Sequence[np.ndarray]) -> Pending:
         args, plans, counts = self.plan_blocks(images)
-        emb = self._run(*args)
-        out, s = [], 0
-        for plan, n in zip(plans, counts):
-            out.append(dict(embeddings=emb[s:s + n], bboxes=torch.tensor(plan.bboxes, dtype=torch.float32).half()))
-            s += n
-        return out
+
+        def finish(emb: torch.Tensor):
+            out, s = [], 0
+            for plan, n in zip(plans, counts):
+                out.append(dict(embeddings=emb[s:s + n],
+                                bboxes=torch.tensor(plan.bboxes, dtype=torch.float32).half()))
+                s += n
+            return out
+
+        return self._submit(args, finish)
 
     def plan_blocks(self, images: Sequence[np.ndarray]):
         offs, img_bytes = self._place_images(images)
@@ -232,15 +282,22 @@ class OakePipeline:
 
     def encode_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray],
                        dry_run: bool = False) -> List[Dict[str, torch.Tensor]]:
+        return self.submit_objects(images, proposals, dry_run).result()
+
+    def submit_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray],
+                       dry_run: bool = False) -> Pending:
         args, plans = self.plan_objects(images, proposals, dry_run)
-        emb = self._run(*args)
-        out, s = [], 0
-        for plan in plans:
-            n = plan.bboxes.shape[0]
-            out.append(dict(embeddings=emb[s:s + n], bboxes=torch.from_numpy(plan.bboxes).half(),
-                            objectness=torch.from_numpy(plan.objectness).half()))
-            s += n
-        return out
+
+        def finish(emb: torch.Tensor):
+            out, s = [], 0
+            for plan in plans:
+                n = plan.bboxes.shape[0]
+                out.append(dict(embeddings=emb[s:s + n], bboxes=torch.from_numpy(plan.bboxes).half(),
+                                objectness=torch.from_numpy(plan.objectness).half()))
+                s += n
+            return out
+
+        return self._submit(args, finish)
 
     def plan_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray], dry_run: bool = False):
         offs, img_bytes = self._place_images(images)
