@@ -304,7 +304,7 @@ int oake_normalized_linear_fwd(const float* x, const float* w, const float* b, i
   cast_kernel<<<static_cast<unsigned>((nx / 4 + 256) / 256), 256, 0, st>>>(x, x_act, nx);
   cast_kernel<<<static_cast<unsigned>((nw / 4 + 256) / 256), 256, 0, st>>>(w, w_act, nw);
   CUtensorMap tmA, tmW;
-  if (make_tmap_act_2d(&tmA, x_act, N, in_features, 128) || make_tmap_act_2d(&tmW, w_act, kDim, in_features, 256))
+  if (make_tmap_act_2d(&tmA, x_act, N, in_features, 128) || make_tmap_act_2d(&tmW, w_act, kDim, in_features, gemm_block_n(kDim)))
     return fail_msg("cuTensorMapEncodeTiled failed");
   GemmEpilogue ep{b, nullptr, nullptr, nullptr, nullptr, h_raw, kDim, 0, 1, 0};
   CK(launch_gemm(st, tmA, tmW, N, kDim, in_features, ep, num_sms()));
@@ -411,7 +411,7 @@ int oake_cosine_logits_bwd(const float* h, const float* text, const float* bg, c
                                                                              ninf_hi, maxabs);
   pack_embeddings_kernel<<<(k_pad + 7) / 8, 256, 0, st>>>(text, bg, num_all, k_pad, e_act, et_act);
   CUtensorMap tmA, tmB;
-  if (make_tmap_act_2d(&tmA, dy_act, N, k_pad, 128) || make_tmap_act_2d(&tmB, et_act, kDim, k_pad, 256))
+  if (make_tmap_act_2d(&tmA, dy_act, N, k_pad, 128) || make_tmap_act_2d(&tmB, et_act, kDim, k_pad, gemm_block_n(kDim)))
     return fail_msg("cuTensorMapEncodeTiled failed");
   GemmEpilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, dh, kDim, 0, 1, 0};
   CK(launch_gemm(st, tmA, tmB, N, kDim, k_pad, ep, num_sms()));

@@ -9,6 +9,13 @@
 // objects.py:330), and it absorbs ln_1 / ln_2 (LayerNorm folded into the consumer's epilogue,
 // row statistics emitted by the producer's epilogue).
 //
+// CTA pairs (`cta_group::2`, default for N % 256 == 0): the two CTAs of a cluster own one 256x256
+// output tile; each loads its 128 A rows and HALF of the W tile, one thread of the leader CTA
+// issues 256x256x16 MMAs that read both shared memories, and each CTA's TMEM receives its own 128
+// accumulator rows.  Per MMA this cuts the TMA->smem and L2->SM traffic of a CTA from 48 KB to
+// 32 KB per k-block (the 1-CTA tile is fed at ~96 B/clk/SM, close to what shared memory sustains
+// next to the epilogue's own traffic).
+//
 // Structure (one CTA per SM, 384 threads):
 //   warp 0     : TMA producer   -- cp.async.bulk.tensor 128x64 A tile + BNx64 W tile per stage,
 //                                  128B-swizzled, completion on the stage's `full` mbarrier
@@ -23,6 +30,7 @@
 // Tiles are walked n-fastest so the CTAs running concurrently share the A rows in L2; the
 // weights (<= 4.7 MB) stay L2-resident.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -42,11 +50,22 @@ enum EpiMode {
   EPI_RES = 2,  // act out: bias + act residual (+ row statistics)
 };
 
-template <int BN>
+// CTA-pair mode for the 256-wide tiles (128-wide tiles stay 1-CTA).  $OAKE_GEMM_CTA_GROUP=1|2
+// overrides the default once per process (A/B measurements); it also decides the W tensor-map box.
+int cta_group() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("OAKE_GEMM_CTA_GROUP");
+    v = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
+template <int BN, int CG = 1>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
   static constexpr int kWarpCols = BN / 2;                  // columns owned by one epilogue warp
@@ -245,11 +264,11 @@ __device__ __forceinline__ void epilogue_f32(const GemmEpilogue& ep, uint32_t t_
   }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     int M, int N, int K, GemmEpilogue ep) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -266,10 +285,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BM - 1) / BM;
+  const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;  // 0 = leader of the pair
+  const int num_m = (M + BM * CG - 1) / (BM * CG);  // tiles of CG * 128 rows
   const int num_n = N / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = K / BK;
+  const int first_tile = blockIdx.x / CG;
+  const int tile_step = gridDim.x / CG;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -282,13 +304,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], kEpiWarps * CG);  // one arrive per epilogue warp of the pair
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  if (warp == 2) {
+    if (CG == 2)
+      tmem_alloc_2cta<C::kTmemCols>(tmem_ptr);
+    else
+      tmem_alloc<C::kTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -297,14 +325,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / num_n;
         const int n_blk = tile - m_blk * num_n;
+        const int a_row = (m_blk * CG + cta_rank) * BM;                // this CTA's 128 rows of A
+        const int w_row = n_blk * BN + cta_rank * (BN / CG);           // this CTA's share of the W tile
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          tma_load_2d(sA + stage * C::kABytes, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sB + stage * C::kBBytes, &tmW, &full_bar[stage], kb * BK, n_blk * BN);
+          if (CG == 2) {
+            // both CTAs' bytes are accounted on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes * 2);
+            tma_load_2d_2cta(sA + stage * C::kABytes, &tmA, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d_2cta(sB + stage * C::kBBytes, &tmW, &full_bar[stage], kb * BK, w_row);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+            tma_load_2d(sA + stage * C::kABytes, &tmA, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d(sB + stage * C::kBBytes, &tmW, &full_bar[stage], kb * BK, w_row);
+          }
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -312,16 +349,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 && cta_rank == 0) {
+    // -------------------------------------------------------------------- MMA issuer (leader CTA)
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_f16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue(s) drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = 0; kb < num_k; ++kb) {
@@ -333,15 +370,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t a_desc = make_smem_desc_k_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t b_desc = make_smem_desc_k_sw128(b_addr + k * UMMA_K * 2);
-            umma_f16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2)
+              umma_f16_2cta(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_f16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs) when these MMAs retire
+          if (CG == 2)
+            umma_commit_2cta(&empty_bar[stage]);
+          else
+            umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (CG == 2)  // accumulator complete -> both CTAs' epilogues
+          umma_commit_2cta(&tmem_full_bar[acc]);
+        else
+          umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -357,10 +404,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* vec = reinterpret_cast<float*>(vec_base + e * C::kVecBytes);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n;
       const int n_blk = tile - m_blk * num_n;
-      const int row0 = m_blk * BM + q * 32;
+      const int row0 = (m_blk * CG + cta_rank) * BM + q * 32;
       const int col_base = n_blk * BN + ch * C::kWarpCols;
       // Everything that does not depend on the accumulator is fetched before waiting for it.
       if (lane * 4 < C::kWarpCols) {
@@ -409,7 +456,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         epilogue_act<BN, MODE>(ep, t_warp, stg, vec, row0, col_base, M, lane, res, ln);
       tc_fence_before();
       __syncwarp();  // every lane is done with TMEM and with `vec` before they are handed back
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2)  // the MMA issuer lives in the leader CTA: arrive on ITS barrier
+          mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+        else
+          mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -419,9 +471,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();  // nobody frees TMEM / exits while the peer may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    if (CG == 2)
+      tmem_dealloc_2cta<C::kTmemCols>(tmem_base);
+    else
+      tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 
@@ -471,29 +527,41 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int CG>
 cudaError_t launch_gemm_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N,
                              int K, const GemmEpilogue& ep, int num_sms) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, CG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * (N / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tcgen05_kernel<BN, MODE><<<grid, kThreads, C::kSmemBytes, st>>>(tmA, tmW, M, N, K, ep);
-  return cudaGetLastError();
+  const int tiles = ((M + BM * CG - 1) / (BM * CG)) * (N / BN);
+  const int slots = num_sms / CG;
+  const int grid = (tiles < slots ? tiles : slots) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, CG>, tmA, tmW, M, N, K, ep);
 }
 
-template <int BN>
+template <int BN, int CG>
 cudaError_t launch_gemm_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N, int K,
                            const GemmEpilogue& ep, int num_sms) {
-  if (ep.out_f32) return launch_gemm_inst<BN, EPI_F32>(st, tmA, tmW, M, N, K, ep, num_sms);
-  if (ep.residual != nullptr) return launch_gemm_inst<BN, EPI_RES>(st, tmA, tmW, M, N, K, ep, num_sms);
-  return launch_gemm_inst<BN, EPI_ACT>(st, tmA, tmW, M, N, K, ep, num_sms);
+  if (ep.out_f32) return launch_gemm_inst<BN, EPI_F32, CG>(st, tmA, tmW, M, N, K, ep, num_sms);
+  if (ep.residual != nullptr) return launch_gemm_inst<BN, EPI_RES, CG>(st, tmA, tmW, M, N, K, ep, num_sms);
+  return launch_gemm_inst<BN, EPI_ACT, CG>(st, tmA, tmW, M, N, K, ep, num_sms);
 }
 
 }  // namespace
@@ -517,7 +585,8 @@ int make_tmap_act_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+// rows of the W tensor-map box: a CTA loads BN / cta_group rows of W per stage
+int gemm_block_n(int N) { return (N % 256 == 0) ? 256 / cta_group() : 128; }
 
 cudaError_t launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N,
                         int K, const GemmEpilogue& ep, int num_sms) {
@@ -528,8 +597,11 @@ cudaError_t launch_gemm(cudaStream_t st, const CUtensorMap& tmA, const CUtensorM
   if (ep.colsum && (!ep.ln_stats || !ep.bias || ep.residual)) return cudaErrorInvalidValue;
   if (ep.residual && ep.act != 0) return cudaErrorInvalidValue;
   if (ep.out_stats && (!ep.residual || N % 256 != 0 || N > 128 * kStatSlots)) return cudaErrorInvalidValue;
-  if (gemm_block_n(N) == 256) return launch_gemm_bn<256>(st, tmA, tmW, M, N, K, ep, num_sms);
-  return launch_gemm_bn<128>(st, tmA, tmW, M, N, K, ep, num_sms);
+  if (N % 256 == 0) {
+    if (cta_group() == 2) return launch_gemm_bn<256, 2>(st, tmA, tmW, M, N, K, ep, num_sms);
+    return launch_gemm_bn<256, 1>(st, tmA, tmW, M, N, K, ep, num_sms);
+  }
+  return launch_gemm_bn<128, 1>(st, tmA, tmW, M, N, K, ep, num_sms);
 }
 
 cudaError_t launch_gemm_simt(cudaStream_t st, const act_t* A, const act_t* W, int M, int N, int K,
