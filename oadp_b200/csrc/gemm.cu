@@ -70,9 +70,9 @@ struct Cfg {
   static constexpr int kBarBytes = 256;
   static constexpr int kWarpCols = BN / 2;                  // columns owned by one epilogue warp
   static constexpr int kStgBytes = 32 * 64;                 // 32 rows x 64 B, XOR-swizzled
-  static constexpr int kVecBytes = 2 * kWarpCols * 4;       // bias + colsum of the warp's columns
+  static constexpr int kVecBytes = 2 * kWarpCols * 4;       // bias + colsum of the warp's columns (x2: double buffered)
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + kBarBytes + kEpiWarps * (kStgBytes + kVecBytes) + 1024;
+      kStages * kStageBytes + kBarBytes + kEpiWarps * (kStgBytes + 2 * kVecBytes) + 1024;
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -107,7 +107,7 @@ struct RowLn {
 template <int BN, int MODE>
 __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_warp, uint8_t* stg,
                                              const float* vec, int row0, int col_base, int M, int lane,
-                                             uint4 (&res)[4], const RowLn ln) {
+                                             uint4 (&res)[4], const RowLn ln, int next_row0, int next_col_base) {
   constexpr int WC = Cfg<BN>::kWarpCols;
   constexpr int NP = WC / 32;
   const int sub_r = lane >> 2;  // coalesced phase: 8 rows per instruction, 4 lanes x 16 B per row
@@ -124,14 +124,16 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
     if (MODE == EPI_RES) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) *stg_chunk(stg, 8 * i + sub_r, sub_c) = res[i];
-      if (pc + 1 < NP) {  // next piece's residual, in flight during the math below
+      {  // next piece's residual (or the first piece of the warp's NEXT tile), in flight during the math
+        const bool same = pc + 1 < NP;
+        const int nr0 = same ? row0 : next_row0;
+        const int nc0 = same ? col0 + 32 : next_col_base;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int r = row0 + 8 * i + sub_r;
+          const int r = nr0 + 8 * i + sub_r;
           res[i] = make_uint4(0, 0, 0, 0);
-          if (r < M)
-            res[i] = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(r) * ep.ld_res + col0 + 32 +
-                                                     sub_c * 8);
+          if (r < M)  // next_row0 >= M when there is no next tile
+            res[i] = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(r) * ep.ld_res + nc0 + sub_c * 8);
         }
       }
       __syncwarp();
@@ -391,42 +393,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = e & 3;    // == warp % 4: the TMEM lane quarter this warp may read
     const int ch = e >> 2;  // which half of the tile's columns
     uint8_t* stg = stg_base + e * C::kStgBytes;
-    float* vec = reinterpret_cast<float*>(vec_base + e * C::kVecBytes);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    float* vec2 = reinterpret_cast<float*>(vec_base + e * 2 * C::kVecBytes);  // two buffers, one per tile parity
+    const bool fold = MODE == EPI_ACT && ep.colsum != nullptr;
+
+    // Per-tile inputs that do not depend on the accumulator (column vectors, row statistics, first
+    // residual piece) are requested ONE TILE AHEAD: in the epilogue-bound regime the next
+    // accumulator is already complete when a tile ends, so anything requested at the top of a tile
+    // would be waited for at full L2 / HBM latency.
+    auto coords = [&](int tile, int& row0, int& col_base) {
       const int m_blk = tile / num_n;
       const int n_blk = tile - m_blk * num_n;
-      const int row0 = (m_blk * CG + cta_rank) * BM + q * 32;
-      const int col_base = n_blk * BN + ch * C::kWarpCols;
-      // Everything that does not depend on the accumulator is fetched before waiting for it.
+      row0 = (m_blk * CG + cta_rank) * BM + q * 32;
+      col_base = n_blk * BN + ch * C::kWarpCols;
+    };
+    auto request_vec = [&](float* vec, int col_base) {
       if (lane * 4 < C::kWarpCols) {
         if (ep.bias != nullptr) cp_async16(vec + lane * 4, ep.bias + col_base + lane * 4);
-        if (MODE == EPI_ACT && ep.colsum != nullptr)
-          cp_async16(vec + C::kWarpCols + lane * 4, ep.colsum + col_base + lane * 4);
+        if (fold) cp_async16(vec + C::kWarpCols + lane * 4, ep.colsum + col_base + lane * 4);
       }
-      uint4 res[4];
-      RowLn ln{1.f, 0.f};
-      if (MODE == EPI_RES) {
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    float4 st[kStatSlots / 2];
+    auto request_stats = [&](int row0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = row0 + 8 * i + (lane >> 2);
-          res[i] = make_uint4(0, 0, 0, 0);
-          if (r < M)
-            res[i] = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(r) * ep.ld_res + col_base +
-                                                     (lane & 3) * 8);
-        }
-      }
-      if (MODE == EPI_ACT && ep.colsum != nullptr && row0 + lane < M) {
+      for (int i = 0; i < kStatSlots / 2; ++i) st[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fold && row0 + lane < M) {
         const float4* sp = reinterpret_cast<const float4*>(ep.ln_stats + static_cast<size_t>(row0 + lane) * kStatSlots);
+#pragma unroll
+        for (int i = 0; i < kStatSlots / 2; ++i) st[i] = sp[i];
+      }
+    };
+    uint4 res[4];
+    auto request_res = [&](int row0, int col_base) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = row0 + 8 * i + (lane >> 2);
+        res[i] = make_uint4(0, 0, 0, 0);
+        if (MODE == EPI_RES && r < M)
+          res[i] = *reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(r) * ep.ld_res + col_base +
+                                                   (lane & 3) * 8);
+      }
+    };
+
+    int acc = 0, buf = 0;
+    uint32_t acc_phase = 0;
+    int row0 = M, col_base = 0;
+    if (first_tile < num_tiles) {
+      coords(first_tile, row0, col_base);
+      request_vec(vec2, col_base);
+      request_stats(row0);
+      request_res(row0, col_base);
+    }
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      float* vec = vec2 + buf * (2 * C::kWarpCols);
+      RowLn ln{1.f, 0.f};
+      if (fold) {
         float sx = 0.f, sxx = 0.f;
 #pragma unroll
         for (int i = 0; i < kStatSlots / 2; ++i) {
-          const float4 t = sp[i];
-          sx += t.x;
-          sx += t.z;
-          sxx += t.y;
-          sxx += t.w;
+          sx += st[i].x;
+          sx += st[i].z;
+          sxx += st[i].y;
+          sxx += st[i].w;
         }
         const float inv_k = 1.0f / static_cast<float>(K);
         const float mean = sx * inv_k;
@@ -434,16 +462,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ln.rstd = rsqrtf(var + 1e-5f);
         ln.nmr = -mean * ln.rstd;
       }
+      // requests for the next tile of this warp
+      int next_row0 = M, next_col_base = 0;
+      const int next = tile + tile_step;
+      if (next < num_tiles) coords(next, next_row0, next_col_base);
+      request_vec(vec2 + (buf ^ 1) * (2 * C::kWarpCols), next < num_tiles ? next_col_base : col_base);
+      request_stats(next_row0);
+
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      cp_async_wait_all();
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // this tile's vectors (all but the newest group)
       __syncwarp();
       const uint32_t t_warp = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(acc * BN + ch * C::kWarpCols);
       if (MODE == EPI_F32)
         epilogue_f32<BN>(ep, t_warp, stg, vec, row0, col_base, M, lane);
       else
-        epilogue_act<BN, MODE>(ep, t_warp, stg, vec, row0, col_base, M, lane, res, ln);
+        epilogue_act<BN, MODE>(ep, t_warp, stg, vec, row0, col_base, M, lane, res, ln, next_row0, next_col_base);
       tc_fence_before();
       __syncwarp();  // every lane is done with TMEM and with `vec` before they are handed back
       if (lane == 0) {
@@ -456,7 +491,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc = 0;
         acc_phase ^= 1;
       }
+      buf ^= 1;
+      row0 = next_row0;
+      col_base = next_col_base;
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   }
 
   tc_fence_before();
