@@ -39,6 +39,9 @@ GFLOP_T50 = 8.818  # algorithmic GFLOP per crop, T=50
 GFLOP_T197 = 33.552  # T=197 + side stream with shared K/V
 WEIGHT_SEED = 1234
 PROPOSALS_PER_IMAGE = 300
+# dram__bytes_read.sum + dram__bytes_write.sum of one c_fc launch at M = 94 644 (478 objects crops), from
+# profiles/r1_04_ncu_gemm_summary.txt; algorithmic bytes of that launch: 145 MB (A) + 4.7 MB (W) + 581 MB (out)
+NCU_TRAFFIC_FC1 = 685.8e6
 
 
 def peaks():
@@ -96,7 +99,7 @@ def make_inputs(n_images: int, rank: int):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the CPU oracle on a bounded sample of the same workload
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(workload: str, n_images: int, steps: int, warmup: int, sample_objects: int = 24):
+def cpu_reference(workload: str, n_images: int, steps: int, warmup: int, sample_objects: int = 96):
     import PIL.Image
     import torch
     from oracle import frontend as ofe
@@ -328,7 +331,7 @@ def main() -> None:
         achieved = d['flops'] / (d['ms'] * 1e-3) / 1e12
         all_ach = sum(v['flops'] for v in gemm.values()) / (sum(v['ms'] for v in gemm.values()) * 1e-3) / 1e12
         roof = dict(bound='tensor', kernel=f'gemm_tcgen05_kernel ({dom})', achieved=achieved, peak=pk['tflops_sustained'],
-                    unit='TFLOP/s', frac=achieved / pk['tflops_sustained'], traffic=None,
+                    unit='TFLOP/s', frac=achieved / pk['tflops_sustained'], traffic=NCU_TRAFFIC_FC1,
                     peak_source=f"{pk['source']} bf16 cuBLAS, sustained (kernel timed inside a long step)",
                     flops_per_launch=d['flops'] / d['launches'], us_per_launch=d['ms'] / d['launches'] * 1e3,
                     share_of_step=d['ms'] / tot_ms,
@@ -348,7 +351,7 @@ def main() -> None:
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        ref = cpu_reference(args.workload, args.images, 2, 1)
+        ref = cpu_reference(args.workload, args.images, 3, 1)
         cpu = dict(value=ref['value'], unit='crops/s', cores=ref['cores'], kind='port', sample=ref['sample'],
                    sec_per_crop=ref['sec_per_crop'])
 

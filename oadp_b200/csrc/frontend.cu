@@ -146,35 +146,46 @@ __device__ __forceinline__ double pil_bicubic(double x) {
   return 0.0;
 }
 
-// libImaging precompute_coeffs + normalize_coeffs_8bpc for ONE output sample `xx`.
-// Writes taps to k[0..*count) and the first source index to *first.
-__device__ void pil_coeffs(int in_size, int out_size, int xx, int* first, int* count, int* k) {
-  const double scale = static_cast<double>(in_size) / static_cast<double>(out_size);
-  const double filterscale = scale < 1.0 ? 1.0 : scale;
-  const double support = __dmul_rn(2.0, filterscale);
-  const double center = __dmul_rn(static_cast<double>(xx) + 0.5, scale);
-  const double ss = 1.0 / filterscale;
-  int xmin = static_cast<int>(__dadd_rn(__dadd_rn(center, -support), 0.5));
+// libImaging precompute_coeffs + normalize_coeffs_8bpc, split so that a whole CTA shares the work:
+// pil_bounds (one thread per output sample) fixes the tap window, pil_weight (one thread per tap)
+// evaluates the filter in double precision, pil_normalize (one thread per sample) performs the
+// sequential sum / divide / fixed-point rounding exactly in libImaging's order.
+struct PilAxis {
+  double scale, ss, support;
+};
+__device__ __forceinline__ PilAxis pil_axis(int in_size, int out_size) {
+  PilAxis a;
+  a.scale = static_cast<double>(in_size) / static_cast<double>(out_size);
+  const double filterscale = a.scale < 1.0 ? 1.0 : a.scale;
+  a.support = __dmul_rn(2.0, filterscale);
+  a.ss = 1.0 / filterscale;
+  return a;
+}
+__device__ __forceinline__ void pil_bounds(const PilAxis& a, int in_size, int xx, int* first, int* count) {
+  const double center = __dmul_rn(static_cast<double>(xx) + 0.5, a.scale);
+  int xmin = static_cast<int>(__dadd_rn(__dadd_rn(center, -a.support), 0.5));
   if (xmin < 0) xmin = 0;
-  int xmax = static_cast<int>(__dadd_rn(__dadd_rn(center, support), 0.5));
+  int xmax = static_cast<int>(__dadd_rn(__dadd_rn(center, a.support), 0.5));
   if (xmax > in_size) xmax = in_size;
   xmax -= xmin;
   if (xmax > kMaxTaps) xmax = kMaxTaps;  // guarded by the host-side scale check
-  double w[kMaxTaps];
+  *first = xmin;
+  *count = xmax;
+}
+__device__ __forceinline__ double pil_weight(const PilAxis& a, int xx, int xmin, int x) {
+  const double center = __dmul_rn(static_cast<double>(xx) + 0.5, a.scale);
+  const double arg = __dmul_rn(__dadd_rn(__dadd_rn(static_cast<double>(x + xmin), -center), 0.5), a.ss);
+  return pil_bicubic(arg);
+}
+__device__ __forceinline__ void pil_normalize(const double* w, int count, int* k) {
   double ww = 0.0;
-  for (int x = 0; x < xmax; ++x) {
-    const double arg = __dmul_rn(__dadd_rn(__dadd_rn(static_cast<double>(x + xmin), -center), 0.5), ss);
-    w[x] = pil_bicubic(arg);
-    ww = __dadd_rn(ww, w[x]);
-  }
-  for (int x = 0; x < xmax; ++x) {
+  for (int x = 0; x < count; ++x) ww = __dadd_rn(ww, w[x]);
+  for (int x = 0; x < count; ++x) {
     double v = w[x];
     if (ww != 0.0) v = __ddiv_rn(v, ww);
     const double f = __dmul_rn(v, static_cast<double>(1 << kPrecBits));
     k[x] = v < 0.0 ? static_cast<int>(__dadd_rn(-0.5, f)) : static_cast<int>(__dadd_rn(0.5, f));
   }
-  *first = xmin;
-  *count = xmax;
 }
 
 __device__ __forceinline__ uint8_t pil_clip8(int ss) {
@@ -187,7 +198,10 @@ struct ResizeSmem {
   int kv[kTile][kMaxTaps];
   int h_first[kTile], h_count[kTile], v_first[kTile], v_count[kTile];
   int r_lo, r_hi;
-  uint8_t tmp[kMaxRows][kTile][3];
+  union {
+    double w[2 * kTile][kMaxTaps];    // raw filter weights (coefficient phase): [0,32) horizontal, [32,64) vertical
+    uint8_t tmp[kMaxRows][kTile][3];  // horizontally resampled rows (pixel phase)
+  };
 };
 
 __global__ void __launch_bounds__(256)
@@ -205,11 +219,30 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
   const int th = min(kTile, job.win_y + job.win_h - oy0);
   const int tid = threadIdx.x;
 
+  const PilAxis ax_h = pil_axis(job.box_w, job.out_w);
+  const PilAxis ax_v = pil_axis(job.box_h, job.out_h);
   if (tid < kTile) {
-    if (tid < tw) pil_coeffs(job.box_w, job.out_w, ox0 + tid, &sm.h_first[tid], &sm.h_count[tid], sm.kh[tid]);
+    if (tid < tw) pil_bounds(ax_h, job.box_w, ox0 + tid, &sm.h_first[tid], &sm.h_count[tid]);
   } else if (tid < 2 * kTile) {
     const int r = tid - kTile;
-    if (r < th) pil_coeffs(job.box_h, job.out_h, oy0 + r, &sm.v_first[r], &sm.v_count[r], sm.kv[r]);
+    if (r < th) pil_bounds(ax_v, job.box_h, oy0 + r, &sm.v_first[r], &sm.v_count[r]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 2 * kTile * kMaxTaps; idx += blockDim.x) {  // one filter tap per thread
+    const int sidx = idx / kMaxTaps, x = idx - sidx * kMaxTaps;
+    if (sidx < kTile) {
+      if (sidx < tw && x < sm.h_count[sidx]) sm.w[sidx][x] = pil_weight(ax_h, ox0 + sidx, sm.h_first[sidx], x);
+    } else {
+      const int r = sidx - kTile;
+      if (r < th && x < sm.v_count[r]) sm.w[sidx][x] = pil_weight(ax_v, oy0 + r, sm.v_first[r], x);
+    }
+  }
+  __syncthreads();
+  if (tid < kTile) {
+    if (tid < tw) pil_normalize(sm.w[tid], sm.h_count[tid], sm.kh[tid]);
+  } else if (tid < 2 * kTile) {
+    const int r = tid - kTile;
+    if (r < th) pil_normalize(sm.w[tid], sm.v_count[r], sm.kv[r]);
   }
   __syncthreads();
   if (tid == 0) {
