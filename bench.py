@@ -318,10 +318,19 @@ def main() -> None:
 
     # ---------------------------------------------------------------- roofline: per-class CUDA events
     engine.profile(True)
+    for pp in pipes.values():
+        pp.profile_frontend = True
     for _ in range(2):
         device_step()
     prof = engine.profile_collect()
     engine.profile(False)
+    prof['frontend_im2col'] = prof.pop('frontend')
+    for pp in pipes.values():
+        pp.profile_frontend = False
+        for name, v in pp.collect_frontend_profile().items():
+            d = prof.setdefault('frontend_' + name, dict(ms=0.0, flops=0.0, launches=0))
+            d['ms'] += v['ms']
+            d['launches'] += v['launches']
     gemm = {k: v for k, v in prof.items() if k.startswith('gemm_') and v['launches']}
     dom = max(gemm, key=lambda k: gemm[k]['ms']) if gemm else None
     tot_ms = sum(v['ms'] for v in prof.values()) or 1.0

@@ -92,6 +92,8 @@ class OakePipeline:
         self.h2d_bytes = 0  # of the last call
         self.d2h_bytes = 0
         self.frontend_launches = 0  # resize / mask kernels launched so far
+        self.profile_frontend = False  # bench roofline pass: CUDA events around the resize / mask kernels
+        self.frontend_events = []  # (name, start, stop)
 
     # the slot being filled
     _arena = property(lambda self: self._slots[self._cur].arena)
@@ -182,16 +184,26 @@ class OakePipeline:
         st = self._stream()
         arena_ptr = self._arena.dev.data_ptr()
         meta_ptr = self._meta.dev.data_ptr()
+        def timed(name, fn):
+            if not self.profile_frontend:
+                fn()
+                return
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            self.frontend_events.append((name, a, b))
+
         for count, tiles, o in job['stages']:
             if count:
-                binding.check(self.lib.oake_resize_u8(arena_ptr, arena_ptr, meta_ptr + o, count, tiles,
-                                                      self._err.data_ptr(), st))
+                timed('resize_u8', lambda: binding.check(self.lib.oake_resize_u8(
+                    arena_ptr, arena_ptr, meta_ptr + o, count, tiles, self._err.data_ptr(), st)))
                 self.frontend_launches += 1
         masks_ptr = None
         if variant == binding.VARIANT_T197 and n:
             masks_ptr = meta_ptr + job['masks_off']
-            binding.check(self.lib.oake_object_masks(meta_ptr + job['fg_off'], meta_ptr + job['box_off'], n,
-                                                     masks_ptr, st))
+            timed('object_masks', lambda: binding.check(self.lib.oake_object_masks(
+                meta_ptr + job['fg_off'], meta_ptr + job['box_off'], n, masks_ptr, st)))
             self.frontend_launches += 1
         out = torch.empty(n, OUT_DIM, dtype=torch.float16, device=self.device)
         step = self.engine.MAX_CROPS[variant]
@@ -203,6 +215,16 @@ class OakePipeline:
                     self.engine._handle, arena_ptr, meta_ptr + job['crops_off'] + s * frontend.CROP_SRC.itemsize, b,
                     variant, (masks_ptr + s * 196 * 4) if masks_ptr else None, out[s:].data_ptr(), None,
                     ws.data_ptr(), ws.numel(), st))
+        return out
+
+    def collect_frontend_profile(self) -> Dict[str, Dict[str, float]]:
+        torch.cuda.synchronize(self.device)
+        out: Dict[str, Dict[str, float]] = {}
+        for name, a, b in self.frontend_events:
+            d = out.setdefault(name, dict(ms=0.0, flops=0.0, launches=0))
+            d['ms'] += a.elapsed_time(b)
+            d['launches'] += 1
+        self.frontend_events = []
         return out
 
     # ------------------------------------------------------------------------------ public API
