@@ -1,20 +1,27 @@
-// tcgen05 attention for the OAKE tower (SURVEY 2.2 K4 + K7): one CTA per (crop, head, 128-row query
-// tile); the math of nn.MultiheadAttention inside every CLIP ResidualAttentionBlock (reference call
-// sites oadp/oake/globals.py:57, blocks.py:129, objects.py:330) plus the objects side token of
-// oadp/oake/objects.py:224-247 as one more query row / key row of the same tile.
+// Persistent tcgen05 attention for the 197-token OAKE tower (SURVEY 2.2 K4 + K7): the math of
+// nn.MultiheadAttention inside every CLIP ResidualAttentionBlock (reference call site
+// oadp/oake/objects.py:330) plus the objects side token of oadp/oake/objects.py:224-247 as one more
+// query row / key row of the same tile.
 //
-//   S = Q K^T      tcgen05.mma, A = Q tile (smem, K-major), B = K tile (smem, K-major), D -> TMEM
-//   P = softmax    straight out of TMEM (tcgen05.ld): 16 warps, four per TMEM lane quarter, each thread
-//                  owning one query row x one quarter of the keys; two passes (max, then exp / sum)
-//                  with the four partial maxima / sums of a row exchanged through shared memory; P
-//                  goes back into TMEM as packed fp16, aliased over the (fully consumed) S columns
-//   O = P V        tcgen05.mma with A = P from TMEM, B = V tile (smem, MN-major: rows = keys), D -> TMEM
+// One CTA per SM walks over (crop, head) items.  An item is two 128-row query tiles (tokens 0..127 and
+// 128..197) against one 208-key K/V tile.  Warp roles:
 //
-// TMEM columns per CTA: S [0, NK) fp32, P [0, NK/2) packed fp16 (written only after the S pieces
-// underneath were consumed), O [NK/2, NK/2 + 64) (written after S is dead): 256 columns for T = 197,
-// 128 for T = 50, so two to four CTAs share an SM and overlap each other's load / MMA / softmax
-// phases.  K and V are loaded once per CTA by TMA (patch rows) + a few 16-byte copies (class / side
-// rows, zero padding).
+//   warps 0-3   softmax group A: query tile 0 of every item, TMEM columns [0, 256)
+//   warps 4-7   softmax group B: query tile 1 of every item, TMEM columns [256, 512)
+//   warp  8     loader: TMA boxes for Q / K / V (+ 16-byte copies for the class / side rows, zero
+//               padding, and the side row's additive bias) into a two-stage shared-memory ring
+//   warp  9     MMA issue (one thread): S = Q K^T and O = P V, interleaved PV(n,t), S(n+1,t)
+//
+// A softmax thread owns one query row (TMEM lane) for all 208 keys, so a row needs no exchange with
+// other threads: pass 1 reads S for the row maximum, pass 2 reads S again, writes P = exp2(s - max)
+// as packed fp16 over the S columns it has already consumed and accumulates the row sum; O lands in
+// the dead S columns behind P and is scaled by 1 / sum on its way to global memory.  While group A
+// is in its exp pass, the tensor core runs group B's MMAs and vice versa (the MUFU pipe is the
+// bound: 197 x 197 exponentials per head against 2 x 128 x 208 x 64 MACs).
+//
+// Tile 1 has only 70 live rows.  Warp w always runs on SM sub-partition w % 4 and owns TMEM lanes
+// 32 (w % 4) .. +31, so a fixed placement would leave sub-partition 3 idle for tile 1; odd items
+// therefore place the 70 rows at lanes 56..125 instead of 0..69.
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -26,23 +33,37 @@ namespace {
 constexpr int kDh = 64;
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <int P, bool SIDE>
-struct TCfg {
+template <bool SIDE>
+struct PCfg {
+  static constexpr int P = 196;
   static constexpr int T = P + 1;
   static constexpr int TQ = T + (SIDE ? 1 : 0);
-  static constexpr int NK = ((TQ + 15) / 16) * 16;  // keys, padded to the MMA K granule
-  static constexpr int MT = (TQ + 127) / 128;       // 128-row query tiles per (crop, head)
-  static constexpr int kQBytes = 128 * 128;
-  static constexpr int kKVRows = ((NK + 7) / 8) * 8;
-  static constexpr int kKVBytes = kKVRows * 128;
-  static constexpr int kXchgBytes = 2 * 4 * 128 * 4;  // partial max / sum: [2][4 groups][128 rows]
-  static constexpr int kSmemBytes = 1024 + kQBytes + 2 * kKVBytes + kXchgBytes + 64;
-  static constexpr int kUnits = NK / 16;  // 16-key units, dealt 4,3,3,3 (NK = 208) / 1,1,1,1 (NK = 64)
-  static constexpr int kOCol = NK / 2;                                  // O accumulator columns start
-  static constexpr int kTmemCols = (NK / 2 + 64 > NK ? NK / 2 + 64 : NK) <= 128 ? 128 : 256;
-  static constexpr int kSoftmaxWarps = 16;
-  static constexpr int kThreads = 32 * (kSoftmaxWarps + 1);  // + 1 control warp (TMA, MMA issue)
+  static constexpr int NK = 208;                 // keys, padded to the MMA K granule (16)
+  static constexpr int kUnits = NK / 16;         // 13
+  static constexpr int kRows1 = TQ - 128;        // live rows of tile 1: 68 patches + class (+ side)
+  static constexpr int kPatch1 = P - 128;        // patch rows of tile 1 (one TMA box)
+  static constexpr int kShift = 56;              // lane offset of tile 1's rows on odd items
+  static constexpr int kQTile = 128 * 128;       // bytes: 128 rows x 64 halves
+  static constexpr int kKV = NK * 128;           // bytes
+  static constexpr int kStage = 2 * kQTile + 2 * kKV;
+  static constexpr int kOCol = NK / 2;           // two O accumulators (even / odd key units) behind the packed P
+  static constexpr int kMaskFloats = 208;        // staged mask row (196 used), 16-byte granules
+  static constexpr int kBufCols = 256;           // TMEM columns per softmax group
+  static constexpr int kNumBars = 16;
+  static constexpr int kMaskBytes = 2048;        // both stages' mask rows, padded
+  static constexpr int kOutStage = 32 * 128;     // bytes per softmax warp: 32 rows x 64 halves, for coalesced stores
+  static constexpr int kSmemBytes = 1024 + 2 * kStage + kMaskBytes + 8 * kOutStage + kNumBars * 8 + 16;
+  static constexpr int kSoftmaxWarps = 8;
+  static constexpr int kLoaderWarp = 8;
+  static constexpr int kMmaWarp = 9;
+  static constexpr int kThreads = 32 * 10;
 };
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -51,6 +72,23 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  // volatile: the two softmax passes must each re-read the mask row instead of keeping 196 biases
+  // alive (and spilled) in between
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
+  return v;
+}
+// Arrives on `bar` (without raising its pending count) once every cp.async this thread has issued
+// so far has landed: the loader never blocks on its own copies.
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
@@ -93,257 +131,407 @@ __device__ __forceinline__ int token_row(int i, int b, int B, int P) {
   return i < P ? b * P + i : (i == P ? B * P + b : B * P + B + b);
 }
 
-template <int P, bool SIDE>
-__global__ void __launch_bounds__(TCfg<P, SIDE>::kThreads, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,   // qkv [R, 3W], box {64, 128}
-                    const __grid_constant__ CUtensorMap tmKV,  // qkv [R, 3W], box {64, P}
+// How a softmax warp biases its scores.
+//   kPlain: main-stream rows only.  Keys 0..196 (patches, class) valid, no bias: pass 1 is a plain
+//           maximum of the raw scores.
+//   kBits / kLoad: the warp that holds the side row (warp-uniform code, per-lane select).  The side
+//           row adds -100 log2e mask[key] on patches, -inf on the class key, 0 on its own key
+//           (objects.py:204-247); main-stream rows add 0 / -inf by key validity.  kBits takes the mask
+//           from 7 words of bits (the reference's masks are 0 / 1 by construction, objects.py:147-153);
+//           kLoad reads the fp32 mask row for any other mask values.
+enum BiasMode { kPlain = 0, kBits = 1, kLoad = 2 };
+
+// One query row: S (fp32, TMEM columns [0, NK) of this thread's lane) -> P (packed fp16, columns
+// [0, NK/2)); returns the row sum of the unrounded exponentials.  Keys are walked in three 64-key
+// steps (all patches: one loop body) and a 16-key tail (patches 192..195, class, side, padding).
+template <bool SIDE, int MODE>
+__device__ __forceinline__ float softmax_row(uint32_t t_row, bool is_y, uint32_t ymask_addr, uint32_t ybits) {
+  using C = PCfg<SIDE>;
+  constexpr float scale = 0.125f * kLog2e;
+  constexpr float kNegB = -100.0f * kLog2e;
+  constexpr int kMain = 192;  // keys handled by the loop
+  static_assert(kMain + 16 == C::NK && kMain <= C::P, "tail layout");
+  // bias of a patch key (MODE != kPlain); `w` = this lane's mask bits of the key's 32-key group
+  auto patch_bias = [&](int col, int j, uint32_t w) -> float {
+    if (MODE == kBits) return (w >> j) & 1u ? kNegB : 0.f;
+    return is_y ? kNegB * lds_f32(ymask_addr + col * 4) : 0.f;
+  };
+  // lane g < 7 holds the bits of keys 32g..32g+31 in `ybits`; rows other than the side row see zeros
+  auto group_bits = [&](int g) -> uint32_t {
+    if (MODE != kBits) return 0u;
+    const uint32_t w = __shfl_sync(0xffffffffu, ybits, g);
+    return is_y ? w : 0u;
+  };
+  // bias of a tail key 192 + j
+  auto tail_bias = [&](int j, uint32_t w) -> float {
+    const int col = kMain + j;
+    if (col < C::P) return MODE == kPlain ? 0.f : patch_bias(col, j, w);
+    const float main_b = col < C::T ? 0.f : -INFINITY;                 // class key valid, side key / padding not
+    if (MODE == kPlain) return main_b;
+    const float y_b = col == C::T ? 0.f : -INFINITY;                    // the side token sees itself, not the class key
+    return is_y ? y_b : main_b;
+  };
+
+  // ---- pass 1: row maximum (base-2 domain)
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+  for (int c = 0; c < kMain / 64; ++c) {
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32(t_row + c * 64, ra);
+    tmem_ld_32x32(t_row + c * 64 + 32, rb);
+    const uint32_t wa = group_bits(2 * c), wb = group_bits(2 * c + 1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (MODE == kPlain) {
+        m4[j & 3] = fmaxf(m4[j & 3], fmaxf(__uint_as_float(ra[j]), __uint_as_float(rb[j])));
+      } else {
+        m4[j & 3] = fmaxf(m4[j & 3], fmaf(__uint_as_float(ra[j]), scale, patch_bias(c * 64 + j, j, wa)));
+        m4[j & 3] = fmaxf(m4[j & 3], fmaf(__uint_as_float(rb[j]), scale, patch_bias(c * 64 + 32 + j, j, wb)));
+      }
+    }
+  }
+  float mx;
+  {
+    uint32_t rt[16];
+    tmem_ld_32x16(t_row + kMain, rt);
+    const uint32_t wt = group_bits(6);
+    tmem_ld_wait();
+    if (MODE == kPlain) {  // the scale is positive: max(s) * scale == max(s * scale)
+      mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale;
+    } else {
+      mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (kMain + j <= C::T) mx = fmaxf(mx, fmaf(__uint_as_float(rt[j]), scale, tail_bias(j, wt)));
+  }
+  const float neg_mx = -mx;
+
+  // ---- pass 2: p = exp2(s - max) -> packed fp16 over the consumed S columns; row sum
+  // (bias added after the fma: a main-stream row gets bit-identical results in every mode, so batch
+  // composition stays invisible)
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int c = 0; c < kMain / 64; ++c) {
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32(t_row + c * 64, ra);
+    tmem_ld_32x32(t_row + c * 64 + 32, rb);
+    const uint32_t wa = group_bits(2 * c), wb = group_bits(2 * c + 1);
+    tmem_ld_wait();
+    uint32_t pa[16], pb[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float p[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int jj = 2 * j + e;
+        if (MODE == kPlain) {
+          p[e] = ex2(fmaf(__uint_as_float(ra[jj]), scale, neg_mx));
+          p[2 + e] = ex2(fmaf(__uint_as_float(rb[jj]), scale, neg_mx));
+        } else {
+          p[e] = ex2(fmaf(__uint_as_float(ra[jj]), scale, neg_mx) + patch_bias(c * 64 + jj, jj, wa));
+          p[2 + e] = ex2(fmaf(__uint_as_float(rb[jj]), scale, neg_mx) + patch_bias(c * 64 + 32 + jj, jj, wb));
+        }
+      }
+      s4[j & 3] += (p[0] + p[1]) + (p[2] + p[3]);
+      pa[j] = pack2(p[0], p[1]);
+      pb[j] = pack2(p[2], p[3]);
+    }
+    tmem_st_32x16(t_row + c * 32, pa);
+    tmem_st_32x16(t_row + c * 32 + 16, pb);
+  }
+  {
+    uint32_t rt[16];
+    tmem_ld_32x16(t_row + kMain, rt);
+    const uint32_t wt = group_bits(6);
+    tmem_ld_wait();
+    uint32_t pt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int jj = 2 * j + e;
+        p[e] = kMain + jj <= C::T ? ex2(fmaf(__uint_as_float(rt[jj]), scale, neg_mx) + tail_bias(jj, wt)) : 0.f;
+      }
+      s4[j & 3] += p[0] + p[1];
+      pt[j] = pack2(p[0], p[1]);
+    }
+    tmem_st_32x8(t_row + kMain / 2, pt);
+  }
+  return (s4[0] + s4[1]) + (s4[2] + s4[3]);
+}
+
+template <bool SIDE>
+__global__ void __launch_bounds__(PCfg<SIDE>::kThreads, 1)
+attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], box {64, 128}
+                    const __grid_constant__ CUtensorMap tmQ1,  // qkv [R, 3W], box {64, 68}
+                    const __grid_constant__ CUtensorMap tmKV,  // qkv [R, 3W], box {64, 196}
                     const act_t* __restrict__ qkv, const float* __restrict__ mask, act_t* __restrict__ out,
-                    int B, int heads, int mt_first, int only_y) {
-  using C = TCfg<P, SIDE>;
+                    int B, int heads) {
+  using C = PCfg<SIDE>;
+  constexpr int P = C::P;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + C::kQBytes;
-  uint8_t* sV = sK + C::kKVBytes;
-  float* s_max = reinterpret_cast<float*>(sV + C::kKVBytes);  // [4][128]
-  float* s_sum = s_max + 4 * 128;                              // [4][128]
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(s_sum + 4 * 128);
-  uint64_t* bar_s = bar_load + 1;
-  uint64_t* bar_p = bar_load + 2;
-  uint64_t* bar_o = bar_load + 3;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_load + 4);
+  float* ymask = reinterpret_cast<float*>(smem + 2 * C::kStage);  // [2][kMaskFloats]: mask row of the item's crop
+  uint8_t* out_stage = smem + 2 * C::kStage + C::kMaskBytes;  // [8 warps][kOutStage]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + 8 * C::kOutStage);
+  uint64_t* qk_full = bars + 0;   // [stage]  loader -> MMA
+  uint64_t* qk_free = bars + 2;   // [stage]  MMA (S of both tiles retired) -> loader
+  uint64_t* v_full = bars + 4;    // [stage]  loader -> MMA, side-row warp (mask row)
+  uint64_t* v_free = bars + 6;    // [stage]  MMA (PV of both tiles retired) -> loader
+  uint64_t* s_full = bars + 8;    // [tile]   MMA -> softmax group
+  uint64_t* p_ready = bars + 10;  // [tile]   softmax group -> MMA
+  uint64_t* o_full = bars + 12;   // [tile]   MMA -> softmax group
+  uint64_t* o_free = bars + 14;   // [tile]   softmax group (O drained) -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mts = C::MT - mt_first;  // query tiles per (crop, head) handled by this launch
-  const int item = blockIdx.x / mts;
-  const int mt = mt_first + (blockIdx.x - item * mts);
-  const int b = item / heads;
-  const int h = item - b * heads;
   const int W = heads * kDh;
   const int ld = 3 * W;
+  const int items = B * heads;
+  const int N = (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
-  constexpr int kCtl = C::kSoftmaxWarps;  // index of the control warp
-  if (warp == kCtl && elect_one()) {
-    tma_prefetch_desc(&tmQ);
+  if (warp == C::kLoaderWarp && lane == 0) {
+    tma_prefetch_desc(&tmQ0);
+    tma_prefetch_desc(&tmQ1);
     tma_prefetch_desc(&tmKV);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, C::kSoftmaxWarps);
-    mbar_init(bar_o, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 33);  // expect_tx arrival + one cp.async arrival per loader lane
+      mbar_init(&qk_free[i], 1);
+      mbar_init(&v_full[i], 33);
+      mbar_init(&v_free[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);  // one arrival per warp of the group
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<C::kTmemCols>(tmem_ptr);
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == kCtl) {
-    // ------------------------------------------------------------------ loads + MMA issue
-    if (elect_one()) {
-      mbar_arrive_expect_tx(bar_load, C::kQBytes + 2 * P * 128);
-      // Q: 128 token rows starting at token mt*128 (all of them patch rows of this crop, or the
-      // rows that follow them in memory -- finite garbage that only feeds rows nobody stores)
-      tma_load_2d(sQ, &tmQ, bar_load, h * kDh, b * P + mt * 128);
-      tma_load_2d(sK, &tmKV, bar_load, W + h * kDh, b * P);
-      tma_load_2d(sV, &tmKV, bar_load, 2 * W + h * kDh, b * P);
-    }
-    // class / side rows and zero padding of K and V (rows the TMA box does not touch): cp.async, so
-    // that all of them are in flight together with the TMA boxes
-    for (int idx = lane; idx < (C::kKVRows - P) * 8; idx += 32) {
-      const int i = P + (idx >> 3), c = idx & 7;
-      const bool ok = i < C::TQ;
-      const act_t* src = qkv + static_cast<size_t>(token_row(ok ? i : P, b, B, P)) * ld + h * kDh + c * 8;
-      cp_async16_zfill(sw128(sK, i, c), src + W, ok);
-      cp_async16_zfill(sw128(sV, i, c), src + 2 * W, ok);
-    }
-    // class / side query rows: they overwrite rows of the Q box, so they are staged in registers and
-    // written once the box has landed
-    uint4 qrow[(C::TQ - P) * 8 / 32 + 1];
-#pragma unroll
-    for (int it = 0; it < (C::TQ - P) * 8 / 32 + 1; ++it) {
-      const int idx = lane + 32 * it;
-      qrow[it] = make_uint4(0, 0, 0, 0);
-      if (idx < (C::TQ - P) * 8) {
-        const int i = P + (idx >> 3), c = idx & 7;
-        const int r = i - mt * 128;
-        if (r >= 0 && r < 128)
-          qrow[it] = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(token_row(i, b, B, P)) * ld + h * kDh + c * 8);
+  if (warp == C::kLoaderWarp) {
+    // ================================================================== loader
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1, u = n >> 1;
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / heads, h = item - b * heads;
+      uint8_t* stg = smem + s * C::kStage;
+      uint8_t* sQ0 = stg;
+      uint8_t* sQ1 = stg + C::kQTile;
+      uint8_t* sK = stg + 2 * C::kQTile;
+      uint8_t* sV = sK + C::kKV;
+      const int shift = s ? C::kShift : 0;
+
+      mbar_wait(&qk_free[s], (u & 1) ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&qk_full[s], C::kQTile + C::kPatch1 * 128 + P * 128);
+        tma_load_2d(sQ0, &tmQ0, &qk_full[s], h * kDh, b * P);
+        tma_load_2d(sQ1 + shift * 128, &tmQ1, &qk_full[s], h * kDh, b * P + 128);
+        tma_load_2d(sK, &tmKV, &qk_full[s], W + h * kDh, b * P);
       }
-    }
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-    mbar_wait(bar_load, 0);
-#pragma unroll
-    for (int it = 0; it < (C::TQ - P) * 8 / 32 + 1; ++it) {
-      const int idx = lane + 32 * it;
-      if (idx < (C::TQ - P) * 8) {
+      __syncwarp();
+      // K rows of the class / side token and the zero padding up to NK
+      for (int idx = lane; idx < (C::NK - P) * 8; idx += 32) {
         const int i = P + (idx >> 3), c = idx & 7;
-        const int r = i - mt * 128;
-        if (r >= 0 && r < 128) *reinterpret_cast<uint4*>(sw128(sQ, r, c)) = qrow[it];
+        const bool ok = i < C::TQ;
+        const act_t* src = qkv + static_cast<size_t>(token_row(ok ? i : P, b, B, P)) * ld + W + h * kDh + c * 8;
+        cp_async16_zfill(sw128(sK, i, c), src, ok);
       }
+      // Q rows of the class / side token: tile-1 rows shift + 68 (, + 69)
+      for (int idx = lane; idx < (C::TQ - P) * 8; idx += 32) {
+        const int i = P + (idx >> 3), c = idx & 7;
+        const act_t* src = qkv + static_cast<size_t>(token_row(i, b, B, P)) * ld + h * kDh + c * 8;
+        cp_async16_zfill(sw128(sQ1, shift + i - 128, c), src, true);
+      }
+      cp_async_arrive_noinc(&qk_full[s]);  // every lane, with or without copies of its own
+
+      mbar_wait(&v_free[s], (u & 1) ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&v_full[s], P * 128);
+        tma_load_2d(sV, &tmKV, &v_full[s], 2 * W + h * kDh, b * P);
+      }
+      __syncwarp();
+      for (int idx = lane; idx < (C::NK - P) * 8; idx += 32) {
+        const int i = P + (idx >> 3), c = idx & 7;
+        const bool ok = i < C::TQ;
+        const act_t* src = qkv + static_cast<size_t>(token_row(ok ? i : P, b, B, P)) * ld + 2 * W + h * kDh + c * 8;
+        cp_async16_zfill(sw128(sV, i, c), src, ok);
+      }
+      if (SIDE) {  // the crop's mask row (196 floats = 49 granules) for the side-row warp
+        const float* mrow = mask + static_cast<size_t>(b) * P;
+        for (int g = lane; g < P / 4; g += 32) cp_async16_zfill(ymask + s * C::kMaskFloats + g * 4, mrow + g * 4, true);
+      }
+      cp_async_arrive_noinc(&v_full[s]);
     }
-    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core
-    __syncwarp();
-    tc_fence_after();
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_f16(128, C::NK);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK);
+    asm volatile("cp.async.wait_all;\n" ::: "memory");  // nothing of this warp in flight at exit
+  } else if (warp == C::kMmaWarp) {
+    // ================================================================== MMA issue
+    constexpr uint32_t idesc_s = make_idesc_f16(128, C::NK);
+    constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, kDh);
+    const uint32_t smem_base = smem_u32(smem);
+    auto issue_s = [&](int n, int t) {  // lane 0 only
+      const uint32_t stg = smem_base + (n & 1) * C::kStage;
+      const uint32_t q_addr = stg + t * C::kQTile, k_addr = stg + 2 * C::kQTile;
 #pragma unroll
       for (int k = 0; k < kDh / 16; ++k)
-        umma_f16(tmem_base, make_smem_desc_k_sw128(q_addr + k * 32), make_smem_desc_k_sw128(k_addr + k * 32),
-                 idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    mbar_wait(bar_p, 0);
-    tc_fence_after();
-    if (elect_one()) {
-      constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, kDh);
-      const uint32_t v_addr = smem_u32(sV);
+        umma_f16(tmem_base + t * C::kBufCols, make_smem_desc_k_sw128(q_addr + k * 32),
+                 make_smem_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&s_full[t]);
+    };
+    auto issue_pv = [&](int n, int t) {  // lane 0 only
+      const uint32_t v_addr = smem_base + (n & 1) * C::kStage + 2 * C::kQTile + C::kKV;
+      const uint32_t buf = tmem_base + t * C::kBufCols;
 #pragma unroll
-      for (int k = 0; k < C::NK / 16; ++k)
-        umma_f16_ts(tmem_base + C::kOCol, tmem_base + k * 8, make_smem_desc_mn_sw128(v_addr + k * 2048), idesc_o,
-                    k != 0 ? 1u : 0u);
-      umma_commit(bar_o);
+      for (int k = 0; k < C::kUnits; ++k)
+        umma_f16_ts(buf + C::kOCol + (k & 1) * kDh, buf + k * 8, make_smem_desc_mn_sw128(v_addr + k * 2048), idesc_o,
+                    k >= 2 ? 1u : 0u);  // even / odd key units accumulate separately: two short chains
+      umma_commit(&o_full[t]);
+    };
+    if (N > 0) {
+      mbar_wait(&qk_full[0], 0);
+      fence_proxy_async();  // the loader's cp.async rows (generic proxy) -> tensor core reads
+      tc_fence_after();
+      if (lane == 0) {
+        issue_s(0, 0);
+        issue_s(0, 1);
+        umma_commit(&qk_free[0]);
+      }
+      __syncwarp();
+    }
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1, u = n >> 1;
+      mbar_wait(&v_full[s], u & 1);
+      fence_proxy_async();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_ready[t], n & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_pv(n, t);
+          if (t == 1) umma_commit(&v_free[s]);
+        }
+        __syncwarp();
+        if (n + 1 < N) {
+          if (t == 0) {
+            mbar_wait(&qk_full[s ^ 1], ((n + 1) >> 1) & 1);
+            fence_proxy_async();
+          }
+          mbar_wait(&o_free[t], n & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_s(n + 1, t);
+            if (t == 1) umma_commit(&qk_free[s ^ 1]);
+          }
+          __syncwarp();
+        }
+      }
     }
   } else {
-    // ------------------------------------------------------------------ softmax
-    // thread = (query row r, key group g): warps q, q+4, q+8, q+12 all read TMEM lane quarter q
+    // ================================================================== softmax groups
+    const int t = warp >> 2;
     const int q = warp & 3;
-    const int g = warp >> 2;
-    const int r = q * 32 + lane;  // row of this tile
-    const int i = mt * 128 + r;   // token index
-    const bool is_y = SIDE && i == C::T;
-    const bool live = only_y ? is_y : (i < C::TQ);  // only_y: last objects block, just the side row
-    // 16-key units of this group: the first (kUnits % 4) groups get one more
-    const int units = C::kUnits / 4 + (g < C::kUnits % 4 ? 1 : 0);
-    const int unit0 = g * (C::kUnits / 4) + (g < C::kUnits % 4 ? g : C::kUnits % 4);
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float scale = 0.125f * kLog2e;
-    const float* mrow = mask + static_cast<size_t>(b) * P;
-    constexpr int kMaxUnits = (C::kUnits + 3) / 4;
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
+    const int r = q * 32 + lane;  // lane of the tile
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * C::kBufCols;
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1, u = n >> 1;
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / heads, h = item - b * heads;
+      const int rr = r - ((t == 1 && s) ? C::kShift : 0);
+      const bool live = t == 0 || (rr >= 0 && rr < C::kRows1);
+      const int i = t * 128 + rr;  // token index
+      const bool is_y = SIDE && live && i == C::T;
+      const bool warp_live = __any_sync(0xffffffffu, live);
+      const bool warp_y = SIDE && __any_sync(0xffffffffu, is_y);
 
-    // Units whose 16 keys are all patches need no masking for a main-stream row: one FMNMX per
-    // score in pass 1 (on the raw score: the scale is positive), FFMA + EX2 + FADD (+ half a pack)
-    // in pass 2.  The unit that holds the class / side / padding keys and the single side-stream
-    // row of a tile (bias -100 * mask, different key set) take the generic masked path.
-    auto generic = [&](float raw, int col) -> float {  // scaled, biased, masked score
-      float v = raw * scale;
-      bool valid = col < C::T;
-      if (is_y) {  // objects.py:204-247: patches with bias -100 * mask, itself, not the class token
-        valid = col < P || col == C::T;
-        if (col < P) v += -100.0f * kLog2e * __ldg(mrow + col);
-      }
-      return valid ? v : -INFINITY;
-    };
-
-    // pass 1: partial row maximum (base-2 domain)
-    float mx_raw = -INFINITY, mx = -INFINITY;
+      mbar_wait(&s_full[t], n & 1);
+      tc_fence_after();
+      float sum = 1.f;
+      if (warp_live) {
+        if (warp_y) {
+          mbar_wait(&v_full[s], u & 1);  // the crop's mask row lands with the V stage
+          const uint32_t ymask_addr = smem_u32(ymask + s * C::kMaskFloats);
+          uint32_t ybits = 0u, other = 0u;  // lane g keeps the bits of keys 32g .. 32g+31
 #pragma unroll
-    for (int u = 0; u < kMaxUnits; ++u) {
-      if (u < units) {
-        uint32_t r16[16];
-        tmem_ld_32x16(t_row + (unit0 + u) * 16, r16);
-        tmem_ld_wait();
-        if (live) {
-          const int col0 = (unit0 + u) * 16;
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          if (col0 + 16 <= P && !is_y) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(r16[j]));
-            mx_raw = fmaxf(mx_raw, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) m4[j & 3] = fmaxf(m4[j & 3], generic(__uint_as_float(r16[j]), col0 + j));
-            mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          for (int g = 0; g < 7; ++g) {
+            const int col = g * 32 + lane;
+            const float m = col < P ? lds_f32(ymask_addr + col * 4) : 0.f;
+            const uint32_t w = __ballot_sync(0xffffffffu, m != 0.f);
+            other |= __ballot_sync(0xffffffffu, m != 0.f && m != 1.f);
+            if (lane == g) ybits = w;
           }
-        }
-      }
-    }
-    mx = fmaxf(mx, mx_raw * scale);
-    s_max[g * 128 + r] = mx;
-    tc_fence_before();
-    asm volatile("bar.sync 1, %0;\n" ::"n"(C::kSoftmaxWarps * 32) : "memory");
-    tc_fence_after();
-    mx = fmaxf(fmaxf(s_max[r], s_max[128 + r]), fmaxf(s_max[256 + r], s_max[384 + r]));
-    const float neg_mx = -mx;
-
-    // pass 2: p = exp2(s - max), partial row sum; P is kept in registers until every warp has
-    // finished reading S (the packed P columns alias S columns owned by other key groups)
-    float sum = 0.f;
-    uint32_t pk[kMaxUnits][8];
-#pragma unroll
-    for (int u = 0; u < kMaxUnits; ++u) {
-      if (u < units) {
-        uint32_t r16[16];
-        tmem_ld_32x16(t_row + (unit0 + u) * 16, r16);
-        tmem_ld_wait();
-        const int col0 = (unit0 + u) * 16;
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (!live) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) pk[u][j] = 0u;
-        } else if (col0 + 16 <= P && !is_y) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float p0 = exp2f(fmaf(__uint_as_float(r16[2 * j]), scale, neg_mx));
-            const float p1 = exp2f(fmaf(__uint_as_float(r16[2 * j + 1]), scale, neg_mx));
-            s4[j & 3] += p0 + p1;
-            pk[u][j] = pack2(p0, p1);
+          if (other == 0u) {
+            sum = softmax_row<SIDE, kBits>(t_row, is_y, ymask_addr, ybits);
+          } else {
+            sum = softmax_row<SIDE, kLoad>(t_row, is_y, ymask_addr, 0u);
           }
         } else {
+          sum = softmax_row<SIDE, kPlain>(t_row, false, 0u, 0u);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[t]);
+
+      if (warp_live) {
+        uint32_t oa0[32], oa1[32], ob0[32], ob1[32];
+        mbar_wait(&o_full[t], n & 1);
+        tc_fence_after();
+        tmem_ld_32x32(t_row + C::kOCol, oa0);
+        tmem_ld_32x32(t_row + C::kOCol + 32, oa1);
+        tmem_ld_32x32(t_row + C::kOCol + kDh, ob0);
+        tmem_ld_32x32(t_row + C::kOCol + kDh + 32, ob1);
+        tmem_ld_wait();
+        // the accumulators are in registers: the tile's TMEM goes back to the tensor core before
+        // the scaling and the global stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[t]);
+        // rows -> shared memory (one 128-byte row per lane, 16-byte chunks XOR-swizzled), then every
+        // store instruction writes four whole 128-byte rows of the output
+        uint8_t* stg = out_stage + warp * C::kOutStage;
+        {
+          const float inv = 1.0f / sum;
+          auto o_at = [&](int c) -> float {
+            return c < 32 ? __uint_as_float(oa0[c & 31]) + __uint_as_float(ob0[c & 31])
+                          : __uint_as_float(oa1[c & 31]) + __uint_as_float(ob1[c & 31]);
+          };
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float p0 = exp2f(generic(__uint_as_float(r16[2 * j]), col0 + 2 * j) + neg_mx);
-            const float p1 = exp2f(generic(__uint_as_float(r16[2 * j + 1]), col0 + 2 * j + 1) + neg_mx);
-            s4[j & 3] += p0 + p1;
-            pk[u][j] = pack2(p0, p1);
+            uint4 v;
+            v.x = pack2(o_at(8 * j + 0) * inv, o_at(8 * j + 1) * inv);
+            v.y = pack2(o_at(8 * j + 2) * inv, o_at(8 * j + 3) * inv);
+            v.z = pack2(o_at(8 * j + 4) * inv, o_at(8 * j + 5) * inv);
+            v.w = pack2(o_at(8 * j + 6) * inv, o_at(8 * j + 7) * inv);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
           }
         }
-        sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      }
-    }
-    s_sum[g * 128 + r] = sum;
-    tc_fence_before();
-    asm volatile("bar.sync 1, %0;\n" ::"n"(C::kSoftmaxWarps * 32) : "memory");
-    tc_fence_after();
+        __syncwarp();
+        {
+          const int chunk = lane & 7;
+          const int shift1 = (t == 1 && s) ? C::kShift : 0;
 #pragma unroll
-    for (int u = 0; u < kMaxUnits; ++u) {
-      if (u < units)
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(
-                         t_row + (unit0 + u) * 8),
-                     "r"(pk[u][0]), "r"(pk[u][1]), "r"(pk[u][2]), "r"(pk[u][3]), "r"(pk[u][4]), "r"(pk[u][5]),
-                     "r"(pk[u][6]), "r"(pk[u][7])
-                     : "memory");
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_p);
-    sum = (s_sum[r] + s_sum[128 + r]) + (s_sum[256 + r] + s_sum[384 + r]);
-
-    // O: each key group stores 16 of the row's 64 output values (32 contiguous bytes)
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    {
-      const float inv = 1.0f / sum;
-      uint32_t o16[16];
-      tmem_ld_32x16(t_row + C::kOCol + g * 16, o16);
-      tmem_ld_wait();
-      if (live) {
-        act_t* dst = out + static_cast<size_t>(token_row(i, b, B, P)) * W + h * kDh + g * 16;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint4 u;
-          u.x = pack2(__uint_as_float(o16[8 * j + 0]) * inv, __uint_as_float(o16[8 * j + 1]) * inv);
-          u.y = pack2(__uint_as_float(o16[8 * j + 2]) * inv, __uint_as_float(o16[8 * j + 3]) * inv);
-          u.z = pack2(__uint_as_float(o16[8 * j + 4]) * inv, __uint_as_float(o16[8 * j + 5]) * inv);
-          u.w = pack2(__uint_as_float(o16[8 * j + 6]) * inv, __uint_as_float(o16[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + j * 8) = u;
+          for (int k = 0; k < 8; ++k) {
+            const int row = 4 * k + (lane >> 3);          // row of this warp's 32
+            const int rr2 = q * 32 + row - shift1;        // row of the tile's live range
+            const bool live2 = t == 0 || (rr2 >= 0 && rr2 < C::kRows1);
+            if (live2) {
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
+              const int tok = t * 128 + rr2;
+              *reinterpret_cast<uint4*>(out + static_cast<size_t>(token_row(tok, b, B, P)) * W + h * kDh + chunk * 8) = v;
+            }
+          }
         }
+        __syncwarp();
+      } else {
+        if (lane == 0) mbar_arrive(&o_free[t]);
       }
     }
   }
@@ -352,59 +540,59 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,   // qkv [R, 3W], b
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
-template <int P, bool SIDE>
-cudaError_t launch_tc(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int heads, int rows,
-                      int mt_first, int only_y) {
-  using C = TCfg<P, SIDE>;
+template <bool SIDE>
+cudaError_t launch_pp(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int heads, int rows) {
+  using C = PCfg<SIDE>;
   static bool attr_set = false;
+  static int num_sms = 0;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<P, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_pp_kernel<SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
     if (e != cudaSuccess) return e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     attr_set = true;
   }
-  CUtensorMap tmQ, tmKV;
-  if (make_tmap_act_2d(&tmQ, qkv, rows, 3 * heads * kDh, 128) || make_tmap_act_2d(&tmKV, qkv, rows, 3 * heads * kDh, P))
+  CUtensorMap tmQ0, tmQ1, tmKV;
+  const uint64_t cols = 3ull * heads * kDh;
+  if (make_tmap_act_2d(&tmQ0, qkv, rows, cols, 128) || make_tmap_act_2d(&tmQ1, qkv, rows, cols, C::kPatch1) ||
+      make_tmap_act_2d(&tmKV, qkv, rows, cols, C::P))
     return cudaErrorInvalidValue;
-  const int grid = B * heads * (C::MT - mt_first);
-  attention_tc_kernel<P, SIDE><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ, tmKV, qkv, mask, out, B, heads, mt_first,
-                                                                         only_y);
+  const int items = B * heads;
+  const int grid = items < num_sms ? items : num_sms;
+  attention_pp_kernel<SIDE><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ0, tmQ1, tmKV, qkv, mask, out, B, heads);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-// Opt-in (OAKE_ATTN=tc).  This non-persistent form is numerically verified but latency-bound: each
-// CTA runs load -> S -> softmax -> PV -> store serially and TMEM (256 columns per 128-row tile)
-// allows only two tiles in flight per SM; the mma.sync kernel of attention.cu is the default until
-// this one is made persistent with ping-pong tiles.
-bool attention_use_tc(int P) {
+// The persistent tcgen05 kernel serves the 197-token tower whenever whole tiles are wanted; the
+// 50-token tower and the last objects block (side row only) stay on the mma.sync kernel of
+// attention.cu.  OAKE_ATTN=mma forces the mma.sync kernel everywhere (A/B runs, tests).
+bool attention_use_tc(int P, int side_only) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("OAKE_ATTN");
-    v = (e == nullptr) ? 2 : (e[0] == 'm' ? 0 : 1);
+    v = (e != nullptr && e[0] == 'm') ? 0 : 1;
   }
-  (void)P;
-  return v == 1;  // measured r1: mma.sync 4.6 ms vs tcgen05 5.8 ms per 478-crop objects batch
+  return v == 1 && P == 196 && !side_only;
 }
 
 cudaError_t launch_attention_tc(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
                                 int heads, int with_side, int side_only) {
   if (B <= 0) return cudaSuccess;
+  if (P != 196 || side_only) return cudaErrorInvalidValue;
   const int rows = B * (P + 1) + (with_side ? B : 0);
   if (with_side) {
-    if (P != 196 || mask == nullptr) return cudaErrorInvalidValue;
-    // side_only: the y row lives in the second query tile; the first one is not needed at all
-    return launch_tc<196, true>(st, qkv, mask, out, B, heads, rows, side_only ? 1 : 0, side_only ? 1 : 0);
+    if (mask == nullptr) return cudaErrorInvalidValue;
+    return launch_pp<true>(st, qkv, mask, out, B, heads, rows);
   }
-  if (side_only) return cudaErrorInvalidValue;
-  if (P == 49) return launch_tc<49, false>(st, qkv, nullptr, out, B, heads, rows, 0, 0);
-  if (P == 196) return launch_tc<196, false>(st, qkv, nullptr, out, B, heads, rows, 0, 0);
-  return cudaErrorInvalidValue;
+  return launch_pp<false>(st, qkv, nullptr, out, B, heads, rows);
 }
 
 }  // namespace oake

@@ -171,7 +171,9 @@ def ref_attention(qkv, B, P, side_mask=None):
     return out
 
 
-@pytest.mark.parametrize('P,B', [(49, 5), (196, 3)])
+# B = 40 x 12 heads = 480 items: more than 3 per SM, so the persistent 197-token kernel cycles its
+# two-stage ring and both tile placements
+@pytest.mark.parametrize('P,B', [(49, 5), (196, 3), (196, 40)])
 def test_attention_main(lib, P, B):
     g = torch.Generator(device=DEV).manual_seed(P)
     R = B * (P + 1)
@@ -184,9 +186,9 @@ def test_attention_main(lib, P, B):
     assert (out.float() - ref).abs().max() < tol, (out.float() - ref).abs().max()
 
 
-@pytest.mark.parametrize('side_only', [1, 0])
-def test_attention_side(lib, side_only):
-    B, P = 5, 196
+@pytest.mark.parametrize('side_only,B', [(1, 5), (0, 5), (0, 53)])
+def test_attention_side(lib, side_only, B):
+    P = 196
     g = torch.Generator(device=DEV).manual_seed(11)
     R = B * (P + 2)
     qkv = (torch.randn(R, 2304, device=DEV, generator=g) * 1.5).to(act_dtype())
