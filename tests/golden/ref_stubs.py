@@ -1,0 +1,397 @@
+"""Stand-ins for the third-party packages the reference imports, so that the reference's OWN source
+files (/root/reference/oadp/...) can be executed in this container -- FIXTURE GENERATION ONLY.
+
+The reference cannot be imported as a package: ``oadp/__init__.py`` pulls ``todd``, ``mmcv``,
+``mmdet``, ``lvis`` and ``clip``, none of which is installed and none of which is vendored
+(SURVEY.md section 0).  ``make_ref_golden.py`` therefore loads individual reference modules with
+``importlib`` after placing the stubs below in ``sys.modules``.  What is stubbed is exactly the
+un-vendored third-party surface; every line of arithmetic that lives in the reference repository
+itself (block grid, box expansion, masks, hooks, model surgery, classifier) runs unmodified.
+
+Stubbed behaviour that the reference does not show is chosen explicitly and
+recorded in DESIGN.md section 8:
+  * todd ``BBoxes.indices(min_wh)``: inclusive (w >= 4 and h >= 4).
+  * ``clip`` fork ``interpolate_positional_embedding``: bilinear, align_corners=False.
+The ``clip.model`` classes restate the published openai/CLIP ``model.py`` (module tree, parameter
+names, sequence-first activations) -- the reference's hooks are written against that tree.
+"""
+from __future__ import annotations
+
+import enum
+import logging
+import os
+import sys
+import types
+from collections import OrderedDict
+from typing import Any, Iterator
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torchvision.transforms as T
+
+# --------------------------------------------------------------------------------------- todd
+
+
+class _StoreMeta(type):
+    """Class attributes annotated ``bool`` read the environment (todd.StoreMeta)."""
+
+    def __getattr__(cls, name: str) -> Any:
+        ann = {}
+        for klass in cls.__mro__:
+            ann.update(getattr(klass, '__annotations__', {}))
+        if name in ann:
+            raw = os.environ.get(name, '')
+            if ann[name] in (bool, 'bool'):
+                return raw not in ('', '0', 'False', 'false')
+            return raw
+        raise AttributeError(name)
+
+
+class _Store(metaclass=_StoreMeta):
+    CUDA: bool
+    CPU: bool
+    MPS: bool
+    DRY_RUN: bool
+    TRAIN_WITH_VAL_DATASET: bool
+
+
+class _NonInstantiableMeta(type):
+
+    def __call__(cls, *args, **kwargs):
+        raise RuntimeError(f'{cls.__name__} is not instantiable')
+
+
+class _RegistryMeta(type):
+    """todd.Registry: the class itself is the registry (``@DatasetRegistry.register()``)."""
+
+    def __init__(cls, name, bases, ns):
+        super().__init__(name, bases, ns)
+        cls._items = {}
+
+    def register(cls, *names):
+
+        def deco(obj):
+            for n in names or (obj.__name__, ):
+                cls._items[n] = obj
+            return obj
+
+        return deco
+
+    def build(cls, config, default_config=None):
+        cfg = dict(default_config or {})
+        cfg.update(config)
+        return cls._items[cfg.pop('type')](**cfg)
+
+
+class _Registry(metaclass=_RegistryMeta):
+    pass
+
+
+class _BBoxes:
+    """Subset of todd 0.3.0 ``BBoxes`` the reference touches (objects.py:76-186)."""
+
+    def __init__(self, t: torch.Tensor) -> None:
+        self._t = t
+
+    def __len__(self) -> int:
+        return self._t.shape[0]
+
+    def __getitem__(self, idx) -> '_BBoxes':
+        return type(self)(self._t[idx])
+
+    def __iter__(self) -> Iterator[tuple]:
+        for row in self.to(_BBoxesXYXY)._t.tolist():  # python floats: PIL.Image.crop needs them
+            yield tuple(row)
+
+    def to_tensor(self) -> torch.Tensor:
+        return self._t
+
+    def to(self, cls) -> '_BBoxes':
+        if cls is type(self):
+            return self
+        return cls(cls._from_ltrb(self.lt, self.rb))
+
+    @property
+    def wh(self) -> torch.Tensor:
+        return self.rb - self.lt
+
+    @property
+    def area(self) -> torch.Tensor:
+        wh = self.wh
+        return wh[:, 0] * wh[:, 1]
+
+    @property
+    def center(self) -> torch.Tensor:
+        return (self.lt + self.rb) / 2
+
+    def indices(self, min_wh=None) -> torch.Tensor:
+        wh = self.wh
+        return (wh[:, 0] >= min_wh[0]) & (wh[:, 1] >= min_wh[1])
+
+
+class _BBoxesXYXY(_BBoxes):
+
+    @property
+    def lt(self) -> torch.Tensor:
+        return self._t[:, :2]
+
+    @property
+    def rb(self) -> torch.Tensor:
+        return self._t[:, 2:]
+
+    @staticmethod
+    def _from_ltrb(lt, rb):
+        return torch.cat([lt, rb], -1)
+
+    def translate(self, offset: torch.Tensor) -> '_BBoxesXYXY':
+        return _BBoxesXYXY(self._t + torch.cat([offset, offset], -1))
+
+
+class _BBoxesCXCYWH(_BBoxes):
+
+    @property
+    def center(self) -> torch.Tensor:
+        return self._t[:, :2]
+
+    @property
+    def wh(self) -> torch.Tensor:
+        return self._t[:, 2:]
+
+    @property
+    def lt(self) -> torch.Tensor:
+        return self._t[:, :2] - self._t[:, 2:] / 2
+
+    @property
+    def rb(self) -> torch.Tensor:
+        return self._t[:, :2] + self._t[:, 2:] / 2
+
+    @staticmethod
+    def _from_ltrb(lt, rb):
+        return torch.cat([(lt + rb) / 2, rb - lt], -1)
+
+    def translate(self, offset: torch.Tensor) -> '_BBoxesCXCYWH':
+        return _BBoxesCXCYWH(torch.cat([self._t[:, :2] + offset, self._t[:, 2:]], -1))
+
+
+class _Config(dict):
+    __getattr__ = dict.__getitem__
+
+    @staticmethod
+    def load(path):  # never reached by the fixture generator
+        raise NotImplementedError
+
+
+class _Validator:
+    """todd.utils.Validator is only subclassed, never run, by the fixture generator."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        pass
+
+    def _control_run_iter(self, batch, memo):
+        return None
+
+    def _run_iter(self, batch, memo):
+        return None
+
+
+class _Control(enum.Enum):
+    CONTINUE = enum.auto()
+    BREAK = enum.auto()
+
+
+def _make_todd() -> types.ModuleType:
+    todd = types.ModuleType('todd')
+    todd.Module = nn.Module
+    todd.StoreMeta = _StoreMeta
+    todd.NonInstantiableMeta = _NonInstantiableMeta
+    todd.Store = _Store
+    todd.Registry = _Registry
+    todd.BBox = tuple
+    todd.BBoxes = _BBoxes
+    todd.BBoxesXYXY = _BBoxesXYXY
+    todd.BBoxesCXCYWH = _BBoxesCXCYWH
+    todd.Config = _Config
+    todd.logger = logging.getLogger('todd-stub')
+    todd.get_local_rank = lambda: int(os.environ.get('LOCAL_RANK', 0))
+    todd.utils = types.ModuleType('todd.utils')
+    todd.utils.Validator = _Validator
+    todd.utils.Memo = dict
+    todd.utils.Control = _Control
+    todd.base = types.ModuleType('todd.base')
+    todd.base.DictAction = object
+    return todd
+
+
+# ------------------------------------------------------------------------- mmdet LINEAR_LAYERS
+
+
+class _MMRegistry:
+
+    def __init__(self) -> None:
+        self.module_dict = {}
+
+    def register_module(self, name=None, force=False, module=None):
+
+        def deco(obj):
+            self.module_dict[name or obj.__name__] = obj
+            return obj
+
+        return deco if module is None else deco(module)
+
+
+# ----------------------------------------------------------------------- clip (openai layout)
+
+
+class LayerNorm(nn.LayerNorm):
+    """fp32 LayerNorm, cast back (openai/CLIP model.py)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return super().forward(x.float()).type(x.dtype)
+
+
+class QuickGELU(nn.Module):
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return x * torch.sigmoid(1.702 * x)
+
+
+class ResidualAttentionBlock(nn.Module):
+
+    def __init__(self, d_model: int, n_head: int, attn_mask=None) -> None:
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = LayerNorm(d_model)
+        self.mlp = nn.Sequential(
+            OrderedDict([('c_fc', nn.Linear(d_model, d_model * 4)), ('gelu', QuickGELU()),
+                         ('c_proj', nn.Linear(d_model * 4, d_model))]))
+        self.ln_2 = LayerNorm(d_model)
+        self.attn_mask = attn_mask
+
+    def attention(self, x: torch.Tensor) -> torch.Tensor:
+        return self.attn(x, x, x, need_weights=False, attn_mask=self.attn_mask)[0]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = x + self.attention(self.ln_1(x))
+        x = x + self.mlp(self.ln_2(x))
+        return x
+
+
+class Transformer(nn.Module):
+
+    def __init__(self, width: int, layers: int, heads: int) -> None:
+        super().__init__()
+        self.width = width
+        self.layers = layers
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads) for _ in range(layers)])
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.resblocks(x)
+
+
+class VisionTransformer(nn.Module):
+
+    def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int,
+                 output_dim: int) -> None:
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.output_dim = output_dim
+        self.patch_size = patch_size  # fork attribute (objects.py:301)
+        self.grid = input_resolution // patch_size  # fork attribute (objects.py:281,297)
+        self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
+        scale = width**-0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(self.grid**2 + 1, width))
+        self.ln_pre = LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+    def interpolate_positional_embedding(self, size) -> torch.Tensor:
+        """Fork method (objects.py:293-295); mode unseen -- bilinear, align_corners=False."""
+        pe = self.positional_embedding.detach()
+        cls_row, grid = pe[:1], pe[1:]
+        d = grid.shape[1]
+        grid = grid.reshape(1, self.grid, self.grid, d).permute(0, 3, 1, 2)
+        grid = F.interpolate(grid, size=tuple(size), mode='bilinear', align_corners=False)
+        grid = grid.permute(0, 2, 3, 1).reshape(size[0] * size[1], d)
+        return torch.cat([cls_row, grid])
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.conv1(x)
+        x = x.reshape(x.shape[0], x.shape[1], -1)
+        x = x.permute(0, 2, 1)
+        cls_tok = self.class_embedding.to(x.dtype) + torch.zeros(
+            x.shape[0], 1, x.shape[-1], dtype=x.dtype, device=x.device)
+        x = torch.cat([cls_tok, x], dim=1)
+        x = x + self.positional_embedding.to(x.dtype)
+        x = self.ln_pre(x)
+        x = x.permute(1, 0, 2)
+        x = self.transformer(x)
+        x = x.permute(1, 0, 2)
+        x = self.ln_post(x[:, 0, :])
+        if self.proj is not None:
+            x = x @ self.proj
+        return x
+
+
+class CLIP(nn.Module):
+    """Image half only (the text tower is not on the OAKE path)."""
+
+    def __init__(self, layers: int = 12) -> None:
+        super().__init__()
+        self.visual = VisionTransformer(224, 32, 768, layers, 12, 512)
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.visual.conv1.weight.dtype
+
+    def encode_image(self, image: torch.Tensor) -> torch.Tensor:
+        return self.visual(image.type(self.dtype))
+
+
+def clip_transform(n_px: int = 224) -> T.Compose:
+    """openai/CLIP ``clip.py::_transform``."""
+    return T.Compose([
+        T.Resize(n_px, interpolation=T.InterpolationMode.BICUBIC),
+        T.CenterCrop(n_px),
+        lambda image: image.convert('RGB'),
+        T.ToTensor(),
+        T.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)),
+    ])
+
+
+_STATE = {'params': None, 'layers': 12}
+
+
+def set_clip_weights(params: dict) -> None:
+    """OpenAI-named visual-tower state dict used by the next ``clip.load_default``."""
+    _STATE['params'] = params
+    _STATE['layers'] = 1 + max(int(k.split('.')[2]) for k in params if k.startswith('transformer.resblocks.'))
+
+
+def _load_default(jit: bool = False):
+    model = CLIP(_STATE['layers'])
+    model.visual.load_state_dict({k: v.clone() for k, v in _STATE['params'].items()}, strict=True)
+    return model.eval(), clip_transform(224)
+
+
+def install() -> None:
+    """Places the stub packages in ``sys.modules`` (idempotent)."""
+    if 'todd' in sys.modules and getattr(sys.modules['todd'], '_oadp_b200_stub', False):
+        return
+    todd = _make_todd()
+    todd._oadp_b200_stub = True
+    sys.modules['todd'] = todd
+    sys.modules['todd.utils'] = todd.utils
+    sys.modules['todd.base'] = todd.base
+    clip = types.ModuleType('clip')
+    clip.model = types.ModuleType('clip.model')
+    for k in (CLIP, VisionTransformer, Transformer, ResidualAttentionBlock, LayerNorm, QuickGELU):
+        setattr(clip.model, k.__name__, k)
+    clip.load_default = _load_default
+    sys.modules['clip'] = clip
+    sys.modules['clip.model'] = clip.model
+    for name in ('mmdet', 'mmdet.models', 'mmdet.models.utils', 'mmdet.models.utils.builder'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['mmdet.models.utils.builder'].LINEAR_LAYERS = _MMRegistry()
