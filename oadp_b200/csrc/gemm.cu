@@ -41,8 +41,11 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 128 + 32 * kEpiWarps;
+// Epilogue warps per CTA: 8 (two per TMEM lane quarter) or 16 (four per quarter).  The LayerNorm-fold
+// / QuickGELU epilogues of the K = 768 GEMMs (QKV, c_fc) are bound by the latency of their dependent
+// tcgen05.ld -> math -> pack -> store chain, not by issue slots: sixteen warps keep four chains per
+// SM sub-partition in flight.  $OAKE_GEMM_EPI_WARPS=8 restores eight everywhere (A/B runs).
+constexpr int epi_warps_for(int mode) { return mode == 1 /* EPI_ACT */ ? 16 : 8; }
 
 enum EpiMode {
   EPI_F32 = 0,  // fp32 out: bias, QuickGELU
@@ -61,14 +64,25 @@ int cta_group() {
   return v;
 }
 
-template <int BN, int CG = 1>
+int epi_warps_act() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("OAKE_GEMM_EPI_WARPS");
+    v = (e != nullptr && e[0] == '8') ? 8 : 16;
+  }
+  return v;
+}
+
+template <int BN, int CG = 1, int EW = 8>
 struct Cfg {
-  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : 6;
+  static constexpr int kEpiWarps = EW;
+  static constexpr int kThreads = 128 + 32 * EW;
+  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : (EW == 16 ? 5 : 6);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kWarpCols = BN / 2;                  // columns owned by one epilogue warp
+  static constexpr int kWarpCols = BN / (EW / 4);           // columns owned by one epilogue warp
   static constexpr int kStgBytes = 32 * 64;                 // 32 rows x 64 B, XOR-swizzled
   static constexpr int kVecBytes = 2 * kWarpCols * 4;       // bias + colsum of the warp's columns (x2: double buffered)
   static constexpr int kSmemBytes =
@@ -104,11 +118,11 @@ struct RowLn {
 //   y = [fold] rstd_m * acc + (nmr_m * s_n + c_n)   |   acc + bias_n
 //   y = QuickGELU(y)                 (c_fc)
 //   y += residual (act_t, may alias out), statistics (sum y, sum y^2)   (out_proj, c_proj)
-template <int BN, int MODE>
+template <int BN, int MODE, int EW>
 __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_warp, uint8_t* stg,
                                              const float* vec, int row0, int col_base, int M, int lane,
                                              uint4 (&res)[4], const RowLn ln, int next_row0, int next_col_base) {
-  constexpr int WC = Cfg<BN>::kWarpCols;
+  constexpr int WC = Cfg<BN, 1, EW>::kWarpCols;
   constexpr int NP = WC / 32;
   const int sub_r = lane >> 2;  // coalesced phase: 8 rows per instruction, 4 lanes x 16 B per row
   const int sub_c = lane & 3;
@@ -213,10 +227,10 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
 }
 
 // fp32 output (patch embedding, final projection): bias / QuickGELU, pieces of 16 columns.
-template <int BN>
+template <int BN, int EW>
 __device__ __forceinline__ void epilogue_f32(const GemmEpilogue& ep, uint32_t t_warp, uint8_t* stg,
                                              const float* vec, int row0, int col_base, int M, int lane) {
-  constexpr int WC = Cfg<BN>::kWarpCols;
+  constexpr int WC = Cfg<BN, 1, EW>::kWarpCols;
   const int sub_r = lane >> 2;
   const int sub_c = lane & 3;
 #pragma unroll 1
@@ -256,11 +270,12 @@ __device__ __forceinline__ void epilogue_f32(const GemmEpilogue& ep, uint32_t t_
   }
 }
 
-template <int BN, int MODE, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int MODE, int CG, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     int M, int N, int K, GemmEpilogue ep) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, EW>;
+  constexpr int kEpiWarps = EW;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -391,7 +406,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ---------------------------------------------------------------------- epilogue
     const int e = warp - 4;
     const int q = e & 3;    // == warp % 4: the TMEM lane quarter this warp may read
-    const int ch = e >> 2;  // which half of the tile's columns
+    const int ch = e >> 2;  // which slice (half / quarter) of the tile's columns
     uint8_t* stg = stg_base + e * C::kStgBytes;
     float* vec2 = reinterpret_cast<float*>(vec_base + e * 2 * C::kVecBytes);  // two buffers, one per tile parity
     const bool fold = MODE == EPI_ACT && ep.colsum != nullptr;
@@ -476,9 +491,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t t_warp = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(acc * BN + ch * C::kWarpCols);
       if (MODE == EPI_F32)
-        epilogue_f32<BN>(ep, t_warp, stg, vec, row0, col_base, M, lane);
+        epilogue_f32<BN, EW>(ep, t_warp, stg, vec, row0, col_base, M, lane);
       else
-        epilogue_act<BN, MODE>(ep, t_warp, stg, vec, row0, col_base, M, lane, res, ln, next_row0, next_col_base);
+        epilogue_act<BN, MODE, EW>(ep, t_warp, stg, vec, row0, col_base, M, lane, res, ln, next_row0, next_col_base);
       tc_fence_before();
       __syncwarp();  // every lane is done with TMEM and with `vec` before they are handed back
       if (lane == 0) {
@@ -556,13 +571,13 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-template <int BN, int MODE, int CG>
+template <int BN, int MODE, int CG, int EW>
 cudaError_t launch_gemm_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N,
                              int K, const GemmEpilogue& ep, int num_sms) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, CG>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, CG, EW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -572,7 +587,7 @@ cudaError_t launch_gemm_inst(cudaStream_t st, const CUtensorMap& tmA, const CUte
   const int grid = (tiles < slots ? tiles : slots) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -582,15 +597,17 @@ cudaError_t launch_gemm_inst(cudaStream_t st, const CUtensorMap& tmA, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, CG>, tmA, tmW, M, N, K, ep);
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, MODE, CG, EW>, tmA, tmW, M, N, K, ep);
 }
 
 template <int BN, int CG>
 cudaError_t launch_gemm_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N, int K,
                            const GemmEpilogue& ep, int num_sms) {
-  if (ep.out_f32) return launch_gemm_inst<BN, EPI_F32, CG>(st, tmA, tmW, M, N, K, ep, num_sms);
-  if (ep.residual != nullptr) return launch_gemm_inst<BN, EPI_RES, CG>(st, tmA, tmW, M, N, K, ep, num_sms);
-  return launch_gemm_inst<BN, EPI_ACT, CG>(st, tmA, tmW, M, N, K, ep, num_sms);
+  if (ep.out_f32) return launch_gemm_inst<BN, EPI_F32, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
+  if (ep.residual != nullptr) return launch_gemm_inst<BN, EPI_RES, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
+  if (BN == 256 && CG == 2 && epi_warps_act() == 16)  // (the 1-CTA 256-wide tile has no shared memory left for it)
+    return launch_gemm_inst<BN, EPI_ACT, CG, BN == 256 ? epi_warps_for(EPI_ACT) : 8>(st, tmA, tmW, M, N, K, ep, num_sms);
+  return launch_gemm_inst<BN, EPI_ACT, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
 }
 
 }  // namespace

@@ -12,6 +12,8 @@ Changed on purpose (B200-first):
   * images are grouped into batches of `batch_images` so that the tower always sees SM-filling
     crop counts, and sharded across ranks by crop count (`oadp_b200.dist`) without duplicates
   * files are written by a small thread pool while the GPU works on the next batch
+  * `--override .store:packed` writes one packed shard per rank (`oadp_b200.store.PackedStore`,
+    SURVEY 8f-1) instead of one pickle per image; resume then skips the keys already in a shard
 """
 from __future__ import annotations
 
@@ -30,6 +32,7 @@ from .. import dist as oake_dist
 from ..compat import CocoImages, Config, DictAction, Store
 from ..model import OakeModel
 from ..pipeline import OakePipeline
+from ..store import PackedStore, PackedWriter, key_of
 
 
 class Item(NamedTuple):
@@ -53,7 +56,13 @@ class BaseDataset(CocoImages, ABC, Generic[T]):
     def output_path(self, id_: int) -> pathlib.Path:
         return self._output_dir / f'{id_:012d}.pth'
 
+    def use_packed(self) -> None:
+        """Resume against the packed shards in the output directory instead of `.pth` files."""
+        self._packed_done = set(PackedStore(str(self._output_dir)).keys())
+
     def is_done(self, id_: int) -> bool:
+        if getattr(self, '_packed_done', None) is not None:
+            return key_of(id_) in self._packed_done
         output = self.output_path(id_)
         if not output.exists():
             return False
@@ -112,14 +121,31 @@ class BaseValidator(ABC, Generic[T]):
     DATASET = BaseDataset
 
     def __init__(self, name: str, model: OakeModel, *, dataloader: Config, log: Optional[Config] = None,
-                 batch_images: int = 8, **_: Any) -> None:
+                 batch_images: int = 8, store: str = 'pth', **_: Any) -> None:
         self._name = name
         self._model = model
         self._pipeline = OakePipeline(model.engine)
         self._log_interval = int((log or {}).get('interval', 50))
         self._batch_images = 1 if Store.DRY_RUN else int(batch_images)
         self._dataset = self._build_dataset(Config(dataloader.dataset))
-        self._writer = concurrent.futures.ThreadPoolExecutor(max_workers=int(dataloader.get('num_workers', 2)) or 1)
+        if store not in ('pth', 'packed'):
+            raise ValueError(f"store must be 'pth' or 'packed', not {store!r}")
+        self._packed: Optional[PackedWriter] = None
+        workers = int(dataloader.get('num_workers', 2)) or 1
+        if store == 'packed':
+            self._dataset.use_packed()
+            out_dir = self._dataset._output_dir
+            rank, _world = oake_dist.rank_world()
+            serial = len(list(out_dir.glob(f'shard-{rank:05d}-*.idx.json')))
+            self._packed = PackedWriter(str(out_dir), '', f'shard-{rank:05d}-{serial:03d}')
+            workers = 1  # appends to one file, in order
+        self._writer = concurrent.futures.ThreadPoolExecutor(max_workers=workers)
+
+    def _write(self, result: Any, item: Item) -> None:
+        if self._packed is not None:
+            self._packed.add(key_of(item.id_), result)
+        else:
+            torch.save(result, item.output)
 
     # ------------------------------------------------------------------ to be provided per task
     @classmethod
@@ -167,7 +193,7 @@ class BaseValidator(ABC, Generic[T]):
         def drain(entry):
             batch_, ticket = entry
             for item, result in zip(batch_, ticket.result()):
-                pending.append(self._writer.submit(torch.save, result, item.output))
+                pending.append(self._writer.submit(self._write, result, item))
 
         for batch in itertools.chain(self._batches(indices), [None]):
             nxt = (batch, self._submit(batch)) if batch is not None else None
@@ -190,6 +216,8 @@ class BaseValidator(ABC, Generic[T]):
         for f in pending:
             f.result()
         self._writer.shutdown(wait=True)
+        if self._packed is not None:
+            self._packed.close()
         return done
 
     @classmethod

@@ -78,3 +78,28 @@ def test_cli_dry_run(dataset, monkeypatch, tmp_path):
     files = sorted((out / 'val').glob('*.pth'))
     assert 1 <= len(files) <= 3
     assert torch.load(files[0])['embeddings'].shape[0] <= 5  # objects.py:166-167
+
+
+def test_cli_packed_store_matches_pth(dataset, monkeypatch, tmp_path):
+    """`--override .store:packed`: one shard per rank holding exactly what the `.pth`
+    files hold; a second run resumes from the shard index and writes nothing new."""
+    monkeypatch.delenv('DRY_RUN', raising=False)
+    import oadp.oake.blocks as cli_blocks
+    from oadp_b200 import store
+    root = pathlib.Path(dataset['root'])
+    out = tmp_path / 'packed'
+    ov = ['--override', '.store:packed', f'.val.dataloader.dataset.output_dir::{out}/val',
+          f'.train.dataloader.dataset.output_dir::{out}/train']
+    cli_blocks.Validator.main(['t', dataset['configs']['blocks']] + ov)
+    packed = store.PackedStore(str(out), 'val')
+    assert list(packed) == [f'{i:012d}' for i in dataset['ids']]
+    if not (root / 'oake' / 'blocks' / 'val').exists():
+        cli_blocks.Validator.main(['t', dataset['configs']['blocks']])
+    pth = store.PthStore(str(root / 'oake' / 'blocks'), 'val')
+    for k in packed:
+        a, b = packed[k], pth[k]
+        assert torch.equal(a['embeddings'], b['embeddings']) and torch.equal(a['bboxes'], b['bboxes'])
+    cli_blocks.Validator.main(['t', dataset['configs']['blocks']] + ov)  # resume
+    again = store.PackedStore(str(out), 'val')
+    assert len(again) == len(packed)
+    assert sum(1 for _ in (out / 'val').glob('*.idx.json')) == 2  # the second run's (empty) shard
