@@ -167,6 +167,15 @@ int oake_cosine_logits_bwd(const float* h, const float* text, const float* bg, c
                            int num_all, int k_pad, float alpha, int ninf_lo, int ninf_hi, float* dh, float* dbg,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* ---- ViLD ensemble scoring (oadp/dp/roi_heads.py:93-112, ViLDEnsembleRoIHead._bbox_forward) ------
+ * out = log( softmax(bbox_logits)^lambda * softmax(object_logits)^(1-lambda) ), last column replaced
+ * by log(1 - sum of the others).  All fp32 device pointers; logits (N, K1 = num_all + 1) with row
+ * pitches ld_* >= K1 (the k_pad pitch of oake_cosine_logits_fwd is accepted as is); lambda [K1] is
+ * the `_lambda` buffer of the reference (2/3 base, 1/3 novel + background, roi_heads.py:55-59).
+ * -inf logits (ObjectMixin forces the background column to -inf, bbox_heads.py:57-60) score 0. */
+int oake_vild_ensemble(const float* bbox_logits, const float* object_logits, const float* lambda, int N, int K1,
+                       int ld_bbox, int ld_object, float* out, int ld_out, void* stream);
+
 /* Error string of the last failing call on this thread ("" if none). */
 const char* oake_last_error(void);
 /* "f16" or "bf16": element type of `act` tensors. */

@@ -52,6 +52,8 @@ SIGNATURES = {
     'oake_cosine_logits_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_size_t, C.c_void_p]),
+    'oake_vild_ensemble': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_void_p]),
     'oake_last_error': (C.c_char_p, []),
     'oake_act_dtype': (C.c_char_p, []),
     'oake_abi_version': (C.c_int, []),

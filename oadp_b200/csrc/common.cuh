@@ -216,8 +216,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// Remote arrive on a peer CTA's barrier.  Default semantics (release at CTA scope), as CUTLASS'
+// ClusterBarrier::arrive: the TMEM hand-over it signals is ordered by the tcgen05 fences around it.
+// A `.release.cluster` arrive instead makes every epilogue warp drain ALL of its outstanding global
+// stores first (MEMBAR + ERRBAR, ~1 us per tile: the top stall of the K = 768 GEMMs in ncu).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result) {  // same warp id in both CTAs

@@ -148,8 +148,9 @@ __device__ __forceinline__ double pil_bicubic(double x) {
 
 // libImaging precompute_coeffs + normalize_coeffs_8bpc, split so that a whole CTA shares the work:
 // pil_bounds (one thread per output sample) fixes the tap window, pil_weight (one thread per tap)
-// evaluates the filter in double precision, pil_normalize (one thread per sample) performs the
-// sequential sum / divide / fixed-point rounding exactly in libImaging's order.
+// evaluates the filter in double precision, pil_weight_sum (one thread per sample) performs the
+// sequential weight sum in libImaging's order; the divide / fixed-point rounding of every tap is
+// independent again (pil_fixed, one thread per tap).
 struct PilAxis {
   double scale, ss, support;
 };
@@ -177,15 +178,15 @@ __device__ __forceinline__ double pil_weight(const PilAxis& a, int xx, int xmin,
   const double arg = __dmul_rn(__dadd_rn(__dadd_rn(static_cast<double>(x + xmin), -center), 0.5), a.ss);
   return pil_bicubic(arg);
 }
-__device__ __forceinline__ void pil_normalize(const double* w, int count, int* k) {
+__device__ __forceinline__ double pil_weight_sum(const double* w, int count) {  // libImaging's order
   double ww = 0.0;
   for (int x = 0; x < count; ++x) ww = __dadd_rn(ww, w[x]);
-  for (int x = 0; x < count; ++x) {
-    double v = w[x];
-    if (ww != 0.0) v = __ddiv_rn(v, ww);
-    const double f = __dmul_rn(v, static_cast<double>(1 << kPrecBits));
-    k[x] = v < 0.0 ? static_cast<int>(__dadd_rn(-0.5, f)) : static_cast<int>(__dadd_rn(0.5, f));
-  }
+  return ww;
+}
+__device__ __forceinline__ int pil_fixed(double v, double ww) {  // normalise + 22-bit fixed point
+  if (ww != 0.0) v = __ddiv_rn(v, ww);
+  const double f = __dmul_rn(v, static_cast<double>(1 << kPrecBits));
+  return v < 0.0 ? static_cast<int>(__dadd_rn(-0.5, f)) : static_cast<int>(__dadd_rn(0.5, f));
 }
 
 __device__ __forceinline__ uint8_t pil_clip8(int ss) {
@@ -198,6 +199,7 @@ struct ResizeSmem {
   int kv[kTile][kMaxTaps];
   int h_first[kTile], h_count[kTile], v_first[kTile], v_count[kTile];
   int r_lo, r_hi;
+  double ww[2 * kTile];
   union {
     double w[2 * kTile][kMaxTaps];    // raw filter weights (coefficient phase): [0,32) horizontal, [32,64) vertical
     uint8_t tmp[kMaxRows][kTile][3];  // horizontally resampled rows (pixel phase)
@@ -239,10 +241,20 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
   }
   __syncthreads();
   if (tid < kTile) {
-    if (tid < tw) pil_normalize(sm.w[tid], sm.h_count[tid], sm.kh[tid]);
+    if (tid < tw) sm.ww[tid] = pil_weight_sum(sm.w[tid], sm.h_count[tid]);
   } else if (tid < 2 * kTile) {
     const int r = tid - kTile;
-    if (r < th) pil_normalize(sm.w[tid], sm.v_count[r], sm.kv[r]);
+    if (r < th) sm.ww[tid] = pil_weight_sum(sm.w[tid], sm.v_count[r]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 2 * kTile * kMaxTaps; idx += blockDim.x) {
+    const int sidx = idx / kMaxTaps, x = idx - sidx * kMaxTaps;
+    if (sidx < kTile) {
+      if (sidx < tw && x < sm.h_count[sidx]) sm.kh[sidx][x] = pil_fixed(sm.w[sidx][x], sm.ww[sidx]);
+    } else {
+      const int r = sidx - kTile;
+      if (r < th && x < sm.v_count[r]) sm.kv[r][x] = pil_fixed(sm.w[sidx][x], sm.ww[sidx]);
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -257,44 +269,57 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
   const int nr = min(sm.r_hi - r_lo, kMaxRows);
   const uint8_t* src = src_arena + job.src_off;
 
-  // horizontal pass: crop rows [r_lo, r_lo + nr) -> tmp (uint8, like Pillow's intermediate image)
-  const int row_elems = tw * 3;
-  for (int idx = tid; idx < nr * row_elems; idx += blockDim.x) {
-    const int r = idx / row_elems;
-    const int rem = idx - r * row_elems;
-    const int j = rem / 3, c = rem - j * 3;
+  // horizontal pass: crop rows [r_lo, r_lo + nr) -> tmp (uint8, like Pillow's intermediate image).
+  // One thread per (row, output column): the three channels share the tap loop, and the taps that
+  // fall outside the source image (zero padding of PIL `crop`) are cut off once, outside the loop.
+  for (int idx = tid; idx < nr * tw; idx += blockDim.x) {
+    const int r = idx / tw;
+    const int j = idx - r * tw;
     const int y = job.box_y0 + r_lo + r;
-    int ss = 1 << (kPrecBits - 1);
+    int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
     if (y >= 0 && y < job.src_h) {
-      const uint8_t* line = src + static_cast<long long>(y) * job.src_pitch_px * 3;
       const int first = job.box_x0 + sm.h_first[j];
-      const int n = sm.h_count[j];
+      const int t0 = max(0, -first);
+      const int t1 = min(sm.h_count[j], job.src_w - first);
+      const uint8_t* px = src + (static_cast<long long>(y) * job.src_pitch_px + first + t0) * 3;
       const int* k = sm.kh[j];
-      for (int t = 0; t < n; ++t) {
-        const int x = first + t;
-        if (x >= 0 && x < job.src_w) ss += static_cast<int>(line[x * 3 + c]) * k[t];
+#pragma unroll 4
+      for (int t = t0; t < t1; ++t, px += 3) {
+        const int kk = k[t];
+        s0 += static_cast<int>(px[0]) * kk;
+        s1 += static_cast<int>(px[1]) * kk;
+        s2 += static_cast<int>(px[2]) * kk;
       }
     }
-    sm.tmp[r][j][c] = pil_clip8(ss);
+    uint8_t* o = sm.tmp[r][j];
+    o[0] = pil_clip8(s0);
+    o[1] = pil_clip8(s1);
+    o[2] = pil_clip8(s2);
   }
   __syncthreads();
 
   // vertical pass
   uint8_t* dst = dst_arena + job.dst_off;
-  for (int idx = tid; idx < th * row_elems; idx += blockDim.x) {
-    const int r = idx / row_elems;
-    const int rem = idx - r * row_elems;
-    const int j = rem / 3, c = rem - j * 3;
+  for (int idx = tid; idx < th * tw; idx += blockDim.x) {
+    const int r = idx / tw;
+    const int j = idx - r * tw;
     const int first = sm.v_first[r] - r_lo;
-    const int n = sm.v_count[r];
+    const int t1 = min(sm.v_count[r], nr - first);
     const int* k = sm.kv[r];
-    int ss = 1 << (kPrecBits - 1);
-    for (int t = 0; t < n; ++t) {
-      const int rr = first + t;
-      if (rr < nr) ss += static_cast<int>(sm.tmp[rr][j][c]) * k[t];
+    const uint8_t* px = sm.tmp[first][j];
+    int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
+#pragma unroll 4
+    for (int t = 0; t < t1; ++t, px += kTile * 3) {
+      const int kk = k[t];
+      s0 += static_cast<int>(px[0]) * kk;
+      s1 += static_cast<int>(px[1]) * kk;
+      s2 += static_cast<int>(px[2]) * kk;
     }
     const int oy = oy0 - job.win_y + r, ox = ox0 - job.win_x + j;
-    dst[(static_cast<long long>(oy) * job.dst_pitch_px + ox) * 3 + c] = pil_clip8(ss);
+    uint8_t* o = dst + (static_cast<long long>(oy) * job.dst_pitch_px + ox) * 3;
+    o[0] = pil_clip8(s0);
+    o[1] = pil_clip8(s1);
+    o[2] = pil_clip8(s2);
   }
 }
 

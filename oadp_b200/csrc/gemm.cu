@@ -44,7 +44,9 @@ constexpr int UMMA_K = 16;
 // Epilogue warps per CTA: 8 (two per TMEM lane quarter) or 16 (four per quarter).  The LayerNorm-fold
 // / QuickGELU epilogues of the K = 768 GEMMs (QKV, c_fc) are bound by the latency of their dependent
 // tcgen05.ld -> math -> pack -> store chain, not by issue slots: sixteen warps keep four chains per
-// SM sub-partition in flight.  $OAKE_GEMM_EPI_WARPS=8 restores eight everywhere (A/B runs).
+// SM sub-partition in flight.  Opt-in ($OAKE_GEMM_EPI_WARPS=16): measured slower than eight on B200
+// (c_fc 878 vs 1015 TFLOP/s) -- the epilogue was bound by a cluster-scope release fence, not by
+// latency hiding (see mbar_arrive_cluster).
 constexpr int epi_warps_for(int mode) { return mode == 1 /* EPI_ACT */ ? 16 : 8; }
 
 enum EpiMode {
@@ -68,7 +70,7 @@ int epi_warps_act() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("OAKE_GEMM_EPI_WARPS");
-    v = (e != nullptr && e[0] == '8') ? 8 : 16;
+    v = (e != nullptr && e[0] == '1') ? 16 : 8;  // measured r1: 16 warps are slower (5 stages, 96 registers)
   }
   return v;
 }

@@ -53,3 +53,13 @@ def object_head_logits(logits: torch.Tensor) -> torch.Tensor:
     out = logits.clone()
     out[:, -1] = float('-inf')
     return out
+
+
+def vild_ensemble(bbox_logits: torch.Tensor, object_logits: torch.Tensor, lambda_: torch.Tensor) -> torch.Tensor:
+    """oadp/dp/roi_heads.py:93-112 (inference branch of ViLDEnsembleRoIHead._bbox_forward), line by
+    line: softmax ** lambda, softmax ** (1 - lambda), product, background = 1 - sum, log."""
+    bbox_scores = bbox_logits.softmax(-1)**lambda_
+    object_scores = object_logits.softmax(-1)**(1 - lambda_)
+    cls_score = bbox_scores * object_scores
+    cls_score[:, -1] = 1 - cls_score[:, :-1].sum(-1)
+    return cls_score.log()
