@@ -73,6 +73,14 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   // volatile: the two softmax passes must each re-read the mask row instead of keeping 196 biases
@@ -496,7 +504,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
         if (lane == 0) mbar_arrive(&o_free[t]);
         // rows -> shared memory (one 128-byte row per lane, 16-byte chunks XOR-swizzled), then every
         // store instruction writes four whole 128-byte rows of the output
-        uint8_t* stg = out_stage + warp * C::kOutStage;
+        const uint32_t stg = smem_u32(out_stage + warp * C::kOutStage);
         {
           const float inv = 1.0f / sum;
           auto o_at = [&](int c) -> float {
@@ -510,7 +518,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
             v.y = pack2(o_at(8 * j + 2) * inv, o_at(8 * j + 3) * inv);
             v.z = pack2(o_at(8 * j + 4) * inv, o_at(8 * j + 5) * inv);
             v.w = pack2(o_at(8 * j + 6) * inv, o_at(8 * j + 7) * inv);
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+            sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v);
           }
         }
         __syncwarp();
@@ -523,7 +531,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
             const int rr2 = q * 32 + row - shift1;        // row of the tile's live range
             const bool live2 = t == 0 || (rr2 >= 0 && rr2 < C::kRows1);
             if (live2) {
-              const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
+              const uint4 v = lds128(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
               const int tok = t * 128 + rr2;
               *reinterpret_cast<uint4*>(out + static_cast<size_t>(token_row(tok, b, B, P)) * W + h * kDh + chunk * 8) = v;
             }

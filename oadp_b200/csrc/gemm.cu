@@ -111,6 +111,25 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ uint4* stg_chunk(uint8_t* stg, int row, int chunk) {
   return reinterpret_cast<uint4*>(stg + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
+// The same slot as a shared-window address, and explicit ld/st.shared on it: the strip and the
+// column vectors are reached through pointers derived from the aligned dynamic-smem base, which the
+// compiler can only treat as generic (LD.E / ST.E: longer latency, long-scoreboard tracking).
+__device__ __forceinline__ uint32_t stg_addr(uint32_t stg, int row, int chunk) {
+  return stg + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 struct RowLn {
   float rstd, nmr;  // y = rstd * acc + nmr * s_n + c_n,  nmr = -mean * rstd
@@ -132,6 +151,8 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
   const bool has_bias = ep.bias != nullptr;
   const bool gelu = MODE == EPI_ACT && ep.act == 1;
   float sum = 0.f, sumsq = 0.f;
+  const uint32_t stg_s = smem_u32(stg);
+  const uint32_t vec_s = smem_u32(vec);
   uint32_t r32[32];
   tmem_ld_32x32(t_warp, r32);
 #pragma unroll 1
@@ -139,7 +160,7 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
     const int col0 = col_base + pc * 32;
     if (MODE == EPI_RES) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) *stg_chunk(stg, 8 * i + sub_r, sub_c) = res[i];
+      for (int i = 0; i < 4; ++i) sts128(stg_addr(stg_s, 8 * i + sub_r, sub_c), res[i]);
       {  // next piece's residual (or the first piece of the warp's NEXT tile), in flight during the math
         const bool same = pc + 1 < NP;
         const int nr0 = same ? row0 : next_row0;
@@ -159,13 +180,13 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r32[j]);
     if (pc + 1 < NP) tmem_ld_32x32(t_warp + (pc + 1) * 32, r32);  // next piece, in flight during the math
-    const float4* c4 = reinterpret_cast<const float4*>(vec + pc * 32);
-    const float4* s4 = reinterpret_cast<const float4*>(vec + WC + pc * 32);
+    const uint32_t c4 = vec_s + pc * 32 * 4;
+    const uint32_t s4 = vec_s + (WC + pc * 32) * 4;
     if (fold) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 sv = s4[j];
-        const float4 cv = c4[j];
+        const float4 sv = lds128f(s4 + j * 16);
+        const float4 cv = lds128f(c4 + j * 16);
         v[4 * j + 0] = fmaf(ln.rstd, v[4 * j + 0], fmaf(ln.nmr, sv.x, cv.x));
         v[4 * j + 1] = fmaf(ln.rstd, v[4 * j + 1], fmaf(ln.nmr, sv.y, cv.y));
         v[4 * j + 2] = fmaf(ln.rstd, v[4 * j + 2], fmaf(ln.nmr, sv.z, cv.z));
@@ -174,7 +195,7 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
     } else if (has_bias) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 cv = c4[j];
+        const float4 cv = lds128f(c4 + j * 16);
         v[4 * j + 0] += cv.x;
         v[4 * j + 1] += cv.y;
         v[4 * j + 2] += cv.z;
@@ -187,9 +208,9 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint4* slot = stg_chunk(stg, lane, j);
+      const uint32_t slot = stg_addr(stg_s, lane, j);
       if (MODE == EPI_RES) {
-        const uint4 rv = *slot;
+        const uint4 rv = lds128(slot);
         const float2 r0 = unpack2(rv.x), r1 = unpack2(rv.y), r2 = unpack2(rv.z), r3 = unpack2(rv.w);
         v[8 * j + 0] += r0.x;
         v[8 * j + 1] += r0.y;
@@ -210,15 +231,17 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
       u.y = pack2(v[8 * j + 2], v[8 * j + 3]);
       u.z = pack2(v[8 * j + 4], v[8 * j + 5]);
       u.w = pack2(v[8 * j + 6], v[8 * j + 7]);
-      *slot = u;
+      sts128(slot, u);
     }
     __syncwarp();
+    uint4 o4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o4[i] = lds128(stg_addr(stg_s, 8 * i + sub_r, sub_c));
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = row0 + 8 * i + sub_r;
       if (r < M)
-        *reinterpret_cast<uint4*>(static_cast<act_t*>(ep.out) + static_cast<size_t>(r) * ep.ldo + col0 + sub_c * 8) =
-            *stg_chunk(stg, 8 * i + sub_r, sub_c);
+        *reinterpret_cast<uint4*>(static_cast<act_t*>(ep.out) + static_cast<size_t>(r) * ep.ldo + col0 + sub_c * 8) = o4[i];
     }
     __syncwarp();
   }
