@@ -14,6 +14,8 @@
 // online softmax, so only a 32-key slice of S lives in registers: ~2 CTAs/SM instead of 1, half
 // the ldmatrix traffic of a one-tile-per-warp layout (mma.sync m16n8k16, fp32 accumulate).
 // Attention is 1-4 % of the tower's FLOPs; the dense contractions go through the tcgen05 GEMM.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace oake {
@@ -332,6 +334,109 @@ cudaError_t launch_attn(cudaStream_t st, const act_t* qkv, const float* mask, ac
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Side row only (last block of the objects tower: the main-stream output is dead, objects.py:249-258).
+// One warp per (crop, head): a single query row against 196 patch keys + itself is two GEMVs, bound
+// by the one pass over K and V (50 KB per warp) -- no tile machinery.
+//   scores: lane = key (7 keys per lane), q in registers, each K row read as 8 x 16 B
+//   softmax over the 197 scores with warp reductions, bias -100 * mask on the patches
+//   output: lane = two of the 64 dims, p_j broadcast by shuffle, each V row read as one 128 B line
+// ------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256) attention_side_row_kernel(const act_t* __restrict__ qkv,
+                                                                 const float* __restrict__ mask,
+                                                                 act_t* __restrict__ out, int B, int heads) {
+  constexpr int NKEY = P + 1;                 // patches + the side token itself
+  constexpr int KPL = (NKEY + 31) / 32;       // keys per lane
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * heads) return;
+  const int b = warp / heads, h = warp - b * heads;
+  const int W = heads * kDh;
+  const size_t ld = 3 * static_cast<size_t>(W);
+  const size_t y_row = static_cast<size_t>(B) * P + B + b;
+  auto key_row = [&](int j) -> size_t { return j < P ? static_cast<size_t>(b) * P + j : y_row; };
+
+  float q[kDh];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(qkv + y_row * ld + h * kDh);
+#pragma unroll
+    for (int c = 0; c < kDh / 8; ++c) {
+      const uint4 u = __ldg(qp + c);
+      const float2 a = unpack2(u.x), b2 = unpack2(u.y), c2 = unpack2(u.z), d = unpack2(u.w);
+      q[8 * c + 0] = a.x; q[8 * c + 1] = a.y; q[8 * c + 2] = b2.x; q[8 * c + 3] = b2.y;
+      q[8 * c + 4] = c2.x; q[8 * c + 5] = c2.y; q[8 * c + 6] = d.x; q[8 * c + 7] = d.y;
+    }
+  }
+  float sc[KPL];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int j = lane + 32 * i;
+    sc[i] = -INFINITY;
+    if (j < NKEY) {
+      const uint4* kp = reinterpret_cast<const uint4*>(qkv + key_row(j) * ld + W + h * kDh);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < kDh / 8; ++c) {
+        const uint4 u = __ldg(kp + c);
+        const float2 a = unpack2(u.x), b2 = unpack2(u.y), c2 = unpack2(u.z), d = unpack2(u.w);
+        acc = fmaf(q[8 * c + 0], a.x, acc); acc = fmaf(q[8 * c + 1], a.y, acc);
+        acc = fmaf(q[8 * c + 2], b2.x, acc); acc = fmaf(q[8 * c + 3], b2.y, acc);
+        acc = fmaf(q[8 * c + 4], c2.x, acc); acc = fmaf(q[8 * c + 5], c2.y, acc);
+        acc = fmaf(q[8 * c + 6], d.x, acc); acc = fmaf(q[8 * c + 7], d.y, acc);
+      }
+      const float bias = j < P ? -100.0f * kLog2e * __ldg(mask + static_cast<size_t>(b) * P + j) : 0.f;
+      sc[i] = fmaf(acc, 0.125f * kLog2e, bias);
+    }
+    mx = fmaxf(mx, sc[i]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    sc[i] = exp2f(sc[i] - mx);  // -inf (no such key) -> 0
+    sum += sc[i];
+  }
+  sum = warp_sum(sum);
+  // V: 16 independent row loads in flight per step (keys past the end re-read the last row with
+  // weight 0), then the 16 weights are broadcast and accumulated
+  float o0 = 0.f, o1 = 0.f;
+  const uint32_t* vbase = reinterpret_cast<const uint32_t*>(qkv + 2 * W + h * kDh) + lane;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+#pragma unroll
+    for (int l0 = 0; l0 < 32; l0 += 16) {
+      if (32 * i + l0 >= NKEY) break;  // compile-time after unrolling
+      uint32_t u[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int j = min(32 * i + l0 + e, NKEY - 1);
+        u[e] = __ldg(vbase + key_row(j) * (ld / 2));
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float pj = __shfl_sync(0xffffffffu, sc[i], l0 + e);  // 0 for keys past the end
+        const float2 v = unpack2(u[e]);
+        o0 = fmaf(pj, v.x, o0);
+        o1 = fmaf(pj, v.y, o1);
+      }
+    }
+  }
+  const float inv = 1.0f / sum;
+  reinterpret_cast<uint32_t*>(out + y_row * W + h * kDh)[lane] = pack2(o0 * inv, o1 * inv);
+}
+
+// OAKE_ATTN=mma keeps the tile kernel for the side-row-only launch too (A/B runs, tests).
+bool attention_side_row_fast() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OAKE_ATTN");
+    v = (e != nullptr && e[0] == 'm') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace
 
 cudaError_t launch_attention(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
@@ -340,6 +445,11 @@ cudaError_t launch_attention(cudaStream_t st, const act_t* qkv, const float* mas
   if (attention_use_tc(P, side_only)) return launch_attention_tc(st, qkv, mask, out, B, P, heads, with_side, side_only);
   if (with_side) {
     if (P != 196 || mask == nullptr) return cudaErrorInvalidValue;
+    if (side_only && attention_side_row_fast()) {
+      const int warps = B * heads;
+      attention_side_row_kernel<196><<<(warps + 7) / 8, 256, 0, st>>>(qkv, mask, out, B, heads);
+      return cudaGetLastError();
+    }
     return launch_attn<196, true>(st, qkv, mask, out, B, heads, side_only);
   }
   if (side_only) return cudaErrorInvalidValue;

@@ -230,15 +230,18 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
     if (r < th) pil_bounds(ax_v, job.box_h, oy0 + r, &sm.v_first[r], &sm.v_count[r]);
   }
   __syncthreads();
-  for (int idx = tid; idx < 2 * kTile * kMaxTaps; idx += blockDim.x) {  // one filter tap per thread
-    const int sidx = idx / kMaxTaps, x = idx - sidx * kMaxTaps;
-    if (sidx < kTile) {
-      if (sidx < tw && x < sm.h_count[sidx]) sm.w[sidx][x] = pil_weight(ax_h, ox0 + sidx, sm.h_first[sidx], x);
-    } else {
-      const int r = sidx - kTile;
-      if (r < th && x < sm.v_count[r]) sm.w[sidx][x] = pil_weight(ax_v, oy0 + r, sm.v_first[r], x);
-    }
-  }
+  // One filter tap per thread: thread = (sample sidx = tid % 64, tap x = tid / 64, + 4, + 8, ...), so a
+  // warp holds 32 samples at the same tap and the loop stops at the widest tap window of the tile
+  // (typically 5..9 of the 48 slots).
+  const int sidx = tid & (2 * kTile - 1);
+  const bool s_h = sidx < kTile;
+  const int s_r = sidx - kTile;
+  const bool s_live = s_h ? sidx < tw : s_r < th;
+  const int s_count = !s_live ? 0 : (s_h ? sm.h_count[sidx] : sm.v_count[s_r]);
+  const int s_first = !s_live ? 0 : (s_h ? sm.h_first[sidx] : sm.v_first[s_r]);
+  const int max_count = __reduce_max_sync(0xffffffffu, s_count);  // widest window among this warp's 32 samples
+  for (int x = tid / (2 * kTile); x < max_count; x += blockDim.x / (2 * kTile))
+    if (x < s_count) sm.w[sidx][x] = pil_weight(s_h ? ax_h : ax_v, s_h ? ox0 + sidx : oy0 + s_r, s_first, x);
   __syncthreads();
   if (tid < kTile) {
     if (tid < tw) sm.ww[tid] = pil_weight_sum(sm.w[tid], sm.h_count[tid]);
@@ -247,15 +250,8 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
     if (r < th) sm.ww[tid] = pil_weight_sum(sm.w[tid], sm.v_count[r]);
   }
   __syncthreads();
-  for (int idx = tid; idx < 2 * kTile * kMaxTaps; idx += blockDim.x) {
-    const int sidx = idx / kMaxTaps, x = idx - sidx * kMaxTaps;
-    if (sidx < kTile) {
-      if (sidx < tw && x < sm.h_count[sidx]) sm.kh[sidx][x] = pil_fixed(sm.w[sidx][x], sm.ww[sidx]);
-    } else {
-      const int r = sidx - kTile;
-      if (r < th && x < sm.v_count[r]) sm.kv[r][x] = pil_fixed(sm.w[sidx][x], sm.ww[sidx]);
-    }
-  }
+  for (int x = tid / (2 * kTile); x < max_count; x += blockDim.x / (2 * kTile))
+    if (x < s_count) (s_h ? sm.kh[sidx] : sm.kv[s_r])[x] = pil_fixed(sm.w[sidx][x], sm.ww[sidx]);
   __syncthreads();
   if (tid == 0) {
     int lo = sm.v_first[0], hi = 0;
@@ -272,9 +268,8 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
   // horizontal pass: crop rows [r_lo, r_lo + nr) -> tmp (uint8, like Pillow's intermediate image).
   // One thread per (row, output column): the three channels share the tap loop, and the taps that
   // fall outside the source image (zero padding of PIL `crop`) are cut off once, outside the loop.
-  for (int idx = tid; idx < nr * tw; idx += blockDim.x) {
-    const int r = idx / tw;
-    const int j = idx - r * tw;
+  const int j = tid & (kTile - 1);  // output column of the tile; rows go tid / 32, + 8, + 16, ...
+  for (int r = tid / kTile; r < nr && j < tw; r += blockDim.x / kTile) {
     const int y = job.box_y0 + r_lo + r;
     int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
     if (y >= 0 && y < job.src_h) {
@@ -300,9 +295,7 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
 
   // vertical pass
   uint8_t* dst = dst_arena + job.dst_off;
-  for (int idx = tid; idx < th * tw; idx += blockDim.x) {
-    const int r = idx / tw;
-    const int j = idx - r * tw;
+  for (int r = tid / kTile; r < th && j < tw; r += blockDim.x / kTile) {
     const int first = sm.v_first[r] - r_lo;
     const int t1 = min(sm.v_count[r], nr - first);
     const int* k = sm.kv[r];
