@@ -1,0 +1,532 @@
+// Persistent tcgen05 attention for the 197-token OAKE tower, column-split form (default).
+//
+// Same contract, data layout and MMA formulation as attention_tc.cu (S = Q K^T into TMEM, packed
+// fp16 P written over consumed S columns, O = P V with P as the TMEM operand and V MN-major), but a
+// different division of labour, chosen from the ncu stall samples of that kernel: there each
+// 128-row tile belonged to ONE group of four softmax warps, so per group the chain
+// softmax -> PV -> O drain -> next S was serial and the MUFU pipe sat idle through its gaps
+// (profiles/r1_11_attention_stalls.txt).  Here
+//
+//   warps 0-7    softmax: ALL eight work on the current tile -- warp w owns TMEM lanes 32 (w % 4)..
+//                and one half of the keys (w < 4: keys 0..95, w >= 4: keys 96..207); the two warps of
+//                a lane quarter exchange their partial row maxima through shared memory (one named
+//                barrier per pair) and leave partial row sums for the drain warps.  They alternate
+//                between the two TMEM tiles and never wait for a PV product.
+//   warps 8-11   drain: one per lane quarter; O -> registers (the tile's TMEM is released at once),
+//                1 / sum, swizzled smem strip, whole 128-byte rows to global memory.
+//   warp  12     loader (TMA boxes + cp.async rows, two-stage ring, non-blocking)
+//   warp  13     MMA issue (one thread), order PV(n,0) S(n+1,0) PV(n,1) S(n+1,1)
+//
+// so that PV(n,t), its drain and S(n+1,t) run underneath the softmax of the other tile.
+//
+// TMEM columns of a tile (256 per tile, 512 per CTA):
+//   S   [0, 208)  fp32 scores, keys in order (196 patches, class, side, 10 x padding)
+//   P   [0, 48)   packed fp16, keys 0..95    (lower half, written in place behind its reads)
+//       [96, 152) packed fp16, keys 96..207  (upper half, likewise)
+//   O   [152, 216) fp32 accumulator (dead S columns of the upper half)
+#include <stdlib.h>
+
+#include "attn_tc_common.cuh"
+
+namespace oake {
+
+namespace {
+
+using namespace attn;
+
+template <bool SIDE>
+struct CCfg {
+  static constexpr int P = 196;
+  static constexpr int T = P + 1;
+  static constexpr int TQ = T + (SIDE ? 1 : 0);
+  static constexpr int NK = 208;                 // keys, padded to the MMA K granule (16)
+  static constexpr int kUnits = NK / 16;         // 13
+  static constexpr int kSplit = 96;              // first key of the upper half
+  static constexpr int kRows1 = TQ - 128;        // live rows of tile 1: 68 patches + class (+ side)
+  static constexpr int kPatch1 = P - 128;        // patch rows of tile 1 (one TMA box)
+  static constexpr int kShift = 56;              // lane offset of tile 1's rows on odd items
+  static constexpr int kQTile = 128 * 128;       // bytes: 128 rows x 64 halves
+  static constexpr int kKV = NK * 128;           // bytes
+  static constexpr int kStage = 2 * kQTile + 2 * kKV;
+  static constexpr int kPHi = kSplit;            // P columns of the upper half start here
+  static constexpr int kOCol = kSplit + (NK - kSplit) / 2;  // 152
+  static constexpr int kBufCols = 256;           // TMEM columns per tile
+  static constexpr int kMaskFloats = 208;        // staged mask row (196 used), 16-byte granules
+  static constexpr int kMaskBytes = 2048;        // both stages' mask rows, padded
+  static constexpr int kXchgBytes = 2 * 2 * 2 * 128 * 4;  // partial max + sum: [2][tile][half][row]
+  static constexpr int kOutStage = 32 * 128;     // bytes per drain warp: 32 rows x 64 halves
+  static constexpr int kNumBars = 16;
+  static constexpr int kSmemBytes = 1024 + 2 * kStage + kMaskBytes + kXchgBytes + 4 * kOutStage + kNumBars * 8 + 16;
+  static constexpr int kSoftmaxWarps = 8;
+  static constexpr int kDrainWarp0 = 8;
+  static constexpr int kLoaderWarp = 12;
+  static constexpr int kMmaWarp = 13;
+  static constexpr int kThreads = 32 * 14;
+};
+
+enum BiasMode { kPlain = 0, kBits = 1, kLoad = 2 };  // see attention_tc.cu
+
+__device__ __forceinline__ void pair_sync(int q) {  // the two softmax warps of lane quarter q
+  asm volatile("bar.sync %0, 64;\n" ::"r"(q + 1) : "memory");
+}
+
+// One half (HI = 0: keys 0..95, HI = 1: keys 96..207) of one query row.  Same arithmetic per element
+// as attention_tc.cu::softmax_row (bit-identical results for a row whichever warp pair it lands in).
+template <bool SIDE, int MODE, int HI>
+struct HalfRow {
+  using C = CCfg<SIDE>;
+  static constexpr float scale = 0.125f * kLog2e;
+  static constexpr float kNegB = -100.0f * kLog2e;
+  static constexpr int k0 = HI ? C::kSplit : 0;   // first key
+  static constexpr int kTail = 192;               // keys 192..207: patches 192..195, class, side, padding
+
+  uint32_t t_row;
+  bool is_y;
+  uint32_t ymask_addr, ybits;
+
+  __device__ __forceinline__ float patch_bias(int col, int j, uint32_t w) const {
+    if (MODE == kBits) return (w >> j) & 1u ? kNegB : 0.f;
+    return is_y ? kNegB * lds_f32(ymask_addr + col * 4) : 0.f;
+  }
+  __device__ __forceinline__ uint32_t group_bits(int g) const {  // lane g < 7 holds keys 32g..32g+31
+    if (MODE != kBits) return 0u;
+    const uint32_t w = __shfl_sync(0xffffffffu, ybits, g);
+    return is_y ? w : 0u;
+  }
+  __device__ __forceinline__ float tail_bias(int j, uint32_t w) const {
+    const int col = kTail + j;
+    if (col < C::P) return MODE == kPlain ? 0.f : patch_bias(col, j, w);
+    const float main_b = col < C::T ? 0.f : -INFINITY;  // class key valid, side key / padding not
+    if (MODE == kPlain) return main_b;
+    const float y_b = col == C::T ? 0.f : -INFINITY;     // the side token sees itself, not the class key
+    return is_y ? y_b : main_b;
+  }
+
+  // partial row maximum in the base-2 domain (scaled, biased)
+  __device__ __forceinline__ float pass_max() const {
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      uint32_t ra[32];
+      tmem_ld_32x32(t_row + k0 + c * 32, ra);
+      const uint32_t wa = group_bits(k0 / 32 + c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (MODE == kPlain) {
+          m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(ra[j]));
+        } else {
+          m4[j & 3] = fmaxf(m4[j & 3], fmaf(__uint_as_float(ra[j]), scale, patch_bias(k0 + c * 32 + j, j, wa)));
+        }
+      }
+    }
+    float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    if (MODE == kPlain) mx *= scale;  // the scale is positive: max(s) * scale == max(s * scale)
+    if (HI) {
+      uint32_t rt[16];
+      tmem_ld_32x16(t_row + kTail, rt);
+      const uint32_t wt = group_bits(6);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (kTail + j <= C::T) mx = fmaxf(mx, fmaf(__uint_as_float(rt[j]), scale, tail_bias(j, wt)));
+    }
+    return mx;
+  }
+
+  // p = exp2(s - max) -> packed fp16 behind the reads; partial row sum of the unrounded values
+  __device__ __forceinline__ float pass_exp(float neg_mx) const {
+    constexpr int pbase = HI ? C::kPHi : 0;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      uint32_t ra[32];
+      tmem_ld_32x32(t_row + k0 + c * 32, ra);
+      const uint32_t wa = group_bits(k0 / 32 + c);
+      tmem_ld_wait();
+      uint32_t pa[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float p[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jj = 2 * j + e;
+          if (MODE == kPlain) {
+            p[e] = ex2(fmaf(__uint_as_float(ra[jj]), scale, neg_mx));
+          } else {  // bias added after the fma: same bits as kPlain for a main-stream row (bias 0)
+            p[e] = ex2(fmaf(__uint_as_float(ra[jj]), scale, neg_mx) + patch_bias(k0 + c * 32 + jj, jj, wa));
+          }
+        }
+        s4[j & 3] += p[0] + p[1];
+        pa[j] = pack2(p[0], p[1]);
+      }
+      tmem_st_32x16(t_row + pbase + c * 16, pa);
+    }
+    if (HI) {
+      uint32_t rt[16];
+      tmem_ld_32x16(t_row + kTail, rt);
+      const uint32_t wt = group_bits(6);
+      tmem_ld_wait();
+      uint32_t pt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jj = 2 * j + e;
+          p[e] = kTail + jj <= C::T ? ex2(fmaf(__uint_as_float(rt[jj]), scale, neg_mx) + tail_bias(jj, wt)) : 0.f;
+        }
+        s4[j & 3] += p[0] + p[1];
+        pt[j] = pack2(p[0], p[1]);
+      }
+      tmem_st_32x8(t_row + pbase + 48, pt);
+    }
+    return (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  }
+};
+
+// pass_max -> exchange with the other half's warp -> pass_exp; leaves the partial sum in `xsum`.
+template <bool SIDE, int MODE, int HI>
+__device__ __forceinline__ void softmax_half(uint32_t t_row, bool is_y, uint32_t ymask_addr, uint32_t ybits, int q,
+                                             float* xmax_mine, const float* xmax_other, float* xsum_mine) {
+  HalfRow<SIDE, MODE, HI> h{t_row, is_y, ymask_addr, ybits};
+  const float mine = h.pass_max();
+  *xmax_mine = mine;
+  pair_sync(q);
+  const float mx = fmaxf(mine, *xmax_other);
+  *xsum_mine = h.pass_exp(-mx);
+}
+
+template <bool SIDE>
+__global__ void __launch_bounds__(CCfg<SIDE>::kThreads, 1)
+attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], box {64, 128}
+                    const __grid_constant__ CUtensorMap tmQ1,  // qkv [R, 3W], box {64, 68}
+                    const __grid_constant__ CUtensorMap tmKV,  // qkv [R, 3W], box {64, 196}
+                    const act_t* __restrict__ qkv, const float* __restrict__ mask, act_t* __restrict__ out,
+                    int B, int heads) {
+  using C = CCfg<SIDE>;
+  constexpr int P = C::P;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* ymask = reinterpret_cast<float*>(smem + 2 * C::kStage);  // [2][kMaskFloats]: mask row of the item's crop
+  float* xmax = reinterpret_cast<float*>(smem + 2 * C::kStage + C::kMaskBytes);  // [tile][half][128]
+  float* xsum = xmax + 2 * 2 * 128;                                               // [tile][half][128]
+  uint8_t* out_stage = smem + 2 * C::kStage + C::kMaskBytes + C::kXchgBytes;      // [4 drain warps][kOutStage]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + 4 * C::kOutStage);
+  uint64_t* qk_full = bars + 0;   // [stage]  loader -> MMA
+  uint64_t* qk_free = bars + 2;   // [stage]  MMA (S of both tiles retired) -> loader
+  uint64_t* v_full = bars + 4;    // [stage]  loader -> MMA, side-row warps (mask row)
+  uint64_t* v_free = bars + 6;    // [stage]  MMA (PV of both tiles retired) -> loader
+  uint64_t* s_full = bars + 8;    // [tile]   MMA -> softmax + drain warps
+  uint64_t* p_ready = bars + 10;  // [tile]   8 softmax warps -> MMA, drain warps (row sums)
+  uint64_t* o_full = bars + 12;   // [tile]   MMA -> drain warps
+  uint64_t* o_free = bars + 14;   // [tile]   4 drain warps (O in registers) -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int W = heads * kDh;
+  const int ld = 3 * W;
+  const int items = B * heads;
+  const int N = (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp == C::kLoaderWarp && lane == 0) {
+    tma_prefetch_desc(&tmQ0);
+    tma_prefetch_desc(&tmQ1);
+    tma_prefetch_desc(&tmKV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 33);  // expect_tx arrival + one cp.async arrival per loader lane
+      mbar_init(&qk_free[i], 1);
+      mbar_init(&v_full[i], 33);
+      mbar_init(&v_free[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], C::kSoftmaxWarps);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == C::kLoaderWarp) {
+    // ================================================================== loader
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1, u = n >> 1;
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / heads, h = item - b * heads;
+      uint8_t* stg = smem + s * C::kStage;
+      uint8_t* sQ0 = stg;
+      uint8_t* sQ1 = stg + C::kQTile;
+      uint8_t* sK = stg + 2 * C::kQTile;
+      uint8_t* sV = sK + C::kKV;
+      const int shift = s ? C::kShift : 0;
+
+      mbar_wait(&qk_free[s], (u & 1) ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&qk_full[s], C::kQTile + C::kPatch1 * 128 + P * 128);
+        tma_load_2d(sQ0, &tmQ0, &qk_full[s], h * kDh, b * P);
+        tma_load_2d(sQ1 + shift * 128, &tmQ1, &qk_full[s], h * kDh, b * P + 128);
+        tma_load_2d(sK, &tmKV, &qk_full[s], W + h * kDh, b * P);
+      }
+      __syncwarp();
+      // K rows of the class / side token and the zero padding up to NK
+      for (int idx = lane; idx < (C::NK - P) * 8; idx += 32) {
+        const int i = P + (idx >> 3), c = idx & 7;
+        const bool ok = i < C::TQ;
+        const act_t* src = qkv + static_cast<size_t>(token_row(ok ? i : P, b, B, P)) * ld + W + h * kDh + c * 8;
+        cp_async16_zfill(sw128(sK, i, c), src, ok);
+      }
+      // Q rows of the class / side token: tile-1 rows shift + 68 (, + 69)
+      for (int idx = lane; idx < (C::TQ - P) * 8; idx += 32) {
+        const int i = P + (idx >> 3), c = idx & 7;
+        const act_t* src = qkv + static_cast<size_t>(token_row(i, b, B, P)) * ld + h * kDh + c * 8;
+        cp_async16_zfill(sw128(sQ1, shift + i - 128, c), src, true);
+      }
+      cp_async_arrive_noinc(&qk_full[s]);  // every lane, with or without copies of its own
+
+      mbar_wait(&v_free[s], (u & 1) ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&v_full[s], P * 128);
+        tma_load_2d(sV, &tmKV, &v_full[s], 2 * W + h * kDh, b * P);
+      }
+      __syncwarp();
+      for (int idx = lane; idx < (C::NK - P) * 8; idx += 32) {
+        const int i = P + (idx >> 3), c = idx & 7;
+        const bool ok = i < C::TQ;
+        const act_t* src = qkv + static_cast<size_t>(token_row(ok ? i : P, b, B, P)) * ld + 2 * W + h * kDh + c * 8;
+        cp_async16_zfill(sw128(sV, i, c), src, ok);
+      }
+      if (SIDE) {  // the crop's mask row (196 floats = 49 granules) for the side-row warps
+        const float* mrow = mask + static_cast<size_t>(b) * P;
+        for (int g = lane; g < P / 4; g += 32) cp_async16_zfill(ymask + s * C::kMaskFloats + g * 4, mrow + g * 4, true);
+      }
+      cp_async_arrive_noinc(&v_full[s]);
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");  // nothing of this warp in flight at exit
+  } else if (warp == C::kMmaWarp) {
+    // ================================================================== MMA issue
+    constexpr uint32_t idesc_s = make_idesc_f16(128, C::NK);
+    constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, kDh);
+    const uint32_t smem_base = smem_u32(smem);
+    auto issue_s = [&](int n, int t) {  // lane 0 only
+      const uint32_t stg = smem_base + (n & 1) * C::kStage;
+      const uint32_t q_addr = stg + t * C::kQTile, k_addr = stg + 2 * C::kQTile;
+#pragma unroll
+      for (int k = 0; k < kDh / 16; ++k)
+        umma_f16(tmem_base + t * C::kBufCols, make_smem_desc_k_sw128(q_addr + k * 32),
+                 make_smem_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&s_full[t]);
+    };
+    auto issue_pv = [&](int n, int t) {  // lane 0 only
+      const uint32_t v_addr = smem_base + (n & 1) * C::kStage + 2 * C::kQTile + C::kKV;
+      const uint32_t buf = tmem_base + t * C::kBufCols;
+#pragma unroll
+      for (int k = 0; k < C::kUnits; ++k) {
+        const uint32_t p_col = k * 16 < C::kSplit ? k * 8 : C::kPHi + (k - C::kSplit / 16) * 8;
+        umma_f16_ts(buf + C::kOCol, buf + p_col, make_smem_desc_mn_sw128(v_addr + k * 2048), idesc_o, k != 0 ? 1u : 0u);
+      }
+      umma_commit(&o_full[t]);
+    };
+    if (N > 0) {
+      mbar_wait(&qk_full[0], 0);
+      fence_proxy_async();  // the loader's cp.async rows (generic proxy) -> tensor core reads
+      tc_fence_after();
+      if (lane == 0) {
+        issue_s(0, 0);
+        issue_s(0, 1);
+        umma_commit(&qk_free[0]);
+      }
+      __syncwarp();
+    }
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1, u = n >> 1;
+      mbar_wait(&v_full[s], u & 1);
+      fence_proxy_async();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_ready[t], n & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_pv(n, t);
+          if (t == 1) umma_commit(&v_free[s]);
+        }
+        __syncwarp();
+        if (n + 1 < N) {
+          if (t == 0) {
+            mbar_wait(&qk_full[s ^ 1], ((n + 1) >> 1) & 1);
+            fence_proxy_async();
+          }
+          mbar_wait(&o_free[t], n & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_s(n + 1, t);
+            if (t == 1) umma_commit(&qk_free[s ^ 1]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================================================================== softmax and drain warps
+    const bool drain = warp >= C::kDrainWarp0;
+    const int q = warp & 3;                    // TMEM lane quarter (== warp % 4 for both roles)
+    const int hi = drain ? 0 : (warp >> 2);    // softmax: which half of the keys
+    const int r = q * 32 + lane;               // lane of the tile
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1, u = n >> 1;
+      const int item = blockIdx.x + n * gridDim.x;
+      const int b = item / heads, h = item - b * heads;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int shift1 = (t == 1 && s) ? C::kShift : 0;
+        const int rr = r - shift1;
+        const bool live = t == 0 || (rr >= 0 && rr < C::kRows1);
+        const int i = t * 128 + rr;  // token index
+        const bool is_y = SIDE && live && i == C::T;
+        const bool warp_live = __any_sync(0xffffffffu, live);
+        const bool warp_y = SIDE && __any_sync(0xffffffffu, is_y);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * C::kBufCols;
+        float* xm = xmax + (t * 2) * 128 + r;  // + 128 for the upper half
+        float* xs = xsum + (t * 2) * 128 + r;
+
+        // every warp passes through s_full: it keeps warps without live rows in step with the tile
+        mbar_wait(&s_full[t], n & 1);
+        tc_fence_after();
+
+        if (!drain) {
+          if (warp_live) {
+            uint32_t ymask_addr = 0u, ybits = 0u;
+            int mode = kPlain;
+            if (warp_y) {
+              mbar_wait(&v_full[s], u & 1);  // the crop's mask row lands with the V stage
+              ymask_addr = smem_u32(ymask + s * C::kMaskFloats);
+              uint32_t other = 0u;  // lane g keeps the bits of keys 32g .. 32g+31
+#pragma unroll
+              for (int g = 0; g < 7; ++g) {
+                const int col = g * 32 + lane;
+                const float m = col < P ? lds_f32(ymask_addr + col * 4) : 0.f;
+                const uint32_t w = __ballot_sync(0xffffffffu, m != 0.f);
+                other |= __ballot_sync(0xffffffffu, m != 0.f && m != 1.f);
+                if (lane == g) ybits = w;
+              }
+              mode = other == 0u ? kBits : kLoad;
+            }
+            if (hi == 0) {
+              if (mode == kPlain) softmax_half<SIDE, kPlain, 0>(t_row, false, 0u, 0u, q, xm, xm + 128, xs);
+              else if (mode == kBits) softmax_half<SIDE, kBits, 0>(t_row, is_y, ymask_addr, ybits, q, xm, xm + 128, xs);
+              else softmax_half<SIDE, kLoad, 0>(t_row, is_y, ymask_addr, 0u, q, xm, xm + 128, xs);
+            } else {
+              if (mode == kPlain) softmax_half<SIDE, kPlain, 1>(t_row, false, 0u, 0u, q, xm + 128, xm, xs + 128);
+              else if (mode == kBits) softmax_half<SIDE, kBits, 1>(t_row, is_y, ymask_addr, ybits, q, xm + 128, xm, xs + 128);
+              else softmax_half<SIDE, kLoad, 1>(t_row, is_y, ymask_addr, 0u, q, xm + 128, xm, xs + 128);
+            }
+            tmem_st_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[t]);
+        } else {
+          if (warp_live) {
+            mbar_wait(&p_ready[t], n & 1);  // all eight softmax warps done: the row sums are in place
+            const float sum = xs[0] + xs[128];
+            mbar_wait(&o_full[t], n & 1);
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(t_row + C::kOCol, o0);
+            tmem_ld_32x32(t_row + C::kOCol + 32, o1);
+            tmem_ld_wait();
+            // the accumulator is in registers: the tile's TMEM goes back to the tensor core before
+            // the scaling and the global stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[t]);
+            const uint32_t stg = smem_u32(out_stage + (warp - C::kDrainWarp0) * C::kOutStage);
+            {
+              const float inv = 1.0f / sum;
+              auto o_at = [&](int c) -> float { return c < 32 ? __uint_as_float(o0[c & 31]) : __uint_as_float(o1[c & 31]); };
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint4 v;
+                v.x = pack2(o_at(8 * j + 0) * inv, o_at(8 * j + 1) * inv);
+                v.y = pack2(o_at(8 * j + 2) * inv, o_at(8 * j + 3) * inv);
+                v.z = pack2(o_at(8 * j + 4) * inv, o_at(8 * j + 5) * inv);
+                v.w = pack2(o_at(8 * j + 6) * inv, o_at(8 * j + 7) * inv);
+                sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), v);
+              }
+            }
+            __syncwarp();
+            {
+              const int chunk = lane & 7;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int row = 4 * k + (lane >> 3);          // row of this warp's 32
+                const int rr2 = q * 32 + row - shift1;        // row of the tile's live range
+                const bool live2 = t == 0 || (rr2 >= 0 && rr2 < C::kRows1);
+                if (live2) {
+                  const uint4 v = lds128(stg + row * 128 + ((chunk ^ (row & 7)) << 4));
+                  const int tok = t * 128 + rr2;
+                  *reinterpret_cast<uint4*>(out + static_cast<size_t>(token_row(tok, b, B, P)) * W + h * kDh + chunk * 8) = v;
+                }
+              }
+            }
+            __syncwarp();
+          } else {
+            if (lane == 0) mbar_arrive(&o_free[t]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <bool SIDE>
+cudaError_t launch_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int heads, int rows) {
+  using C = CCfg<SIDE>;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_cs_kernel<SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap tmQ0, tmQ1, tmKV;
+  const uint64_t cols = 3ull * heads * kDh;
+  if (make_tmap_act_2d(&tmQ0, qkv, rows, cols, 128) || make_tmap_act_2d(&tmQ1, qkv, rows, cols, C::kPatch1) ||
+      make_tmap_act_2d(&tmKV, qkv, rows, cols, C::P))
+    return cudaErrorInvalidValue;
+  const int items = B * heads;
+  const int grid = items < num_sms ? items : num_sms;
+  attention_cs_kernel<SIDE><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ0, tmQ1, tmKV, qkv, mask, out, B, heads);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_attention_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
+                                int heads, int with_side, int side_only) {
+  if (B <= 0) return cudaSuccess;
+  if (P != 196 || side_only) return cudaErrorInvalidValue;
+  const int rows = B * (P + 1) + (with_side ? B : 0);
+  if (with_side) {
+    if (mask == nullptr) return cudaErrorInvalidValue;
+    return launch_cs<true>(st, qkv, mask, out, B, heads, rows);
+  }
+  return launch_cs<false>(st, qkv, nullptr, out, B, heads, rows);
+}
+
+}  // namespace oake

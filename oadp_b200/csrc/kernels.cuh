@@ -71,6 +71,10 @@ cudaError_t launch_attention(cudaStream_t st, const act_t* qkv, const float* mas
 bool attention_use_tc(int P, int side_only);
 cudaError_t launch_attention_tc(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
                                 int heads, int with_side, int side_only);
+// attention_cs.cu: the column-split form of the persistent kernel (all eight softmax warps on one
+// tile, dedicated drain warps); default.  OAKE_ATTN=pp selects the row-owner form of attention_tc.cu.
+cudaError_t launch_attention_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
+                                int heads, int with_side, int side_only);
 
 // ------------------------------------------------------------ frontend.cu
 // pixels fp32 NCHW [B,3,224,224] (already CLIP-normalised) -> act [B*P, 3*32*32] conv1 patches,
