@@ -140,3 +140,30 @@ def test_crop_outside_the_image_and_scale_limit(pipe):
     jobs['box_w'], jobs['box_h'] = 2900, 2900  # ... and, if a caller skips that check, flagged by the kernel
     with pytest.raises(binding.OakeError):
         pipe.debug_crops_u8([big], jobs)
+
+
+def test_full_size_step_properties(lib):
+    """BASELINE-size step (8 COCO-shaped images, 300 proposals each, full 12-layer tower) checked
+    through size-independent properties: unit-norm fp16 rows, bit-identical results when the same
+    images are encoded in different batch compositions and on a second run, and an object crop
+    that equals the whole image giving the same pixels as the global crop path."""
+    pipe = OakePipeline(OakeEngine(synth.visual_params(0), 'cuda'))
+    sizes = [(640, 480), (640, 427), (480, 640), (427, 640), (500, 375), (640, 640), (612, 612), (640, 426)]
+    imgs = [synth.image(w, h, 100 + k) for k, (w, h) in enumerate(sizes)]
+    props = [synth.proposals(w, h, 300, seed=200 + k) for k, (w, h) in enumerate(sizes)]
+    full = pipe.encode_objects(imgs, props)
+    n = sum(o['embeddings'].shape[0] for o in full)
+    assert 2300 < n <= 2400  # ~2 % of the proposals are degenerate (SURVEY 8d-3)
+    for o in full:
+        e = o['embeddings'].float()
+        assert torch.isfinite(e).all() and ((e.norm(dim=-1) - 1).abs() < 2e-3).all()
+    halves = pipe.encode_objects(imgs[:3], props[:3]) + pipe.encode_objects(imgs[3:], props[3:])
+    again = pipe.encode_objects(list(reversed(imgs)), list(reversed(props)))[::-1]
+    for a, b, c in zip(full, halves, again):
+        assert torch.equal(a['embeddings'], b['embeddings']) and torch.equal(a['embeddings'], c['embeddings'])
+        assert torch.equal(a['bboxes'], b['bboxes']) and torch.equal(a['objectness'], c['objectness'])
+    blocks = pipe.encode_blocks(imgs)
+    assert [b['embeddings'].shape[0] for b in blocks] == [27, 22, 27, 22, 17, 39, 39, 22]  # SURVEY 8a / 8d-2
+    g = pipe.encode_globals(imgs)
+    for gi, bi in zip(g, blocks):
+        assert torch.equal(gi, bi['embeddings'][0])  # block 0 is the global crop (blocks.py:95)
