@@ -176,6 +176,25 @@ int oake_cosine_logits_bwd(const float* h, const float* text, const float* bg, c
 int oake_vild_ensemble(const float* bbox_logits, const float* object_logits, const float* lambda, int N, int K1,
                        int ld_bbox, int ld_object, float* out, int ld_out, void* stream);
 
+/* ---- distillation-side losses: value and gradient w.r.t. the first argument in one call -
+ * All fp32 device pointers.  `scale` = weight / numel for reduction='mean', weight for 'sum' (todd
+ * BaseLoss.reduce; the configs' WarmupScheduler is a scalar at a given step).  loss: 1 float.  grad:
+ * same shape as the first argument or NULL.  ws: oake_loss_workspace_bytes(rkd_rows) bytes (rkd_rows = 0
+ * unless oake_rkd_loss is called).  Sums are fixed-order: results are deterministic.
+ *   oake_pair_loss       kind 0: todd L1Loss, kind 1: todd MSELoss on (pred, target)
+ *                        (configs/dp/models/{vild_ensemble_faster_rcnn_r50_fpn,block,global_}.py)
+ *   oake_rkd_loss        RKDLoss, oadp/base/losses.py:68-108: MSE of s s^T - t t^T, rows (N, dim);
+ *                        scale = weight / N^2 for 'mean'
+ *   oake_asymmetric_loss AsymmetricLoss, oadp/base/losses.py:10-65: x probabilities, y uint8 0/1 */
+int oake_loss_workspace_bytes(int rkd_rows, size_t* out_bytes);
+int oake_pair_loss(const float* pred, const float* target, long long n, int kind, float scale, float* loss,
+                   float* grad, void* ws, size_t ws_bytes, void* stream);
+int oake_rkd_loss(const float* s, const float* t, int N, int dim, float scale, float* loss, float* grad_s, void* ws,
+                  size_t ws_bytes, void* stream);
+int oake_asymmetric_loss(const float* x, const uint8_t* y, long long n, float gamma_neg, float gamma_pos,
+                         float clip, float eps, float scale, float* loss, float* grad, void* ws, size_t ws_bytes,
+                         void* stream);
+
 /* Error string of the last failing call on this thread ("" if none). */
 const char* oake_last_error(void);
 /* "f16" or "bf16": element type of `act` tensors. */

@@ -54,6 +54,14 @@ SIGNATURES = {
                                          C.c_size_t, C.c_void_p]),
     'oake_vild_ensemble': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p]),
+    'oake_loss_workspace_bytes': (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    'oake_pair_loss': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    'oake_rkd_loss': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_size_t, C.c_void_p]),
+    'oake_asymmetric_loss': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_void_p]),
     'oake_last_error': (C.c_char_p, []),
     'oake_act_dtype': (C.c_char_p, []),
     'oake_abi_version': (C.c_int, []),

@@ -66,8 +66,15 @@ struct CCfg {
 
 enum BiasMode { kPlain = 0, kBits = 1, kLoad = 2 };  // see attention_tc.cu
 
-__device__ __forceinline__ void pair_sync(int q) {  // the two softmax warps of lane quarter q
-  asm volatile("bar.sync %0, 64;\n" ::"r"(q + 1) : "memory");
+// Named barrier of the two softmax warps of lane quarter q (ids 1..4, 64 threads; id 0 is
+// __syncthreads).  Immediate ids: ptxas then reserves five barriers instead of all sixteen.
+__device__ __forceinline__ void pair_sync(int q) {
+  switch (q) {
+    case 0: asm volatile("bar.sync 1, 64;\n" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;\n" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;\n" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;\n" ::: "memory"); break;
+  }
 }
 
 // One half (HI = 0: keys 0..95, HI = 1: keys 96..207) of one query row.  Same arithmetic per element

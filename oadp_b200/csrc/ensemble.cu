@@ -45,31 +45,33 @@ __global__ void __launch_bounds__(256) vild_ensemble_kernel(const float* __restr
   float sb = 0.f, so = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxPerLane; ++i) {
-    vb[i] = expf(vb[i] - mb);  // -inf (masked column, padding) -> 0
-    vo[i] = expf(vo[i] - mo);
-    sb += vb[i];
-    so += vo[i];
+    vb[i] -= mb;  // -inf (masked column, padding) stays -inf
+    vo[i] -= mo;
+    sb += expf(vb[i]);
+    so += expf(vo[i]);
   }
-  const float rb = 1.0f / warp_sum(sb);
-  const float ro = 1.0f / warp_sum(so);
+  // log-domain: log(softmax(b)^l * softmax(o)^(1-l)) = l (b - mb - log sb) + (1-l) (o - mo - log so);
+  // one exponential per element is left, for the foreground sum the background column needs
+  const float lb = logf(warp_sum(sb));
+  const float lo = logf(warp_sum(so));
   float fg = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxPerLane; ++i) {
     const int c = lane + 32 * i;
-    float s = 0.f;
+    float ls = -INFINITY;
     if (c < K1) {
       const float l = __ldg(lambda + c);
-      s = powf(vb[i] * rb, l) * powf(vo[i] * ro, 1.0f - l);
+      ls = l * (vb[i] - lb) + (1.0f - l) * (vo[i] - lo);  // lambda in (0, 1): -inf terms give -inf, never NaN
     }
-    vb[i] = s;
-    if (c < K1 - 1) fg += s;
+    vb[i] = ls;
+    if (c < K1 - 1) fg += expf(ls);
   }
   fg = warp_sum(fg);
   float* dst = out + static_cast<size_t>(row) * ld_out;
 #pragma unroll
   for (int i = 0; i < kMaxPerLane; ++i) {
     const int c = lane + 32 * i;
-    if (c < K1) dst[c] = logf(c == K1 - 1 ? 1.0f - fg : vb[i]);
+    if (c < K1) dst[c] = c == K1 - 1 ? logf(1.0f - fg) : vb[i];
   }
 }
 

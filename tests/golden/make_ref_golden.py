@@ -7,7 +7,7 @@ dependencies (todd, clip, mmcv, mmdet, lvis, pycocotools) are neither installed 
 the individual modules below are loaded with importlib on top of the stand-ins in ``ref_stubs.py``:
 
     oadp/oake/base.py  oadp/oake/globals.py  oadp/oake/blocks.py  oadp/oake/objects.py
-    oadp/base/globals_.py  oadp/dp/utils.py  oadp/dp/classifiers.py
+    oadp/base/globals_.py  oadp/dp/utils.py  oadp/dp/classifiers.py  oadp/base/losses.py
 
 Everything recorded in the fixture is produced by the reference's code: ``Dataset._partition`` /
 ``_partitions`` / ``_block`` / ``_bbox`` / ``_preprocess`` (blocks.py:40-109), ``_preprocess``
@@ -87,6 +87,16 @@ def ref_inputs():
     return images, proposals
 
 
+def loss_inputs():
+    g = torch.Generator().manual_seed(77)
+    probs = torch.sigmoid(torch.randn(11, 65, generator=g) * 2)
+    probs[0, 0], probs[0, 1] = 0.0, 1.0  # the eps / clip clamps
+    targets = torch.rand(11, 65, generator=g) > 0.9
+    student = torch.nn.functional.normalize(torch.randn(9, 512, generator=g), dim=-1)
+    teacher = torch.nn.functional.normalize(torch.randn(9, 512, generator=g), dim=-1).half().float()
+    return probs, targets, student, teacher
+
+
 def classifier_inputs():
     g = torch.Generator().manual_seed(99)
     names = [f'cat{i:02d}' for i in range(9)]
@@ -126,6 +136,7 @@ def _load_reference_modules():
     m['objects'] = load('oake.objects', 'oadp/oake/objects.py')
     m['utils'] = load('dp.utils', 'oadp/dp/utils.py')
     m['classifiers'] = load('dp.classifiers', 'oadp/dp/classifiers.py')
+    m['losses'] = load('base.losses', 'oadp/base/losses.py')
     return m
 
 
@@ -141,7 +152,7 @@ def main() -> None:
     images, proposals = ref_inputs()
     out = dict(weight_seed=WEIGHT_SEED, images=IMAGES, reference_files=[
         'oadp/oake/base.py', 'oadp/oake/globals.py', 'oadp/oake/blocks.py', 'oadp/oake/objects.py',
-        'oadp/base/globals_.py', 'oadp/dp/utils.py', 'oadp/dp/classifiers.py'
+        'oadp/base/globals_.py', 'oadp/dp/utils.py', 'oadp/dp/classifiers.py', 'oadp/base/losses.py'
     ])
 
     # ---- blocks.py: _partition over every length a COCO image can have
@@ -226,6 +237,23 @@ def main() -> None:
     finally:
         ppath.unlink()
     out['classifier'] = res
+
+    # ---- losses.py: AsymmetricLoss (block / global heads) and RKDLoss (block relations), value + gradient
+    L = m['losses']
+    probs, targets, student, teacher = loss_inputs()
+    lres = {}
+    for name, kw in (('asl_configs', dict(gamma_neg=4, gamma_pos=0)), ('asl_defaults', dict()),
+                     ('asl_sum_w16', dict(gamma_neg=4, gamma_pos=0, reduction='sum', weight=16.0))):
+        x = probs.clone().requires_grad_(True)
+        loss = L.AsymmetricLoss(**kw)(x, targets)
+        loss.backward()
+        lres[name] = dict(loss=loss.detach(), grad=x.grad.clone())
+    for name, kw in (('rkd', dict()), ('rkd_w8', dict(weight=8.0))):
+        sx = student.clone().requires_grad_(True)
+        loss = L.RKDLoss(**kw)(sx, teacher)
+        loss.backward()
+        lres[name] = dict(loss=loss.detach(), grad=sx.grad.clone())
+    out['losses'] = lres
 
     torch.save(out, HERE / 'ref_golden.pt')
     size = (HERE / 'ref_golden.pt').stat().st_size

@@ -200,6 +200,59 @@ class _Control(enum.Enum):
     BREAK = enum.auto()
 
 
+# ------------------------------------------------------------------------------- todd.losses / mmcv
+
+
+class _BaseLoss(nn.Module):
+    """todd 0.3.0 ``losses.BaseLoss`` as the reference uses it: ``reduce`` applies the reduction
+    (default mean) and a scalar weight (the configs' WarmupScheduler is a scalar at a given step)."""
+
+    def __init__(self, reduction: str = 'mean', weight: float = 1.0, **kwargs) -> None:
+        super().__init__()
+        self._reduction = reduction
+        self._weight = float(weight)
+
+    def reduce(self, loss: torch.Tensor, **kwargs) -> torch.Tensor:
+        if self._reduction == 'mean':
+            loss = loss.mean()
+        elif self._reduction == 'sum':
+            loss = loss.sum()
+        return self._weight * loss
+
+
+class _MSELoss(_BaseLoss):
+
+    def forward(self, pred: torch.Tensor, target: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        return self.reduce(F.mse_loss(pred, target, reduction='none'), **kwargs)
+
+
+class _L1Loss(_BaseLoss):
+
+    def forward(self, pred: torch.Tensor, target: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        return self.reduce(F.l1_loss(pred, target, reduction='none'), **kwargs)
+
+
+def _force_fp32(apply_to=()):
+    """mmcv.runner.force_fp32: named tensor arguments are cast to fp32 (fp16_enabled is False here)."""
+    import functools
+    import inspect
+
+    def deco(fn):
+        names = list(inspect.signature(fn).parameters)
+
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            args = list(args)
+            for i, a in enumerate(args):
+                if i < len(names) and names[i] in apply_to and torch.is_tensor(a) and a.is_floating_point():
+                    args[i] = a.float()
+            return fn(*args, **kwargs)
+
+        return wrapper
+
+    return deco
+
+
 def _make_todd() -> types.ModuleType:
     todd = types.ModuleType('todd')
     todd.Module = nn.Module
@@ -220,6 +273,15 @@ def _make_todd() -> types.ModuleType:
     todd.utils.Control = _Control
     todd.base = types.ModuleType('todd.base')
     todd.base.DictAction = object
+    todd.losses = types.ModuleType('todd.losses')
+    todd.losses.BaseLoss = _BaseLoss
+    todd.losses.MSELoss = _MSELoss
+    todd.losses.L1Loss = _L1Loss
+
+    class LossRegistry(_Registry):
+        pass
+
+    todd.losses.LossRegistry = LossRegistry
     return todd
 
 
@@ -385,6 +447,7 @@ def install() -> None:
     sys.modules['todd'] = todd
     sys.modules['todd.utils'] = todd.utils
     sys.modules['todd.base'] = todd.base
+    sys.modules['todd.losses'] = todd.losses
     clip = types.ModuleType('clip')
     clip.model = types.ModuleType('clip.model')
     for k in (CLIP, VisionTransformer, Transformer, ResidualAttentionBlock, LayerNorm, QuickGELU):
@@ -392,6 +455,7 @@ def install() -> None:
     clip.load_default = _load_default
     sys.modules['clip'] = clip
     sys.modules['clip.model'] = clip.model
-    for name in ('mmdet', 'mmdet.models', 'mmdet.models.utils', 'mmdet.models.utils.builder'):
+    for name in ('mmdet', 'mmdet.models', 'mmdet.models.utils', 'mmdet.models.utils.builder', 'mmcv', 'mmcv.runner'):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules['mmdet.models.utils.builder'].LINEAR_LAYERS = _MMRegistry()
+    sys.modules['mmcv.runner'].force_fp32 = _force_fp32

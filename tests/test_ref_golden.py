@@ -166,3 +166,30 @@ def test_product_objects_plan_vs_reference(inputs):
         assert torch.equal(torch.from_numpy(plan.bboxes), want['bboxes'])
         assert torch.equal(torch.from_numpy(plan.objectness), want['objectness'])
         assert torch.equal(torch.from_numpy(plan.expanded), want['expanded'])
+
+
+# ---------------------------------------------------------------------------------------------- losses
+@pytest.mark.parametrize('name,kw', [('asl_configs', dict(gamma_neg=4, gamma_pos=0)), ('asl_defaults', dict()),
+                                     ('asl_sum_w16', dict(gamma_neg=4, gamma_pos=0, reduction='sum', weight=16.0))])
+def test_asymmetric_loss_vs_reference(name, kw):
+    """oadp/base/losses.py:10-65, value and gradient (the focusing weight carries no gradient)."""
+    from oracle import losses as ol
+    probs, targets, _, _ = mk.loss_inputs()
+    x = probs.clone().requires_grad_(True)
+    loss = ol.asymmetric_loss(x, targets, **kw)
+    loss.backward()
+    want = REF['losses'][name]
+    assert abs(float(loss) - float(want['loss'])) <= 1e-6 * abs(float(want['loss']))
+    assert (x.grad - want['grad']).abs().max() <= 1e-5 * want['grad'].abs().max()
+
+
+@pytest.mark.parametrize('name,kw', [('rkd', dict()), ('rkd_w8', dict(weight=8.0))])
+def test_rkd_loss_vs_reference(name, kw):
+    from oracle import losses as ol
+    _, _, student, teacher = mk.loss_inputs()
+    s = student.clone().requires_grad_(True)
+    loss = ol.rkd_loss(s, teacher, **kw)
+    loss.backward()
+    want = REF['losses'][name]
+    assert abs(float(loss) - float(want['loss'])) <= 1e-5 * abs(float(want['loss']))
+    assert (s.grad - want['grad']).abs().max() <= 1e-5 * want['grad'].abs().max()
