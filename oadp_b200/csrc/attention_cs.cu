@@ -68,7 +68,9 @@ enum BiasMode { kPlain = 0, kBits = 1, kLoad = 2 };  // see attention_tc.cu
 
 // Named barrier of the two softmax warps of lane quarter q (ids 1..4, 64 threads; id 0 is
 // __syncthreads).  Immediate ids: ptxas then reserves five barriers instead of all sixteen.
-__device__ __forceinline__ void pair_sync(int q) {
+// __noinline__: both halves' instantiations then arrive from the same instruction, which is what
+// compute-sanitizer's synccheck expects of the participants of one barrier.
+__device__ __noinline__ void pair_sync(int q) {
   switch (q) {
     case 0: asm volatile("bar.sync 1, 64;\n" ::: "memory"); break;
     case 1: asm volatile("bar.sync 2, 64;\n" ::: "memory"); break;
