@@ -200,7 +200,7 @@ def main() -> None:
         raise SystemExit('bench.py --impl ours needs a CUDA device: the OAKE hot path has no CPU fallback')
     torch.cuda.set_device(local_rank % torch.cuda.device_count())
     if world > 1:
-        dist.init_process_group('nccl')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', torch.cuda.current_device()))
     from oadp_b200 import build, synth
     if rank == 0:
         build.build()

@@ -18,6 +18,7 @@ Changed on purpose (B200-first):
 from __future__ import annotations
 
 import argparse
+import collections
 import concurrent.futures
 import itertools
 import pathlib
@@ -132,6 +133,7 @@ class BaseValidator(ABC, Generic[T]):
             raise ValueError(f"store must be 'pth' or 'packed', not {store!r}")
         self._packed: Optional[PackedWriter] = None
         workers = int(dataloader.get('num_workers', 2)) or 1
+        self._decode_workers = 0 if Store.DRY_RUN else int(dataloader.get('num_workers', 2))
         if store == 'packed':
             self._dataset.use_packed()
             out_dir = self._dataset._output_dir
@@ -170,10 +172,30 @@ class BaseValidator(ABC, Generic[T]):
         costs = [self._dataset.cost(i) for i in todo]
         return oake_dist.balanced_partition(costs, world)[rank]
 
+    def _items(self, indices: List[int]) -> Iterator[Optional[Item]]:
+        """Dataset items in order, decoded ahead of the GPU by a few host threads (PIL releases the
+        GIL while it decodes) -- the role of the reference's DataLoader workers (base.py:78-89), minus
+        the PIL crop / resize work, which lives on the GPU here.  DRY_RUN: no threads (base.py:82-83)."""
+        if self._decode_workers <= 0:
+            for i in indices:
+                yield self._dataset[i]
+            return
+        depth = max(2 * self._batch_images, 2 * self._decode_workers)
+        with concurrent.futures.ThreadPoolExecutor(max_workers=self._decode_workers) as pool:
+            window: 'collections.deque' = collections.deque()
+            it = iter(indices)
+            for i in itertools.islice(it, depth):
+                window.append(pool.submit(self._dataset.__getitem__, i))
+            while window:
+                item = window.popleft().result()
+                nxt = next(it, None)
+                if nxt is not None:
+                    window.append(pool.submit(self._dataset.__getitem__, nxt))
+                yield item
+
     def _batches(self, indices: List[int]) -> Iterator[List[Item]]:
         batch: List[Item] = []
-        for i in indices:
-            item = self._dataset[i]
+        for item in self._items(indices):
             if item is None:  # already on disk (base.py:45-47)
                 continue
             batch.append(item)
@@ -229,10 +251,11 @@ class BaseValidator(ABC, Generic[T]):
         if not Store.CUDA:
             raise RuntimeError('oadp_b200 OAKE needs a CUDA (sm_100a) device; there is no CPU path')
         import os
-        if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not torch.distributed.is_initialized():
-            torch.distributed.init_process_group(backend='nccl')
         local_rank = int(os.environ.get('LOCAL_RANK', '0'))
         torch.cuda.set_device(local_rank % torch.cuda.device_count())
+        if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not torch.distributed.is_initialized():
+            torch.distributed.init_process_group(backend='nccl',
+                                                 device_id=torch.device('cuda', torch.cuda.current_device()))
 
         model, _ = cls._build_model()
         train = config.pop('train')
