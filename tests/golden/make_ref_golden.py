@@ -97,6 +97,14 @@ def loss_inputs():
     return probs, targets, student, teacher
 
 
+def recall_inputs():
+    g = torch.Generator().manual_seed(31)
+    logits = torch.randn(54, 65, generator=g)
+    targets = torch.rand(54, 65, generator=g) > 0.93
+    targets[:, 7] = False  # a label that never occurs
+    return logits, targets
+
+
 def classifier_inputs():
     g = torch.Generator().manual_seed(99)
     names = [f'cat{i:02d}' for i in range(9)]
@@ -254,6 +262,14 @@ def main() -> None:
         loss.backward()
         lres[name] = dict(loss=loss.detach(), grad=sx.grad.clone())
     out['losses'] = lres
+
+    # ---- utils.py: MultilabelTopKRecall (sklearn macro recall over the labels that occur)
+    rres = {}
+    for k in (1, 5, 20):
+        rres[k] = m['utils'].MultilabelTopKRecall(k=k)(*recall_inputs())
+    empty_logits, empty_targets = recall_inputs()
+    rres['no_positive'] = m['utils'].MultilabelTopKRecall(k=5)(empty_logits, torch.zeros_like(empty_targets))
+    out['recall'] = rres
 
     torch.save(out, HERE / 'ref_golden.pt')
     size = (HERE / 'ref_golden.pt').stat().st_size

@@ -193,3 +193,21 @@ def test_rkd_loss_vs_reference(name, kw):
     want = REF['losses'][name]
     assert abs(float(loss) - float(want['loss'])) <= 1e-5 * abs(float(want['loss']))
     assert (s.grad - want['grad']).abs().max() <= 1e-5 * want['grad'].abs().max()
+
+
+@pytest.mark.parametrize('k', [1, 5, 20, 'no_positive'])
+def test_topk_recall_vs_reference(k):
+    """oadp/dp/utils.py:13-44 (sklearn macro recall on the host) vs the device-side restatement the
+    product ships (pure torch reductions; runs on CPU tensors as well)."""
+    from oadp_b200.dp.utils import MultilabelTopKRecall
+    logits, targets = mk.recall_inputs()
+    if k == 'no_positive':
+        got = MultilabelTopKRecall(k=5)(logits, torch.zeros_like(targets))
+    else:
+        got = MultilabelTopKRecall(k=k)(logits, targets)
+    want = REF['recall'][k]
+    assert got.shape == want.shape and got.dtype == want.dtype
+    if torch.isnan(want):
+        assert torch.isnan(got)
+    else:
+        assert abs(float(got) - float(want)) < 1e-4
