@@ -32,7 +32,9 @@ def image(width: int, height: int, seed: int) -> np.ndarray:
     fine = rng.random((height, width, 3))
     out = 0.8 * smooth + 0.2 * fine
     out = (out - out.min()) / (out.max() - out.min())
-    return (out * 255.0 + 0.5).astype(np.uint8)
+    # C-contiguous HWC like a decoded image (the fancy indexing above leaves a permuted memory order,
+    # which would make every staging copy a strided gather)
+    return np.ascontiguousarray((out * 255.0 + 0.5).astype(np.uint8))
 
 
 def images(n: int, seed: int = 0, sizes=COCO_SIZES) -> List[np.ndarray]:
