@@ -442,7 +442,7 @@ bool attention_side_row_fast() {
 cudaError_t launch_attention(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
                              int heads, int with_side, int side_only) {
   if (B <= 0) return cudaSuccess;
-  if (attention_use_tc(P, side_only)) return launch_attention_tc(st, qkv, mask, out, B, P, heads, with_side, side_only);
+  if (attention_use_tc(P, side_only)) return launch_attention_cs(st, qkv, mask, out, B, P, heads, with_side, side_only);
   if (with_side) {
     if (P != 196 || mask == nullptr) return cudaErrorInvalidValue;
     if (side_only && attention_side_row_fast()) {

@@ -1,11 +1,14 @@
-// Persistent tcgen05 attention for the 197-token OAKE tower, column-split form (default).
+// Persistent tcgen05 attention for the 197-token OAKE tower (SURVEY 2.2 K4 + K7): the math of
+// nn.MultiheadAttention inside every CLIP ResidualAttentionBlock (reference call site
+// oadp/oake/objects.py:330) plus the objects side token of oadp/oake/objects.py:224-247 as one more
+// query row / key row of the same tile.
 //
-// Same contract, data layout and MMA formulation as attention_tc.cu (S = Q K^T into TMEM, packed
-// fp16 P written over consumed S columns, O = P V with P as the TMEM operand and V MN-major), but a
-// different division of labour, chosen from the ncu stall samples of that kernel: there each
-// 128-row tile belonged to ONE group of four softmax warps, so per group the chain
-// softmax -> PV -> O drain -> next S was serial and the MUFU pipe sat idle through its gaps
-// (profiles/r1_11_attention_stalls.txt).  Here
+// One CTA per SM walks over (crop, head) items; an item is two 128-row query tiles (tokens 0..127 and
+// 128..197) against one 208-key K/V tile: S = Q K^T into TMEM, P = exp2(S - max) as packed fp16
+// written over the consumed S columns, O = P V with P as the TMEM operand and V MN-major.  Division
+// of labour (chosen from ncu stall samples of a first version in which each tile belonged to ONE
+// group of four softmax warps that also drained it: per group the chain softmax -> PV -> O drain ->
+// next S was serial and the MUFU pipe idle through its gaps, profiles/r1_11_attention_stalls.txt):
 //
 //   warps 0-7    softmax: ALL eight work on the current tile -- warp w owns TMEM lanes 32 (w % 4)..
 //                and one half of the keys (w < 4: keys 0..95, w >= 4: keys 96..207); the two warps of
@@ -64,7 +67,14 @@ struct CCfg {
   static constexpr int kThreads = 32 * 14;
 };
 
-enum BiasMode { kPlain = 0, kBits = 1, kLoad = 2 };  // see attention_tc.cu
+// How a softmax warp biases its scores.
+//   kPlain: main-stream rows only.  Keys 0..196 (patches, class) valid, no bias.
+//   kBits / kLoad: the warps that hold the side row (warp-uniform code, per-lane select).  The side
+//           row adds -100 log2e mask[key] on patches, -inf on the class key, 0 on its own key
+//           (objects.py:204-247); main-stream rows add 0 / -inf by key validity.  kBits takes the mask
+//           from 7 words of bits (the reference's masks are 0 / 1 by construction, objects.py:147-153);
+//           kLoad reads the fp32 mask row for any other mask values.
+enum BiasMode { kPlain = 0, kBits = 1, kLoad = 2 };
 
 // Named barrier of the two softmax warps of lane quarter q (ids 1..4, 64 threads; id 0 is
 // __syncthreads).  Immediate ids: ptxas then reserves five barriers instead of all sixteen.
@@ -79,8 +89,9 @@ __device__ __noinline__ void pair_sync(int q) {
   }
 }
 
-// One half (HI = 0: keys 0..95, HI = 1: keys 96..207) of one query row.  Same arithmetic per element
-// as attention_tc.cu::softmax_row (bit-identical results for a row whichever warp pair it lands in).
+// One half (HI = 0: keys 0..95, HI = 1: keys 96..207) of one query row.  The arithmetic of a
+// main-stream row is the same in every mode (bias added after the fma), so a row gets bit-identical
+// results whichever warp pair it lands in: batch composition stays invisible.
 template <bool SIDE, int MODE, int HI>
 struct HalfRow {
   using C = CCfg<SIDE>;
@@ -525,6 +536,18 @@ cudaError_t launch_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_
 }
 
 }  // namespace
+
+// The persistent tcgen05 kernel serves the 197-token tower whenever whole tiles are wanted; the
+// 50-token tower stays on the mma.sync kernel of attention.cu and the last objects block (side row
+// only) on its one-warp-per-head kernel.  OAKE_ATTN=mma forces the mma.sync kernels everywhere (A/B).
+bool attention_use_tc(int P, int side_only) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OAKE_ATTN");
+    v = (e != nullptr && e[0] == 'm') ? 0 : 1;
+  }
+  return v == 1 && P == 196 && !side_only;
+}
 
 cudaError_t launch_attention_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
                                 int heads, int with_side, int side_only) {

@@ -1,4 +1,4 @@
-// Helpers shared by the tcgen05 attention kernels (attention_tc.cu, attention_cs.cu): inline-PTX
+// Helpers of the tcgen05 attention kernel (attention_cs.cu): inline-PTX
 // wrappers for TMEM stores / TS-MMA / MN-major descriptors, shared-window loads and stores, the
 // token -> activation-row map.  Included inside each file's anonymous namespace users via `oake::attn`.
 #pragma once

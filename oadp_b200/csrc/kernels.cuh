@@ -66,13 +66,9 @@ cudaError_t launch_l2norm_half(cudaStream_t st, const float* e, __half* out, int
 //                  side_only = 1 writes just the B side rows (last block of the objects tower).
 cudaError_t launch_attention(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
                              int heads, int with_side, int side_only);
-// attention_tc.cu: persistent tcgen05 implementation of the same contract for the 197-token tower
-// (whole tiles; default there); OAKE_ATTN=mma selects the mma.sync kernel of attention.cu instead.
+// attention_cs.cu: persistent tcgen05 implementation of the same contract for the 197-token tower
+// (whole tiles; default there).  OAKE_ATTN=mma selects the mma.sync kernel of attention.cu instead.
 bool attention_use_tc(int P, int side_only);
-cudaError_t launch_attention_tc(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
-                                int heads, int with_side, int side_only);
-// attention_cs.cu: the column-split form of the persistent kernel (all eight softmax warps on one
-// tile, dedicated drain warps); default.  OAKE_ATTN=pp selects the row-owner form of attention_tc.cu.
 cudaError_t launch_attention_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
                                 int heads, int with_side, int side_only);
 

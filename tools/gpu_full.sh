@@ -13,7 +13,7 @@ echo "$(ts) == launch list"
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --images 2 > gpurun_out/launches_bench.log 2>&1
 echo "$(ts) == ncu full: attention + gemm"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_pp|gemm_tcgen05" -s 6 -c 5 -f -o gpurun_out/prof_tower \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_cs|gemm_tcgen05" -s 6 -c 5 -f -o gpurun_out/prof_tower \
   python tools/quick_bench.py --variant 1 --batch 478 --iters 1 > gpurun_out/ncu_tower.log 2>&1; tail -2 gpurun_out/ncu_tower.log
 fi
 echo "$(ts) done"
