@@ -41,40 +41,11 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-// Epilogue warps per CTA: 8 (two per TMEM lane quarter) or 16 (four per quarter).  The LayerNorm-fold
-// / QuickGELU epilogues of the K = 768 GEMMs (QKV, c_fc) are bound by the latency of their dependent
-// tcgen05.ld -> math -> pack -> store chain, not by issue slots: sixteen warps keep four chains per
-// SM sub-partition in flight.  Opt-in ($OAKE_GEMM_EPI_WARPS=16): measured slower than eight on B200
-// (c_fc 878 vs 1015 TFLOP/s) -- the epilogue was bound by a cluster-scope release fence, not by
-// latency hiding (see mbar_arrive_cluster).
-constexpr int epi_warps_for(int mode) { return mode == 1 /* EPI_ACT */ ? 16 : 8; }
-
-enum EpiMode {
-  EPI_F32 = 0,  // fp32 out: bias, QuickGELU
-  EPI_ACT = 1,  // act out: LayerNorm fold | bias, QuickGELU
-  EPI_RES = 2,  // act out: bias + act residual (+ row statistics)
-};
-
-// CTA-pair mode for the 256-wide tiles (128-wide tiles stay 1-CTA).  $OAKE_GEMM_CTA_GROUP=1|2
-// overrides the default once per process (A/B measurements); it also decides the W tensor-map box.
-int cta_group() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("OAKE_GEMM_CTA_GROUP");
-    v = (e != nullptr && e[0] == '1') ? 1 : 2;
-  }
-  return v;
-}
-
-int epi_warps_act() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("OAKE_GEMM_EPI_WARPS");
-    v = (e != nullptr && e[0] == '1') ? 16 : 8;  // measured r1: 16 warps are slower (5 stages, 96 registers)
-  }
-  return v;
-}
-
+// Epilogue warps per CTA (template parameter EW): 8 = two per TMEM lane quarter, each owning half of
+// the tile's columns.  Sixteen (four per quarter, 5 pipeline stages, 96 registers) were measured
+// SLOWER on B200 (c_fc 878 vs 1015 TFLOP/s, r1): the epilogue was bound by a cluster-scope release
+// fence and by generic-pointer shared-memory accesses, not by latency hiding -- see
+// mbar_arrive_cluster and lds128 / sts128.  Only EW = 8 is instantiated.
 template <int BN, int CG = 1, int EW = 8>
 struct Cfg {
   static constexpr int kEpiWarps = EW;
@@ -630,8 +601,6 @@ cudaError_t launch_gemm_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtens
                            const GemmEpilogue& ep, int num_sms) {
   if (ep.out_f32) return launch_gemm_inst<BN, EPI_F32, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
   if (ep.residual != nullptr) return launch_gemm_inst<BN, EPI_RES, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
-  if (BN == 256 && CG == 2 && epi_warps_act() == 16)  // (the 1-CTA 256-wide tile has no shared memory left for it)
-    return launch_gemm_inst<BN, EPI_ACT, CG, BN == 256 ? epi_warps_for(EPI_ACT) : 8>(st, tmA, tmW, M, N, K, ep, num_sms);
   return launch_gemm_inst<BN, EPI_ACT, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
 }
 
