@@ -46,6 +46,24 @@ constexpr int UMMA_K = 16;
 // SLOWER on B200 (c_fc 878 vs 1015 TFLOP/s, r1): the epilogue was bound by a cluster-scope release
 // fence and by generic-pointer shared-memory accesses, not by latency hiding -- see
 // mbar_arrive_cluster and lds128 / sts128.  Only EW = 8 is instantiated.
+
+enum EpiMode {
+  EPI_F32 = 0,  // fp32 out: bias, QuickGELU
+  EPI_ACT = 1,  // act out: LayerNorm fold | bias, QuickGELU
+  EPI_RES = 2,  // act out: bias + act residual (+ row statistics)
+};
+
+// CTA-pair mode for the 256-wide tiles (128-wide tiles stay 1-CTA).  $OAKE_GEMM_CTA_GROUP=1|2
+// overrides the default once per process (A/B measurements); it also decides the W tensor-map box.
+int cta_group() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("OAKE_GEMM_CTA_GROUP");
+    v = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 template <int BN, int CG = 1, int EW = 8>
 struct Cfg {
   static constexpr int kEpiWarps = EW;
