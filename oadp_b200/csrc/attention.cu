@@ -322,13 +322,7 @@ cudaError_t launch_attn(cudaStream_t st, const act_t* qkv, const float* mask, ac
                         int side_only) {
   using C = ACfg<P, SIDE>;
   if (heads % C::HPC != 0) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<P, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<attention_kernel<P, SIDE>>(C::kSmemBytes); e != cudaSuccess) return e;
   attention_kernel<P, SIDE><<<B * (heads / C::HPC), C::kThreads, C::kSmemBytes, st>>>(qkv, mask, out, B, heads,
                                                                                       side_only);
   return cudaGetLastError();

@@ -513,17 +513,10 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
 template <bool SIDE>
 cudaError_t launch_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int heads, int rows) {
   using C = CCfg<SIDE>;
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_cs_kernel<SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<attention_cs_kernel<SIDE>>(C::kSmemBytes); e != cudaSuccess) return e;
+  int dev = 0, num_sms = 0;
+  if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+  if (cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); e != cudaSuccess) return e;
   CUtensorMap tmQ0, tmQ1, tmKV;
   const uint64_t cols = 3ull * heads * kDh;
   if (make_tmap_act_2d(&tmQ0, qkv, rows, cols, 128) || make_tmap_act_2d(&tmQ1, qkv, rows, cols, C::kPatch1) ||

@@ -371,13 +371,8 @@ cudaError_t launch_im2col_u8(cudaStream_t st, const uint8_t* arena, const oake_c
 cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs,
                              int n_jobs, int max_tiles, int* err_flag) {
   if (n_jobs <= 0 || max_tiles <= 0) return cudaSuccess;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(resize_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(ResizeSmem)));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<resize_u8_kernel>(static_cast<int>(sizeof(ResizeSmem))); e != cudaSuccess)
+    return e;
   dim3 grid(max_tiles, n_jobs);
   resize_u8_kernel<<<grid, 256, sizeof(ResizeSmem), st>>>(src, dst, jobs, err_flag);
   return cudaGetLastError();

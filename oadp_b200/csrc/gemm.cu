@@ -589,13 +589,8 @@ template <int BN, int MODE, int CG, int EW>
 cudaError_t launch_gemm_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N,
                              int K, const GemmEpilogue& ep, int num_sms) {
   using C = Cfg<BN, CG, EW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, MODE, CG, EW>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem<gemm_tcgen05_kernel<BN, MODE, CG, EW>>(C::kSmemBytes); e != cudaSuccess)
+    return e;
   const int tiles = ((M + BM * CG - 1) / (BM * CG)) * (N / BN);
   const int slots = num_sms / CG;
   const int grid = (tiles < slots ? tiles : slots) * CG;

@@ -6,6 +6,20 @@
 
 namespace oake {
 
+// Raises a kernel's dynamic shared-memory limit once per (kernel, device): the attribute belongs to
+// the device's context, so a process that drives several GPUs needs it on each of them.
+template <auto Kernel>
+inline cudaError_t ensure_dynamic_smem(int bytes) {
+  static unsigned long long done = 0;  // one bit per device ordinal
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && ((done >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
+  return e;
+}
+
 // ---------------------------------------------------------------- gemm.cu
 // Row statistics travel as kStatSlots partial (sum, sum of squares) pairs per row: the producing
 // GEMM writes one slot per 128 output columns (N <= 1024), the consumer adds the slots in a fixed
