@@ -8,6 +8,7 @@ the individual modules below are loaded with importlib on top of the stand-ins i
 
     oadp/oake/base.py  oadp/oake/globals.py  oadp/oake/blocks.py  oadp/oake/objects.py
     oadp/base/globals_.py  oadp/dp/utils.py  oadp/dp/classifiers.py  oadp/base/losses.py
+    oadp/dp/datasets.py (LoadCLIPFeatures)
 
 Everything recorded in the fixture is produced by the reference's code: ``Dataset._partition`` /
 ``_partitions`` / ``_block`` / ``_bbox`` / ``_preprocess`` (blocks.py:40-109), ``_preprocess``
@@ -97,6 +98,32 @@ def loss_inputs():
     return probs, targets, student, teacher
 
 
+def feature_store_inputs():
+    """Per-image records in the layout OAKE writes (fp16), plus mmdet-style `results` dicts."""
+    g = torch.Generator().manual_seed(55)
+    rng = np.random.default_rng(55)
+
+    def boxes(m):
+        lt = torch.rand(m, 2, generator=g) * 400
+        return torch.cat([lt, lt + 2 + torch.rand(m, 2, generator=g) * 200], 1).half()
+
+    records, results = {}, {}
+    for i in range(3):
+        key = f'{500 + i:012d}'
+        nb, no = 5 + 3 * i, 9 + 2 * i
+        ob = boxes(no)
+        ob[1] = torch.tensor([10.0, 10.0, 13.0, 40.0]).half()  # w < 4: dropped by the re-applied min_wh filter
+        records[key] = dict(globals=torch.randn(1, 512, generator=g).half()[0],
+                            blocks=dict(embeddings=torch.randn(nb, 512, generator=g).half(), bboxes=boxes(nb)),
+                            objects=dict(embeddings=torch.randn(no, 512, generator=g).half(), bboxes=ob,
+                                         objectness=torch.rand(no, 1, generator=g).half()))
+        xy = rng.uniform(0, 400, size=(6, 2)).astype(np.float32)
+        results[key] = dict(img_info=dict(id=500 + i), bbox_fields=['gt_bboxes'],
+                            gt_bboxes=np.concatenate([xy, xy + rng.uniform(5, 200, size=(6, 2)).astype(np.float32)], 1),
+                            gt_labels=np.array([3, 5, 6, 9, 0, 2]))  # 6 and 9 are pseudo labels (>= num_all = 6)
+    return records, results
+
+
 def recall_inputs():
     g = torch.Generator().manual_seed(31)
     logits = torch.randn(54, 65, generator=g)
@@ -145,6 +172,9 @@ def _load_reference_modules():
     m['utils'] = load('dp.utils', 'oadp/dp/utils.py')
     m['classifiers'] = load('dp.classifiers', 'oadp/dp/classifiers.py')
     m['losses'] = load('base.losses', 'oadp/base/losses.py')
+    base = sys.modules[f'{PKG}.base']
+    base.coco, base.lvis = globals_.coco, globals_.lvis  # `from ..base import Globals, coco, lvis`
+    m['datasets'] = load('dp.datasets', 'oadp/dp/datasets.py')
     return m
 
 
@@ -160,7 +190,8 @@ def main() -> None:
     images, proposals = ref_inputs()
     out = dict(weight_seed=WEIGHT_SEED, images=IMAGES, reference_files=[
         'oadp/oake/base.py', 'oadp/oake/globals.py', 'oadp/oake/blocks.py', 'oadp/oake/objects.py',
-        'oadp/base/globals_.py', 'oadp/dp/utils.py', 'oadp/dp/classifiers.py', 'oadp/base/losses.py'
+        'oadp/base/globals_.py', 'oadp/dp/utils.py', 'oadp/dp/classifiers.py', 'oadp/base/losses.py',
+        'oadp/dp/datasets.py'
     ])
 
     # ---- blocks.py: _partition over every length a COCO image can have
@@ -270,6 +301,24 @@ def main() -> None:
     empty_logits, empty_targets = recall_inputs()
     rres['no_positive'] = m['utils'].MultilabelTopKRecall(k=5)(empty_logits, torch.zeros_like(empty_targets))
     out['recall'] = rres
+
+    # ---- datasets.py: LoadCLIPFeatures (the consumer of the OAKE files) on in-memory access layers
+    import todd
+    records, results = feature_store_inputs()
+    ALR = todd.datasets.AccessLayerRegistry
+    for task in ('globals', 'blocks', 'objects'):
+        ALR.stores[f'coco/oake/{task}/train'] = {k: v[task] for k, v in records.items()}
+    G.Globals.categories = G.Categories(bases=('a', 'b', 'c', 'd'), novels=('e', 'f'))  # num_all = 6
+    step = m['datasets'].LoadCLIPFeatures(default=dict(type='PthAccessLayer', data_root='unused'),
+                                          globals_=dict(task_name='coco/oake/globals/train'),
+                                          blocks=dict(task_name='coco/oake/blocks/train'),
+                                          objects=dict(task_name='coco/oake/objects/train'))
+    fres = {}
+    for key, res in results.items():
+        r = step(dict(res, bbox_fields=list(res['bbox_fields'])))
+        fres[key] = {k: r[k] for k in ('clip_global', 'clip_blocks', 'block_bboxes', 'block_labels', 'clip_objects',
+                                       'object_bboxes', 'bbox_fields')}
+    out['load_clip_features'] = fres
 
     torch.save(out, HERE / 'ref_golden.pt')
     size = (HERE / 'ref_golden.pt').stat().st_size

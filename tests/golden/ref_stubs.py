@@ -129,6 +129,13 @@ class _BBoxes:
         wh = self.wh
         return (wh[:, 0] >= min_wh[0]) & (wh[:, 1] >= min_wh[1])
 
+    def __and__(self, other: '_BBoxes') -> torch.Tensor:
+        """Pairwise intersection areas (n, m) -- todd ``BBoxes.intersections`` (datasets.py:192-195)."""
+        lt = torch.maximum(self.lt[:, None], other.lt[None])
+        rb = torch.minimum(self.rb[:, None], other.rb[None])
+        wh = (rb - lt).clamp_min(0)
+        return wh[..., 0] * wh[..., 1]
+
 
 class _BBoxesXYXY(_BBoxes):
 
@@ -282,6 +289,21 @@ def _make_todd() -> types.ModuleType:
         pass
 
     todd.losses.LossRegistry = LossRegistry
+
+    todd.datasets = types.ModuleType('todd.datasets')
+
+    class AccessLayerRegistry:
+        """``ALR.build(config, default)``: the fixture generator registers in-memory mappings under
+        the ``task_name`` the merged config names (PthAccessLayer contract: Mapping[key] -> value)."""
+        stores = {}
+
+        @classmethod
+        def build(cls, config, default):
+            cfg = dict(default)
+            cfg.update(config)
+            return cls.stores[cfg['task_name']]
+
+    todd.datasets.AccessLayerRegistry = AccessLayerRegistry
     return todd
 
 
@@ -448,6 +470,7 @@ def install() -> None:
     sys.modules['todd.utils'] = todd.utils
     sys.modules['todd.base'] = todd.base
     sys.modules['todd.losses'] = todd.losses
+    sys.modules['todd.datasets'] = todd.datasets
     clip = types.ModuleType('clip')
     clip.model = types.ModuleType('clip.model')
     for k in (CLIP, VisionTransformer, Transformer, ResidualAttentionBlock, LayerNorm, QuickGELU):
@@ -459,3 +482,15 @@ def install() -> None:
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules['mmdet.models.utils.builder'].LINEAR_LAYERS = _MMRegistry()
     sys.modules['mmcv.runner'].force_fp32 = _force_fp32
+    # mmdet.datasets / lvis: only names that oadp/dp/datasets.py imports at module level
+    md = types.ModuleType('mmdet.datasets')
+    md.DATASETS, md.PIPELINES = _MMRegistry(), _MMRegistry()
+    for cname in ('CocoDataset', 'CustomDataset', 'LVISV1Dataset'):
+        setattr(md, cname, type(cname, (), {}))
+    sys.modules['mmdet.datasets'] = md
+    aw = types.ModuleType('mmdet.datasets.api_wrappers')
+    aw.COCO, aw.COCOeval = type('COCO', (), {}), type('COCOeval', (), {})
+    sys.modules['mmdet.datasets.api_wrappers'] = aw
+    lv = types.ModuleType('lvis')
+    lv.LVIS = type('LVIS', (), {})
+    sys.modules['lvis'] = lv

@@ -151,3 +151,39 @@ def test_load_clip_features(tmp_path, layer):
             assert np.array_equal(got[name], want[name])
         assert got['clip_objects'].shape[0] == v['objects']['embeddings'].shape[0] - 1
         assert not got['block_labels'][:, 65:].any() if got['block_labels'].shape[1] > 65 else True
+
+
+@pytest.mark.parametrize('layer', ['PthAccessLayer', 'PackedStore'])
+def test_load_clip_features_vs_reference_class(tmp_path, layer):
+    """oadp_b200.store.LoadCLIPFeatures against the reference's own `LoadCLIPFeatures.__call__`
+    (oadp/dp/datasets.py:171-214, executed on stubs by tests/golden/make_ref_golden.py): every result
+    key, dtype and value, for both storage layouts."""
+    import pathlib
+    import sys
+    sys.path.insert(0, str(pathlib.Path(__file__).parent / 'golden'))
+    import make_ref_golden as mk
+    ref = torch.load(pathlib.Path(__file__).parent / 'golden' / 'ref_golden.pt', weights_only=False)['load_clip_features']
+    records, results = mk.feature_store_inputs()
+    for task in ('globals', 'blocks', 'objects'):
+        name = f'coco/oake/{task}/train'
+        if layer == 'PackedStore':
+            with store.PackedWriter(str(tmp_path), name) as w:
+                for k, v in records.items():
+                    w.add(k, v[task])
+        else:
+            s = store.PthStore(str(tmp_path), name)
+            for k, v in records.items():
+                s[k] = v[task]
+    step = store.LoadCLIPFeatures(dict(type=layer, data_root=str(tmp_path)),
+                                  globals_=dict(task_name='coco/oake/globals/train'),
+                                  blocks=dict(task_name='coco/oake/blocks/train'),
+                                  objects=dict(task_name='coco/oake/objects/train'), num_all=6)
+    for key, res in results.items():
+        got = step(dict(res, bbox_fields=list(res['bbox_fields'])))
+        want = ref[key]
+        assert got['bbox_fields'] == want['bbox_fields']
+        for name in ('clip_global', 'clip_blocks', 'clip_objects'):
+            assert got[name].dtype == want[name].dtype and torch.equal(got[name], want[name]), name
+        for name in ('block_bboxes', 'block_labels', 'object_bboxes'):
+            assert got[name].dtype == want[name].dtype and np.array_equal(got[name], want[name]), name
+        assert not got['block_labels'].all() and got['block_labels'].any()
