@@ -217,29 +217,32 @@ class BaseValidator(ABC, Generic[T]):
             for item, result in zip(batch_, ticket.result()):
                 pending.append(self._writer.submit(self._write, result, item))
 
-        for batch in itertools.chain(self._batches(indices), [None]):
-            nxt = (batch, self._submit(batch)) if batch is not None else None
-            if in_flight is not None:
-                drain(in_flight)
-            in_flight = nxt
-            if batch is None:
-                break
-            done += len(batch)
-            if done % max(self._log_interval, 1) < len(batch):
-                dt = time.perf_counter() - t0
-                print(f'[{self._name}] {done}/{len(indices)} images, {done / dt:.1f} img/s', flush=True)
-            still = []
+        try:
+            for batch in itertools.chain(self._batches(indices), [None]):
+                nxt = (batch, self._submit(batch)) if batch is not None else None
+                if in_flight is not None:
+                    drain(in_flight)
+                in_flight = nxt
+                if batch is None:
+                    break
+                done += len(batch)
+                if done % max(self._log_interval, 1) < len(batch):
+                    dt = time.perf_counter() - t0
+                    print(f'[{self._name}] {done}/{len(indices)} images, {done / dt:.1f} img/s', flush=True)
+                still = []
+                for f in pending:
+                    if f.done():
+                        f.result()  # surface write errors
+                    else:
+                        still.append(f)
+                pending = still
             for f in pending:
-                if f.done():
-                    f.result()  # surface write errors
-                else:
-                    still.append(f)
-            pending = still
-        for f in pending:
-            f.result()
-        self._writer.shutdown(wait=True)
-        if self._packed is not None:
-            self._packed.close()
+                f.result()
+        finally:
+            # whatever was encoded is published even if the run dies: the shard index is written last
+            self._writer.shutdown(wait=True)
+            if self._packed is not None:
+                self._packed.close()
         return done
 
     @classmethod
