@@ -195,6 +195,68 @@ int oake_asymmetric_loss(const float* x, const uint8_t* y, long long n, float ga
                          float clip, float eps, float scale, float* loss, float* grad, void* ws, size_t ws_bytes,
                          void* stream);
 
+/* ---- GPU JPEG decode (the step in front of the resize: oadp/oake/base.py:53,
+ * `PIL.Image.open(...).convert('RGB')`) -----------------------------------------------------------
+ * Baseline / extended-sequential 8-bit Huffman JPEG, one interleaved scan, grayscale or YCbCr with
+ * 4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling -> uint8 HWC RGB, bit-identical to what Pillow
+ * (libjpeg-turbo: islow IDCT, "fancy" triangle chroma upsampling, 16-bit fixed-point YCbCr->RGB)
+ * returns for the same file.  The host parses the headers into a descriptor (oake_jpeg_parse, no
+ * GPU needed); the whole file travels to the GPU as is and the entropy decode, the IDCT and the
+ * colour conversion run there (oake_jpeg_decode).  Files outside that envelope (progressive,
+ * arithmetic, CMYK, 12-bit, other sampling, multi-scan) make oake_jpeg_parse return
+ * OAKE_JPEG_UNSUPPORTED; the caller then decodes that file with Pillow, as the reference does. */
+#define OAKE_JPEG_UNSUPPORTED 2
+
+typedef struct {
+  uint16_t look[512];  /* 9-bit prefix -> (code length << 8) | symbol; 0 = code longer than 9 bits */
+  int32_t maxcode[18]; /* largest code of each length 1..16 (-1 = none); [17] = sentinel */
+  int32_t valoff[17];  /* symbol index = code + valoff[length] */
+  uint8_t huffval[256];
+} oake_jpeg_huff;
+
+typedef struct {
+  uint32_t h, v;               /* sampling factors as used (1,1 for a single-component scan) */
+  uint32_t blocks_w, blocks_h; /* 8x8 blocks stored per row / column (padded to whole MCUs) */
+  uint32_t width, height;      /* real samples of the component (libjpeg downsampled_width / _height) */
+  uint32_t dc_tbl, ac_tbl, quant, _pad;
+  uint64_t coef_off;  /* int16 coefficients, [block][64] in zig-zag (file) order: BYTE offset into scratch */
+  uint64_t plane_off; /* uint8 samples after the IDCT, row pitch blocks_w * 8: byte offset into scratch */
+} oake_jpeg_comp;
+
+typedef struct {
+  uint32_t width, height;
+  uint32_t ncomp; /* 1 (grayscale) or 3 (YCbCr) */
+  uint32_t hmax, vmax;
+  uint32_t mcus_x, mcus_y;
+  uint32_t restart_interval; /* MCUs, 0 = none */
+  uint32_t total_blocks;     /* over all components */
+  uint32_t _pad;
+  uint64_t scan_off;      /* entropy-coded bytes: byte offset into the `bytes` arena ... */
+  uint64_t scan_len;      /* ... and how many there are up to the end of the file */
+  uint64_t out_off;       /* RGB HWC output (width * height * 3 bytes): byte offset into `out` */
+  uint64_t scratch_bytes; /* coefficients + planes of this image */
+  oake_jpeg_comp comp[3];
+  uint16_t quant[4][64]; /* natural (row-major) order */
+  oake_jpeg_huff dc[2], ac[2];
+} oake_jpeg_desc;
+
+size_t oake_jpeg_desc_bytes(void); /* sizeof(oake_jpeg_desc), for bindings that keep it opaque */
+/* HOST call, no GPU: parses `data` (one whole JPEG file, host memory).  Offsets in `desc` are
+ * relative (scan_off to the start of the file, coef/plane offsets to this image's scratch, out_off
+ * 0) until oake_jpeg_place.  Returns 0, OAKE_JPEG_UNSUPPORTED (desc->width / height still valid
+ * when the frame header was reached), or 1 = malformed (message in oake_last_error). */
+int oake_jpeg_parse(const uint8_t* data, size_t len, oake_jpeg_desc* desc);
+/* HOST call: rebases a parsed descriptor onto arena offsets chosen by the caller; *scratch_off is
+ * advanced by the image's (256-byte aligned) scratch size. */
+int oake_jpeg_place(oake_jpeg_desc* desc, uint64_t file_off, uint64_t out_off, uint64_t* scratch_off);
+/* Decodes n images.  descs_host / descs_dev: the same n placed descriptors in host memory (read
+ * during the call, for grid sizes) and in device memory; bytes: device arena holding the files;
+ * scratch: device, >= the final *scratch_off of oake_jpeg_place; out: device arena the RGB pixels
+ * go to (the `src_arena` of oake_resize_u8); status: device int32[n], 0 = ok, non-zero = the
+ * entropy-coded data of that image was damaged or truncated (its pixels are then undefined). */
+int oake_jpeg_decode(const uint8_t* bytes, const oake_jpeg_desc* descs_host, const oake_jpeg_desc* descs_dev, int n,
+                     void* scratch, uint8_t* out, int32_t* status, void* stream);
+
 /* Error string of the last failing call on this thread ("" if none). */
 const char* oake_last_error(void);
 /* "f16" or "bf16": element type of `act` tensors. */

@@ -39,7 +39,7 @@ def sources() -> list[pathlib.Path]:
 
 def _digest(extra_flags: list[str]) -> str:
     h = hashlib.sha256()
-    for f in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(INCLUDE.glob('*.h'))):
+    for f in sorted(list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.h')) + list(INCLUDE.glob('*.h'))):
         h.update(f.name.encode())
         h.update(f.read_bytes())
     h.update(' '.join(NVCC_FLAGS + extra_flags).encode())

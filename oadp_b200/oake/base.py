@@ -14,6 +14,9 @@ Changed on purpose (B200-first):
   * files are written by a small thread pool while the GPU works on the next batch
   * `--override .store:packed` writes one packed shard per rank (`oadp_b200.store.PackedStore`,
     SURVEY 8f-1) instead of one pickle per image; resume then skips the keys already in a shard
+  * `--override .decode:gpu` hands the compressed JPEG files to the pipeline, which
+    decodes them on the GPU bit-identically to Pillow (`oadp_b200.jpeg`); the default `pillow` decodes
+    on host threads as the reference's DataLoader workers do
 """
 from __future__ import annotations
 
@@ -30,6 +33,7 @@ import numpy as np
 import torch
 
 from .. import dist as oake_dist
+from .. import jpeg as oake_jpeg
 from ..compat import CocoImages, Config, DictAction, Store
 from ..model import OakeModel
 from ..pipeline import OakePipeline
@@ -39,7 +43,7 @@ from ..store import PackedStore, PackedWriter, key_of
 class Item(NamedTuple):
     id_: int
     output: pathlib.Path
-    image: np.ndarray  # uint8 HWC RGB
+    image: Any  # uint8 HWC RGB array, or the still-compressed file (`jpeg.JpegSource`) with decode='gpu'
     extra: Any = None
 
 
@@ -51,6 +55,7 @@ class BaseDataset(CocoImages, ABC, Generic[T]):
     def __init__(self, *args, auto_fix: bool = False, output_dir: str, **kwargs) -> None:
         super().__init__(*args, **kwargs)
         self._auto_fix = auto_fix
+        self.gpu_decode = False  # set by the validator (`decode='gpu'`)
         self._output_dir = pathlib.Path(output_dir)
         self._output_dir.mkdir(parents=True, exist_ok=True)
 
@@ -80,7 +85,10 @@ class BaseDataset(CocoImages, ABC, Generic[T]):
         id_ = self.ids[index]
         if self.is_done(id_):
             return None
-        image = np.asarray(self._load_image(id_), dtype=np.uint8)
+        if self.gpu_decode:
+            image = oake_jpeg.load(self.image_path(id_))
+        else:
+            image = np.asarray(self._load_image(id_), dtype=np.uint8)
         return Item(id_, self.output_path(id_), image, self._extra(id_))
 
     def _extra(self, id_: int) -> Any:
@@ -122,13 +130,16 @@ class BaseValidator(ABC, Generic[T]):
     DATASET = BaseDataset
 
     def __init__(self, name: str, model: OakeModel, *, dataloader: Config, log: Optional[Config] = None,
-                 batch_images: int = 8, store: str = 'pth', **_: Any) -> None:
+                 batch_images: int = 8, store: str = 'pth', decode: str = 'pillow', **_: Any) -> None:
         self._name = name
         self._model = model
         self._pipeline = OakePipeline(model.engine)
         self._log_interval = int((log or {}).get('interval', 50))
         self._batch_images = 1 if Store.DRY_RUN else int(batch_images)
         self._dataset = self._build_dataset(Config(dataloader.dataset))
+        if decode not in ('pillow', 'gpu'):
+            raise ValueError(f"decode must be 'pillow' or 'gpu', not {decode!r}")
+        self._dataset.gpu_decode = decode == 'gpu'
         if store not in ('pth', 'packed'):
             raise ValueError(f"store must be 'pth' or 'packed', not {store!r}")
         self._packed: Optional[PackedWriter] = None

@@ -2,7 +2,9 @@
 
 This is the public API the `oadp.oake.*` validators and `bench.py` call.  Per batch of images it
   1. copies the raw uint8 images and a few KB of job descriptors to the GPU (one pinned staging
-     buffer each, async H2D),
+     buffer each, async H2D); an image may also arrive as a still-compressed `jpeg.JpegSource`, in
+     which case the file travels instead and `oake_jpeg_decode` produces the pixels on the GPU, on a
+     side stream, while the previous batch is still in the tower,
   2. runs the Pillow-exact resize kernel for every crop / pyramid level (`oake_resize_u8`),
   3. runs the tower on the uint8 crops in SM-friendly chunks (`oake_encode_crops_u8`),
   4. copies the fp16 embeddings back.
@@ -20,6 +22,7 @@ import numpy as np
 import torch
 
 from . import binding, frontend
+from . import jpeg as oake_jpeg
 from .model import OUT_DIM, OakeEngine
 
 CROP_BYTES = frontend.SIZE * frontend.SIZE * 3
@@ -37,13 +40,16 @@ class _Staging:
         self.host: Optional[torch.Tensor] = None
         self.dev: Optional[torch.Tensor] = None
 
-    def reserve(self, host_bytes: int, dev_bytes: Optional[int] = None) -> None:
+    def reserve(self, host_bytes: int, dev_bytes: Optional[int] = None) -> bool:
+        """-> True when the device buffer was (re)allocated by this call."""
         dev_bytes = host_bytes if dev_bytes is None else dev_bytes
         if self.host is None or self.host.numel() < host_bytes:
             self.host = torch.empty(max(host_bytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
         if self.dev is None or self.dev.numel() < dev_bytes:
             self.dev = None
             self.dev = torch.empty(max(dev_bytes, 1 << 20), dtype=torch.uint8, device=self.device)
+            return True
+        return False
 
     def upload(self, nbytes: int) -> None:
         self.dev[:nbytes].copy_(self.host[:nbytes], non_blocking=True)
@@ -55,6 +61,12 @@ class _Slot:
     def __init__(self, device: torch.device) -> None:
         self.arena = _Staging(device)  # images | pyramid levels | resized crops
         self.meta = _Staging(device)  # resize jobs | crop descriptors | fg | box
+        self.jpeg = _Staging(device)  # descriptors | compressed files (host + device)
+        self.jpeg_scratch = _Staging(device)  # coefficients | component planes (device only)
+        self.jpeg_status: Optional[torch.Tensor] = None  # int32 per compressed image
+        self.jpeg_status_host: Optional[torch.Tensor] = None
+        self.jpeg_count = 0
+        self.jpeg_done = torch.cuda.Event()
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.out_host: Optional[torch.Tensor] = None
@@ -76,6 +88,11 @@ class Pending:
             if int(self._slot.err_host.item()) != 0:
                 self._slot.err.zero_()
                 raise binding.OakeError('oake_resize_u8: a crop exceeded the resize kernel limits')
+            if self._slot.jpeg_count:
+                bad = self._slot.jpeg_status_host[:self._slot.jpeg_count].nonzero().flatten().tolist()
+                if bad:
+                    raise binding.OakeError(f'oake_jpeg_decode: damaged or truncated entropy-coded data in '
+                                            f'compressed image(s) {bad} of the batch')
             self._done = self._finish(self._host.clone())
         return self._done
 
@@ -94,11 +111,13 @@ class OakePipeline:
         self.frontend_launches = 0  # resize / mask kernels launched so far
         self.profile_frontend = False  # bench roofline pass: CUDA events around the resize / mask kernels
         self.frontend_events = []  # (name, start, stop)
+        self._decode_stream = torch.cuda.Stream(self.device)  # JPEG decode of batch k+1 beside the tower of batch k
 
     # the slot being filled
     _arena = property(lambda self: self._slots[self._cur].arena)
     _meta = property(lambda self: self._slots[self._cur].meta)
     _err = property(lambda self: self._slots[self._cur].err)
+    _slot = property(lambda self: self._slots[self._cur])
 
     # ------------------------------------------------------------------------------ internals
     def _stream(self) -> int:
@@ -108,7 +127,7 @@ class OakePipeline:
         offs, off = [], 0
         for im in images:
             if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
-                raise ValueError('images must be uint8 HWC RGB arrays')
+                raise ValueError('images must be uint8 HWC RGB arrays (or jpeg.JpegSource)')
             offs.append(off)
             off += _align(im.shape[0] * im.shape[1] * 3)
         return offs, off
@@ -132,6 +151,10 @@ class OakePipeline:
         slot.event.record(torch.cuda.current_stream(self.device))
         slot.busy = True
         self.d2h_bytes = n * OUT_DIM * 2 + 4
+        if slot.jpeg_count:
+            slot.jpeg_status_host[:slot.jpeg_count].copy_(slot.jpeg_status[:slot.jpeg_count], non_blocking=True)
+            slot.event.record(torch.cuda.current_stream(self.device))
+            self.d2h_bytes += 4 * slot.jpeg_count
         return Pending(self, slot, host, finish)
 
     def _run(self, *plan_args) -> torch.Tensor:
@@ -162,21 +185,73 @@ class OakePipeline:
         meta_host_bytes = off
         meta_dev_bytes = off + (n * 196 * 4 if variant == binding.VARIANT_T197 else 0)
         self._meta.reserve(meta_host_bytes, meta_dev_bytes)
-        self._arena.reserve(img_bytes, arena_bytes)
+        fresh = self._arena.reserve(img_bytes, arena_bytes)
         mh = self._meta.host.numpy()
         for o, b in parts:
             mh[o:o + b.size] = b
         ah = self._arena.host.numpy()
+        compressed = []
         for im, o in zip(images, img_offs):
-            ah[o:o + im.size] = im.reshape(-1)
-        return dict(n=n, variant=variant, img_bytes=img_bytes, meta_host_bytes=meta_host_bytes,
+            if isinstance(im, oake_jpeg.JpegSource):
+                compressed.append((im, o))
+            else:
+                ah[o:o + im.size] = im.reshape(-1)
+        jpeg_job = self._stage_jpeg(compressed, fresh) if compressed else None
+        self._slot.jpeg_count = len(compressed)
+        return dict(n=n, variant=variant, img_bytes=img_bytes, meta_host_bytes=meta_host_bytes, jpeg=jpeg_job,
+                    raw_images=len(images) - len(compressed),
                     stages=[(j.size, frontend.max_tiles(j), o) for j, o in zip(stages, stage_offs)],
                     crops_off=crops_off, fg_off=fg_off, box_off=box_off, masks_off=masks_off)
 
+    def _stage_jpeg(self, compressed, fresh: bool) -> dict:
+        """Host only: descriptors (rebased onto this slot's arenas) and files into pinned memory."""
+        slot, lib = self._slot, self.lib
+        n, db = len(compressed), oake_jpeg.desc_bytes()
+        files_off = _align(n * db)
+        total = files_off + sum(_align(len(src.data), 16) for src, _ in compressed)
+        fresh |= slot.jpeg.reserve(total)
+        host = slot.jpeg.host.numpy()
+        base = slot.jpeg.host.data_ptr()
+        off = files_off
+        scratch = C.c_uint64(0)
+        for i, (src, out_off) in enumerate(compressed):
+            host[i * db:(i + 1) * db] = np.frombuffer(src.desc, dtype=np.uint8)
+            host[off:off + len(src.data)] = np.frombuffer(src.data, dtype=np.uint8)
+            binding.check(lib.oake_jpeg_place(base + i * db, off, out_off, C.byref(scratch)))
+            off += _align(len(src.data), 16)
+        fresh |= slot.jpeg_scratch.reserve(0, int(scratch.value))
+        if slot.jpeg_status is None or slot.jpeg_status.numel() < n:
+            slot.jpeg_status = torch.zeros(max(n, 256), dtype=torch.int32, device=self.device)
+            slot.jpeg_status_host = torch.zeros(max(n, 256), dtype=torch.int32).pin_memory()
+            fresh = True
+        return dict(n=n, bytes=total, fresh=fresh)
+
     def upload(self, job: dict) -> None:
-        self._arena.upload(job['img_bytes'])
-        self._meta.upload(job['meta_host_bytes'])
-        self.h2d_bytes = job['img_bytes'] + job['meta_host_bytes']
+        self.h2d_bytes = job['meta_host_bytes']
+        if job['raw_images']:  # (a batch of compressed files only has nothing to send here)
+            self._arena.upload(job['img_bytes'])
+            self.h2d_bytes += job['img_bytes']
+        if job['meta_host_bytes']:
+            self._meta.upload(job['meta_host_bytes'])
+        jj = job['jpeg']
+        if jj is not None:
+            # Side stream: the files go up and are decoded while the main stream is still busy with the
+            # previous batch.  The slot's buffers are idle by now (`_submit` waited for its last batch);
+            # only memory the caching allocator handed out just now may still be in use by work queued
+            # on the main stream, so a fresh allocation makes the side stream wait for that work once.
+            slot, main = self._slot, torch.cuda.current_stream(self.device)
+            if jj['fresh']:
+                self._decode_stream.wait_stream(main)
+            with torch.cuda.stream(self._decode_stream):
+                slot.jpeg.upload(jj['bytes'])
+                binding.check(self.lib.oake_jpeg_decode(
+                    slot.jpeg.dev.data_ptr(), slot.jpeg.host.data_ptr(), slot.jpeg.dev.data_ptr(), jj['n'],
+                    slot.jpeg_scratch.dev.data_ptr(), slot.arena.dev.data_ptr(), slot.jpeg_status.data_ptr(),
+                    self._decode_stream.cuda_stream))
+                slot.jpeg_done.record(self._decode_stream)
+            main.wait_event(slot.jpeg_done)
+            self.h2d_bytes += jj['bytes']
+            self.frontend_launches += 3
 
     def launch(self, job: dict) -> torch.Tensor:
         """Device only: resize stages, masks, tower.  Returns the DEVICE fp16 (n, 512) tensor."""
@@ -338,6 +413,24 @@ class OakePipeline:
         box = np.concatenate([p.expanded for p in plans]) if plans else np.zeros((0, 4), np.float32)
         return (images, offs, img_bytes, img_bytes + total * CROP_BYTES, [jobs], crops, binding.VARIANT_T197, fg,
                 box), plans
+
+    def decode_jpegs(self, sources: Sequence['oake_jpeg.JpegSource']) -> List[np.ndarray]:
+        """Runs only the JPEG decode; returns the uint8 HWC pixels of each file (tests, tools)."""
+        offs, img_bytes = self._place_images(sources)
+        self._cur ^= 1
+        slot = self._slot
+        if slot.busy:
+            slot.event.synchronize()
+        fresh = slot.arena.reserve(1, img_bytes)
+        jj = self._stage_jpeg(list(zip(sources, offs)), fresh)
+        slot.jpeg_count = 0
+        self.upload(dict(meta_host_bytes=0, raw_images=0, img_bytes=img_bytes, jpeg=jj))
+        torch.cuda.synchronize(self.device)
+        status = slot.jpeg_status[:len(sources)].cpu()
+        if bool(status.any()):
+            raise binding.OakeError(f'oake_jpeg_decode: damaged data in {status.nonzero().flatten().tolist()}')
+        arena = slot.arena.dev
+        return [arena[o:o + s.size].cpu().numpy().reshape(s.shape) for s, o in zip(sources, offs)]
 
     # --------------------------------------------------------------- test hooks (uint8 crops)
     def debug_crops_u8(self, images: Sequence[np.ndarray], jobs: np.ndarray) -> np.ndarray:

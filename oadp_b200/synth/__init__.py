@@ -107,9 +107,10 @@ def visual_params(seed: int = 0, layers: int = 12) -> Dict[str, 'np.ndarray']:
 
 
 def write_coco_dataset(root, n_images: int, seed: int = 0, n_proposals: int = 40, sizes=COCO_SIZES,
-                       first_id: int = 101) -> dict:
-    """Materialises a tiny COCO-format dataset (lossless PNG images, instances json, proposal pickle
-    in image-id order) plus an OAKE config for each task.  Returns the paths."""
+                       first_id: int = 101, fmt: str = 'png') -> dict:
+    """Materialises a tiny COCO-format dataset (lossless PNG images -- or, with fmt='jpg', JPEG files
+    of mixed quality / chroma sampling as COCO's are --, instances json, proposal pickle in image-id
+    order) plus an OAKE config for each task.  Returns the paths."""
     import json
     import pathlib
     import pickle
@@ -122,8 +123,11 @@ def write_coco_dataset(root, n_images: int, seed: int = 0, n_proposals: int = 40
         w, h = sizes[i % len(sizes)]
         id_ = first_id + 7 * i
         arr = image(w, h, seed * 100003 + i)
-        name = f'{id_:012d}.png'
-        PIL.Image.fromarray(arr).save(root / 'images' / name)
+        name = f'{id_:012d}.{fmt}'
+        if fmt == 'jpg':
+            PIL.Image.fromarray(arr).save(root / 'images' / name, quality=(95, 85, 75)[i % 3], subsampling=(2, 0, 1)[i % 3])
+        else:
+            PIL.Image.fromarray(arr).save(root / 'images' / name)
         infos.append(dict(id=id_, file_name=name, width=w, height=h))
         props.append(proposals(w, h, n_proposals, seed=seed * 7919 + i))
     ann = root / 'instances.json'
