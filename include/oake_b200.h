@@ -201,8 +201,9 @@ int oake_asymmetric_loss(const float* x, const uint8_t* y, long long n, float ga
  * 4:4:4, 4:2:2 (2x1) or 4:2:0 (2x2) sampling -> uint8 HWC RGB, bit-identical to what Pillow
  * (libjpeg-turbo: islow IDCT, "fancy" triangle chroma upsampling, 16-bit fixed-point YCbCr->RGB)
  * returns for the same file.  The host parses the headers into a descriptor (oake_jpeg_parse, no
- * GPU needed); the whole file travels to the GPU as is and the entropy decode, the IDCT and the
- * colour conversion run there (oake_jpeg_decode).  Files outside that envelope (progressive,
+ * GPU needed) and copies the entropy-coded segment, minus its stuffing bytes, into the staging
+ * buffer (oake_jpeg_stage); the entropy decode, the IDCT and the colour conversion run on the GPU
+ * (oake_jpeg_decode).  Files outside that envelope (progressive,
  * arithmetic, CMYK, 12-bit, other sampling, multi-scan) make oake_jpeg_parse return
  * OAKE_JPEG_UNSUPPORTED; the caller then decodes that file with Pillow, as the reference does. */
 #define OAKE_JPEG_UNSUPPORTED 2
@@ -230,11 +231,12 @@ typedef struct {
   uint32_t mcus_x, mcus_y;
   uint32_t restart_interval; /* MCUs, 0 = none */
   uint32_t total_blocks;     /* over all components */
-  uint32_t _pad;
+  uint32_t sync_slots;       /* capacity of the subsequence table at sync_off (parallel entropy decode) */
   uint64_t scan_off;      /* entropy-coded bytes: byte offset into the `bytes` arena ... */
   uint64_t scan_len;      /* ... and how many there are up to the end of the file */
   uint64_t out_off;       /* RGB HWC output (width * height * 3 bytes): byte offset into `out` */
-  uint64_t scratch_bytes; /* coefficients + planes of this image */
+  uint64_t scratch_bytes; /* coefficients + planes + subsequence table of this image */
+  uint64_t sync_off;      /* subsequence table, 24 bytes per slot: byte offset into scratch */
   oake_jpeg_comp comp[3];
   uint16_t quant[4][64]; /* natural (row-major) order */
   oake_jpeg_huff dc[2], ac[2];
@@ -243,15 +245,22 @@ typedef struct {
 size_t oake_jpeg_desc_bytes(void); /* sizeof(oake_jpeg_desc), for bindings that keep it opaque */
 /* HOST call, no GPU: parses `data` (one whole JPEG file, host memory).  Offsets in `desc` are
  * relative (scan_off to the start of the file, coef/plane offsets to this image's scratch, out_off
- * 0) until oake_jpeg_place.  Returns 0, OAKE_JPEG_UNSUPPORTED (desc->width / height still valid
+ * 0) until oake_jpeg_stage.  Returns 0, OAKE_JPEG_UNSUPPORTED (desc->width / height still valid
  * when the frame header was reached), or 1 = malformed (message in oake_last_error). */
 int oake_jpeg_parse(const uint8_t* data, size_t len, oake_jpeg_desc* desc);
-/* HOST call: rebases a parsed descriptor onto arena offsets chosen by the caller; *scratch_off is
- * advanced by the image's (256-byte aligned) scratch size. */
-int oake_jpeg_place(oake_jpeg_desc* desc, uint64_t file_off, uint64_t out_off, uint64_t* scratch_off);
-/* Decodes n images.  descs_host / descs_dev: the same n placed descriptors in host memory (read
- * during the call, for grid sizes) and in device memory; bytes: device arena holding the files;
- * scratch: device, >= the final *scratch_off of oake_jpeg_place; out: device arena the RGB pixels
+/* HOST calls: oake_jpeg_stage copies the entropy-coded segment of `file` (the `len` bytes that were
+ * parsed into `parsed`) to `dst` -- normally pinned memory -- without the 0x00 bytes the format stuffs
+ * after every 0xFF, cut at the end-of-image marker and zero-padded to a multiple of 4 plus 16 bytes;
+ * at most oake_jpeg_stream_bound(parsed) bytes, the count is returned in *written.  `placed` receives
+ * the descriptor rebased onto the caller's arenas: scan_off = stream_off (the offset `dst` will have
+ * in the device `bytes` arena, a multiple of 4), out_off, and coefficient / plane offsets moved behind
+ * *scratch_off, which is advanced by the image's (256-byte aligned) scratch size. */
+size_t oake_jpeg_stream_bound(const oake_jpeg_desc* parsed);
+int oake_jpeg_stage(const oake_jpeg_desc* parsed, const uint8_t* file, size_t len, uint8_t* dst, uint64_t stream_off,
+                    uint64_t out_off, uint64_t* scratch_off, oake_jpeg_desc* placed, uint64_t* written);
+/* Decodes n images.  descs_host / descs_dev: the same n staged descriptors in host memory (read
+ * during the call, for grid sizes) and in device memory; bytes: device copy of the staged streams;
+ * scratch: device, >= the final *scratch_off of oake_jpeg_stage; out: device arena the RGB pixels
  * go to (the `src_arena` of oake_resize_u8); status: device int32[n], 0 = ok, non-zero = the
  * entropy-coded data of that image was damaged or truncated (its pixels are then undefined). */
 int oake_jpeg_decode(const uint8_t* bytes, const oake_jpeg_desc* descs_host, const oake_jpeg_desc* descs_dev, int n,

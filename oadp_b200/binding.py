@@ -64,7 +64,9 @@ SIGNATURES = {
                                        C.c_void_p]),
     'oake_jpeg_desc_bytes': (C.c_size_t, []),
     'oake_jpeg_parse': (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
-    'oake_jpeg_place': (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    'oake_jpeg_stream_bound': (C.c_size_t, [C.c_void_p]),
+    'oake_jpeg_stage': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_uint64,
+                                  C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]),
     'oake_jpeg_decode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     'oake_last_error': (C.c_char_p, []),

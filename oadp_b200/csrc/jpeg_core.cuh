@@ -33,102 +33,98 @@ OAKE_HD constexpr int zigzag_pos(int natural) {
 }
 
 // ------------------------------------------------------------------------------- entropy decode
-// MSB-first bit reader over the entropy-coded segment: removes the 0x00 stuffed after each 0xFF and
-// stops at any marker (from then on it supplies zero bits and counts them as padding).
-struct BitReader {
-  const uint8_t* src;
-  uint64_t pos, end;
-  uint64_t bits;  // the low `n` bits are valid
-  int n;
-  int pad;  // zero bits appended after the data ran out
-
-  OAKE_HD void reset() {
-    bits = 0;
-    n = 0;
-    pad = 0;
-  }
-  OAKE_HD void refill() {  // brings n to >= 57 (so 32 bits can be used between two calls)
-    while (n <= 56) {
-      uint32_t b = 0;
-      if (pos < end) {
-        b = src[pos];
-        if (b != 0xFFu) {
-          ++pos;
-        } else if (pos + 1 < end && src[pos + 1] == 0u) {
-          pos += 2;
-        } else {  // a marker (or a truncated file): stay on it
-          b = 0;
-          pad += 8;
-        }
-      } else {
-        pad += 8;
-      }
-      bits = (bits << 8) | b;
-      n += 8;
-    }
-  }
-  OAKE_HD uint32_t peek16() const { return static_cast<uint32_t>(bits >> (n - 16)) & 0xFFFFu; }
-  OAKE_HD void skip(int k) { n -= k; }
-  OAKE_HD int32_t receive_extend(int s) {  // T.81 F.2.2.1 / F.2.4.3; s in 0..16
-    if (s == 0) return 0;
-    const int32_t v = static_cast<int32_t>((bits >> (n - s)) & ((1u << s) - 1u));
-    n -= s;
-    return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
-  }
-  // true when bits that were never in the file have been consumed
-  OAKE_HD bool overran() const { return n < pad; }
-  // end of a restart interval: drop the bits left in the last byte and step over RSTn
-  OAKE_HD bool restart() {
-    const bool bad = overran();
-    reset();
-    while (pos < end && src[pos] != 0xFFu) ++pos;                      // (nothing to skip in a sound file)
-    while (pos + 1 < end && src[pos] == 0xFFu && src[pos + 1] == 0xFFu) ++pos;  // fill bytes
-    if (pos + 1 < end && src[pos] == 0xFFu && (src[pos + 1] & 0xF8u) == 0xD0u) {
-      pos += 2;
-      return !bad;
-    }
-    return false;
-  }
-};
-
-// One Huffman symbol.  `look`, `maxcode`, `valoff`, `huffval`: the four parts of an oake_jpeg_huff
-// (possibly copied to faster memory).  Returns the symbol; a code that is in no table returns 0 and
-// sets *bad.
-OAKE_HD int decode_symbol(BitReader& br, const uint16_t* look, const int32_t* maxcode, const int32_t* valoff,
-                          const uint8_t* huffval, bool* bad) {
-  const uint32_t c16 = br.peek16();
-  const uint32_t e = look[c16 >> 7];
-  if (e != 0) {
-    br.skip(static_cast<int>(e >> 8));
-    return static_cast<int>(e & 0xFFu);
-  }
-  for (int l = 10; l <= 16; ++l) {
-    const int32_t code = static_cast<int32_t>(c16 >> (16 - l));
-    if (code <= maxcode[l]) {
-      br.skip(l);
-      return huffval[(code + valoff[l]) & 0xFF];
-    }
-  }
-  *bad = true;
-  br.skip(16);
-  return 0;
+// The scan arrives "clean": the host has already dropped the 0x00 stuffed after every 0xFF data byte
+// and cut the segment at the first marker that is not RSTn (jpeg_parse.h, stage()), the stream starts
+// on a 4-byte boundary and is followed by at least 16 zero bytes.  That turns the refill into one
+// aligned 32-bit load per 32 consumed bits, requested one refill ahead of its use -- what matters in a
+// loop that is one long dependency chain run by a single thread.
+OAKE_HD uint32_t load_be32(const uint32_t* p) {
+  const uint32_t w = *p;
+  return (w >> 24) | ((w >> 8) & 0xFF00u) | ((w << 8) & 0xFF0000u) | (w << 24);
 }
 
-struct HuffView {
-  const uint16_t* look;
-  const int32_t* maxcode;
-  const int32_t* valoff;
-  const uint8_t* huffval;
+struct BitReader {
+  const uint32_t* words;
+  uint32_t pos, limit;  // next word to request / first word beyond the zero padding
+  uint64_t buf;         // left-aligned: bit 63 is the next bit of the stream
+  int cnt;              // valid bits in buf
+  uint32_t nxt;         // word `pos - 1`, loaded but not yet in buf
+
+  OAKE_HD uint32_t fetch() { return pos < limit ? load_be32(words + pos++) : (++pos, 0u); }
+  OAKE_HD void start(const uint8_t* stream, uint64_t len) {
+    words = reinterpret_cast<const uint32_t*>(stream);
+    pos = 0;
+    limit = static_cast<uint32_t>((len + 15) / 4);
+    buf = static_cast<uint64_t>(fetch()) << 32;
+    buf |= fetch();
+    cnt = 64;
+    nxt = fetch();
+  }
+  // positions the reader on an arbitrary bit of the stream
+  OAKE_HD void start_at(const uint8_t* stream, uint64_t len, uint32_t bit) {
+    words = reinterpret_cast<const uint32_t*>(stream);
+    pos = bit >> 5;
+    limit = static_cast<uint32_t>((len + 15) / 4);
+    buf = static_cast<uint64_t>(fetch()) << 32;
+    buf |= fetch();
+    cnt = 64;
+    nxt = fetch();
+    skip(static_cast<int>(bit & 31u));
+    refill();
+  }
+  OAKE_HD void refill() {  // afterwards cnt > 32: a code (<= 16 bits) and its value (<= 16 bits) fit
+    if (cnt <= 32) {
+      buf |= static_cast<uint64_t>(nxt) << (32 - cnt);
+      cnt += 32;
+      nxt = fetch();
+    }
+  }
+  OAKE_HD uint32_t top32() const { return static_cast<uint32_t>(buf >> 32); }
+  OAKE_HD void skip(int k) {
+    buf <<= k;
+    cnt -= k;
+  }
+  // bits of the stream consumed so far
+  OAKE_HD uint64_t consumed() const { return static_cast<uint64_t>(pos - 1) * 32 - static_cast<uint64_t>(cnt); }
+  // end of a restart interval: drop the rest of the current byte, expect RSTn
+  OAKE_HD bool restart() {
+    skip(cnt & 7);  // words are whole bytes, so the misalignment of the read position is cnt mod 8
+    refill();
+    const uint32_t m = top32() >> 16;
+    skip(16);
+    refill();
+    return (m & 0xFFF8u) == 0xFFD0u;
+  }
 };
 
-// Entropy-decodes one whole image into zero-initialised coefficient blocks.  `tables[0..1]` = DC,
-// `tables[2..3]` = AC.  Returns 0, or non-zero if the data was damaged / ran out.
-OAKE_HD int decode_scan(const oake_jpeg_desc& d, const uint8_t* bytes, const HuffView* tables, uint8_t* scratch) {
+// One Huffman symbol: returns (code length << 8) | symbol without consuming anything.  A code that is
+// in no table comes back as length 16, symbol 0, and sets *bad.
+OAKE_HD uint32_t peek_symbol(uint32_t top, const oake_jpeg_huff* t, bool* bad) {
+  const uint32_t e = t->look[top >> 23];
+  if (e != 0) return e;
+  const uint32_t c16 = top >> 16;
+  for (int l = 10; l <= 16; ++l) {
+    const int32_t code = static_cast<int32_t>(c16 >> (16 - l));
+    if (code <= t->maxcode[l]) return (static_cast<uint32_t>(l) << 8) | t->huffval[(code + t->valoff[l]) & 0xFF];
+  }
+  *bad = true;
+  return 16u << 8;
+}
+
+// T.81 F.2.2.1 EXTEND of the s (1..16) bits that follow the `len`-bit code at the top of `top`
+OAKE_HD int32_t extend_after(uint32_t top, int len, int s) {
+  const uint32_t t = top << len;
+  const int32_t v = static_cast<int32_t>(t >> (32 - s));
+  // leading bit 0 -> negative: v - (2^s - 1)
+  return v - (static_cast<int32_t>(~t) >> 31 & ((1 << s) - 1));
+}
+
+// Entropy-decodes one whole image into zero-initialised coefficient blocks.  `tables`: the four
+// tables of the descriptor, dc[0], dc[1], ac[0], ac[1] (contiguous there; the kernels copy them to
+// shared memory).  Returns 0, or non-zero if the data was damaged / ran out.
+OAKE_HD int decode_scan(const oake_jpeg_desc& d, const uint8_t* bytes, const oake_jpeg_huff* tables, uint8_t* scratch) {
   BitReader br;
-  br.src = bytes + d.scan_off;
-  br.pos = 0;
-  br.end = d.scan_len;
-  br.reset();
+  br.start(bytes + d.scan_off, d.scan_len);
   bool bad = false;
   int32_t pred[3] = {0, 0, 0};
   const uint32_t n_mcus = d.mcus_x * d.mcus_y;
@@ -142,27 +138,35 @@ OAKE_HD int decode_scan(const oake_jpeg_desc& d, const uint8_t* bytes, const Huf
     }
     for (uint32_t c = 0; c < d.ncomp; ++c) {
       const oake_jpeg_comp& k = d.comp[c];
-      const HuffView dc = tables[k.dc_tbl], ac = tables[2 + k.ac_tbl];
+      const oake_jpeg_huff* dc = tables + k.dc_tbl;
+      const oake_jpeg_huff* ac = tables + 2 + k.ac_tbl;
       int16_t* plane = reinterpret_cast<int16_t*>(scratch + k.coef_off);
       for (uint32_t v = 0; v < k.v; ++v) {
         for (uint32_t h = 0; h < k.h; ++h) {
           int16_t* blk = plane + (static_cast<uint64_t>(my * k.v + v) * k.blocks_w + (mx * k.h + h)) * 64;
           br.refill();
-          const int s = decode_symbol(br, dc.look, dc.maxcode, dc.valoff, dc.huffval, &bad) & 15;
-          pred[c] += br.receive_extend(s);
-          blk[0] = static_cast<int16_t>(pred[c]);
+          {
+            const uint32_t top = br.top32();
+            const uint32_t e = peek_symbol(top, dc, &bad);
+            const int len = static_cast<int>(e >> 8), s = static_cast<int>(e & 15u);
+            if (s != 0) pred[c] += extend_after(top, len, s);
+            br.skip(len + s);
+            blk[0] = static_cast<int16_t>(pred[c]);
+          }
           for (int i = 1; i < 64;) {
             br.refill();
-            const int rs = decode_symbol(br, ac.look, ac.maxcode, ac.valoff, ac.huffval, &bad);
-            const int r = rs >> 4, sz = rs & 15;
-            if (sz == 0) {
+            const uint32_t top = br.top32();
+            const uint32_t e = peek_symbol(top, ac, &bad);
+            const int len = static_cast<int>(e >> 8), r = static_cast<int>((e >> 4) & 15u), s = static_cast<int>(e & 15u);
+            if (s == 0) {
+              br.skip(len);
               if (r != 15) break;  // end of block
               i += 16;
               continue;
             }
             i += r;
-            const int32_t val = br.receive_extend(sz);
-            if (i < 64) blk[i] = static_cast<int16_t>(val);
+            if (i < 64) blk[i] = static_cast<int16_t>(extend_after(top, len, s));
+            br.skip(len + s);
             ++i;
           }
         }
@@ -174,7 +178,130 @@ OAKE_HD int decode_scan(const oake_jpeg_desc& d, const uint8_t* bytes, const Huf
       ++my;
     }
   }
-  return (bad || br.overran()) ? 1 : 0;
+  return (bad || br.consumed() > d.scan_len * 8) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- parallel entropy decode
+// A scan without restart markers has no marked entry points, but Huffman streams re-synchronise: a
+// decoder started on a wrong bit falls into step with the true symbol sequence after a few dozen
+// symbols.  So the stream is cut into subsequences of kSubBits bits, every subsequence gets its own
+// thread, and the threads find their true entry states by iteration (Klein & Wiseman; for JPEG
+// Weissenberger & Schmidt, "Accelerating JPEG decompression on GPUs"):
+//   1. thread i decodes the symbols that START inside [entry_i, (i+1) kSubBits) -- entry_0 is the true
+//      start, the others guess "block boundary at i kSubBits" -- and publishes where it stopped: bit
+//      position, block of the MCU, zig-zag index;
+//   2. repeat: thread i takes the stop state of thread i-1 as its entry; if that differs from the entry
+//      it used, it decodes again.  Entry i is final after at most i rounds (in practice 2-3 in all);
+//   3. the blocks completed per subsequence, prefix-summed, say which block each entry state is in;
+//   4. every thread decodes once more, now writing coefficients (DC as the difference it reads);
+//   5. the DC differences are prefix-summed per component in scan order.
+// decode_subsequence is steps 1, 2 and 4 for one thread; jpeg.cu holds the CTA-level orchestration, the
+// CPU harness the same thing with plain loops.
+constexpr uint32_t kSubBits = 1024;
+
+// which component / block of it each block of an MCU is: one nibble per block of the MCU (<= 6)
+struct McuMap {
+  uint32_t bpm;  // blocks per MCU
+  uint32_t comp4, v4, h4;
+  OAKE_HD uint32_t comp(uint32_t b) const { return (comp4 >> (4 * b)) & 15u; }
+  OAKE_HD uint32_t v(uint32_t b) const { return (v4 >> (4 * b)) & 15u; }
+  OAKE_HD uint32_t h(uint32_t b) const { return (h4 >> (4 * b)) & 15u; }
+};
+
+OAKE_HD McuMap make_mcu_map(const oake_jpeg_desc& d) {
+  McuMap m;
+  m.bpm = m.comp4 = m.v4 = m.h4 = 0;
+  for (uint32_t c = 0; c < d.ncomp; ++c)
+    for (uint32_t v = 0; v < d.comp[c].v; ++v)
+      for (uint32_t h = 0; h < d.comp[c].h; ++h) {
+        m.comp4 |= c << (4 * m.bpm);
+        m.v4 |= v << (4 * m.bpm);
+        m.h4 |= h << (4 * m.bpm);
+        ++m.bpm;
+      }
+  return m;
+}
+
+// decoder state between two symbols: bit position | block of the MCU << 32 | zig-zag index << 40
+OAKE_HD uint64_t pack_state(uint32_t bit, uint32_t b, uint32_t z) {
+  return static_cast<uint64_t>(bit) | (static_cast<uint64_t>(b) << 32) | (static_cast<uint64_t>(z) << 40);
+}
+
+// coefficient block number `B` of the scan (MCU-major, then the MCU's block order)
+OAKE_HD int16_t* scan_block(const oake_jpeg_desc& d, const McuMap& map, uint8_t* scratch, uint32_t B) {
+  const uint32_t mcu = B / map.bpm, kb = B - mcu * map.bpm;
+  const uint32_t my = mcu / d.mcus_x, mx = mcu - my * d.mcus_x;
+  const oake_jpeg_comp& k = d.comp[map.comp(kb)];
+  const uint64_t idx = static_cast<uint64_t>(my * k.v + map.v(kb)) * k.blocks_w + (mx * k.h + map.h(kb));
+  return reinterpret_cast<int16_t*>(scratch + k.coef_off) + idx * 64;
+}
+
+struct SubResult {
+  uint64_t exit;   // state after the last symbol that started inside the subsequence
+  uint32_t count;  // blocks completed
+  bool bad;        // WRITE only: a code outside the tables inside a real block
+};
+
+template <bool WRITE>
+OAKE_HD SubResult decode_subsequence(const oake_jpeg_desc& d, const McuMap& map, const uint8_t* stream,
+                                     const oake_jpeg_huff* tables, uint64_t entry, uint32_t end_bit, uint32_t B,
+                                     uint8_t* scratch) {
+  const uint32_t total_bits = static_cast<uint32_t>(d.scan_len * 8);
+  if (end_bit > total_bits) end_bit = total_bits;
+  uint32_t b = static_cast<uint32_t>(entry >> 32) & 0xFFu, z = static_cast<uint32_t>(entry >> 40) & 0xFFu;
+  BitReader br;
+  br.start_at(stream, d.scan_len, static_cast<uint32_t>(entry));
+  SubResult r;
+  r.count = 0;
+  r.bad = false;
+  bool bad = false;
+  int16_t* blk = nullptr;
+  if (WRITE && B < d.total_blocks) blk = scan_block(d, map, scratch, B);
+  uint32_t bit = static_cast<uint32_t>(entry);
+  // tables of the block being decoded (they change with the block, not with the symbol)
+  const oake_jpeg_huff* dc = tables + d.comp[map.comp(b)].dc_tbl;
+  const oake_jpeg_huff* ac = tables + 2 + d.comp[map.comp(b)].ac_tbl;
+  while (bit < end_bit) {
+    br.refill();
+    const uint32_t top = br.top32();
+    int used;
+    if (z == 0) {
+      const uint32_t e = peek_symbol(top, dc, &bad);
+      const int len = static_cast<int>(e >> 8), s = static_cast<int>(e & 15u);
+      if (WRITE && blk != nullptr) blk[0] = static_cast<int16_t>(s != 0 ? extend_after(top, len, s) : 0);
+      used = len + s;
+      z = 1;
+    } else {
+      const uint32_t e = peek_symbol(top, ac, &bad);
+      const int len = static_cast<int>(e >> 8), run = static_cast<int>((e >> 4) & 15u), s = static_cast<int>(e & 15u);
+      if (s == 0) {
+        used = len;
+        z = run == 15 ? z + 16 : 64;
+      } else {
+        z += static_cast<uint32_t>(run);
+        if (WRITE && blk != nullptr && z < 64) blk[z] = static_cast<int16_t>(extend_after(top, len, s));
+        used = len + s;
+        ++z;
+      }
+    }
+    br.skip(used);
+    bit += static_cast<uint32_t>(used);
+    if (WRITE && blk != nullptr && bad) r.bad = true;
+    bad = false;
+    if (z >= 64) {
+      z = 0;
+      b = b + 1 == map.bpm ? 0 : b + 1;
+      dc = tables + d.comp[map.comp(b)].dc_tbl;
+      ac = tables + 2 + d.comp[map.comp(b)].ac_tbl;
+      ++r.count;
+      if (WRITE) {
+        ++B;
+        blk = B < d.total_blocks ? scan_block(d, map, scratch, B) : nullptr;
+      }
+    }
+  }
+  r.exit = pack_state(bit, b, z);
+  return r;
 }
 
 // ----------------------------------------------------------------------------------------- IDCT

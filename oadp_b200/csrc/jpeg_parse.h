@@ -210,22 +210,68 @@ inline int parse(const uint8_t* p, size_t len, oake_jpeg_desc* d, std::string* w
     k.plane_off = off;
     off = align256(off + static_cast<uint64_t>(k.blocks_w) * k.blocks_h * 64);
   }
-  d->scratch_bytes = off;
   d->scan_off = pos;
   d->scan_len = len - pos;
+  // one slot per 1024 bits of entropy-coded data (jpeg_core.cuh kSubBits): entry state, exit state,
+  // block count, first block -- 24 bytes
+  d->sync_slots = static_cast<uint32_t>((d->scan_len * 8 + 1023) / 1024 + 1);
+  d->sync_off = off;
+  off = align256(off + static_cast<uint64_t>(d->sync_slots) * 24);
+  d->scratch_bytes = off;
   d->out_off = 0;
   return kOk;
 }
 
-inline void place(oake_jpeg_desc* d, uint64_t file_off, uint64_t out_off, uint64_t* scratch_off) {
-  const uint64_t base = align256(*scratch_off);
-  for (uint32_t c = 0; c < d->ncomp; ++c) {
-    d->comp[c].coef_off += base;
-    d->comp[c].plane_off += base;
+// Upper bound of what stage() writes for a file whose parsed descriptor is `d`.
+inline uint64_t stream_bound(const oake_jpeg_desc& d) { return ((d.scan_len + 3) & ~static_cast<uint64_t>(3)) + 16; }
+
+// Copies the entropy-coded segment of `file` to `dst` WITHOUT the 0x00 stuffed after each 0xFF data byte,
+// cut at the first marker that is not RSTn and followed by >= 16 zero bytes (what jpeg_core.cuh's
+// BitReader expects), and rebases the descriptor: `placed` = `parsed` with scan_off = stream_off (the
+// offset `dst` will have in the device byte arena; a multiple of 4), scan_len = clean length, out_off,
+// and the coefficient / plane offsets moved behind *scratch_off (which is advanced).  Returns the bytes
+// written (a multiple of 4, <= stream_bound()).
+inline uint64_t stage(const oake_jpeg_desc& parsed, const uint8_t* file, uint8_t* dst, uint64_t stream_off,
+                      uint64_t out_off, uint64_t* scratch_off, oake_jpeg_desc* placed) {
+  const uint8_t* s = file + parsed.scan_off;
+  const uint8_t* end = s + parsed.scan_len;
+  uint8_t* o = dst;
+  while (s < end) {
+    const uint8_t* ff = static_cast<const uint8_t*>(memchr(s, 0xFF, static_cast<size_t>(end - s)));
+    const size_t run = static_cast<size_t>((ff ? ff : end) - s);
+    memcpy(o, s, run);
+    o += run;
+    s += run;
+    if (!ff) break;
+    const uint8_t next = s + 1 < end ? s[1] : 0xD9;
+    if (next == 0x00) {  // a data byte 0xFF
+      *o++ = 0xFF;
+      s += 2;
+    } else if ((next & 0xF8) == 0xD0) {  // RSTn stays in the stream; the decoder knows where to expect it
+      *o++ = 0xFF;
+      *o++ = next;
+      s += 2;
+    } else if (next == 0xFF) {  // fill byte in front of a marker
+      s += 1;
+    } else {
+      break;  // EOI or any other marker: the scan ends here
+    }
   }
-  d->scan_off += file_off;
-  d->out_off = out_off;
-  *scratch_off = base + d->scratch_bytes;
+  const uint64_t clean = static_cast<uint64_t>(o - dst);
+  const uint64_t total = ((clean + 3) & ~static_cast<uint64_t>(3)) + 16;
+  memset(o, 0, static_cast<size_t>(total - clean));
+  if (placed != &parsed) *placed = parsed;
+  const uint64_t base = align256(*scratch_off);
+  for (uint32_t c = 0; c < placed->ncomp; ++c) {
+    placed->comp[c].coef_off += base;
+    placed->comp[c].plane_off += base;
+  }
+  placed->sync_off += base;
+  placed->scan_off = stream_off;
+  placed->scan_len = clean;
+  placed->out_off = out_off;
+  *scratch_off = base + placed->scratch_bytes;
+  return total;
 }
 
 }  // namespace jpeg

@@ -28,7 +28,7 @@ def desc_bytes() -> int:
 
 class JpegSource:
     """One parsed, still compressed JPEG file."""
-    __slots__ = ('data', 'desc', 'shape', 'scratch_bytes')
+    __slots__ = ('data', 'desc', 'shape', 'scratch_bytes', 'stream_bound')
     dtype = np.dtype(np.uint8)
     ndim = 3
 
@@ -38,6 +38,8 @@ class JpegSource:
         width, height = struct.unpack_from('<II', desc, 0)
         self.shape = (height, width, 3)
         self.scratch_bytes = _scratch_bytes(desc)
+        scan_len = struct.unpack_from('<Q', desc, 48)[0]
+        self.stream_bound = (scan_len + 3) // 4 * 4 + 16  # what oake_jpeg_stage writes at most
 
     @property
     def size(self) -> int:

@@ -61,7 +61,7 @@ class _Slot:
     def __init__(self, device: torch.device) -> None:
         self.arena = _Staging(device)  # images | pyramid levels | resized crops
         self.meta = _Staging(device)  # resize jobs | crop descriptors | fg | box
-        self.jpeg = _Staging(device)  # descriptors | compressed files (host + device)
+        self.jpeg = _Staging(device)  # descriptors | entropy-coded streams (host + device)
         self.jpeg_scratch = _Staging(device)  # coefficients | component planes (device only)
         self.jpeg_status: Optional[torch.Tensor] = None  # int32 per compressed image
         self.jpeg_status_host: Optional[torch.Tensor] = None
@@ -204,21 +204,22 @@ class OakePipeline:
                     crops_off=crops_off, fg_off=fg_off, box_off=box_off, masks_off=masks_off)
 
     def _stage_jpeg(self, compressed, fresh: bool) -> dict:
-        """Host only: descriptors (rebased onto this slot's arenas) and files into pinned memory."""
+        """Host only: descriptors (rebased onto this slot's arenas) and entropy-coded streams into pinned memory."""
         slot, lib = self._slot, self.lib
         n, db = len(compressed), oake_jpeg.desc_bytes()
-        files_off = _align(n * db)
-        total = files_off + sum(_align(len(src.data), 16) for src, _ in compressed)
+        streams_off = _align(n * db)
+        total = streams_off + sum(_align(src.stream_bound, 16) for src, _ in compressed)
         fresh |= slot.jpeg.reserve(total)
         host = slot.jpeg.host.numpy()
         base = slot.jpeg.host.data_ptr()
-        off = files_off
-        scratch = C.c_uint64(0)
+        off = streams_off
+        scratch, written = C.c_uint64(0), C.c_uint64(0)
         for i, (src, out_off) in enumerate(compressed):
-            host[i * db:(i + 1) * db] = np.frombuffer(src.desc, dtype=np.uint8)
-            host[off:off + len(src.data)] = np.frombuffer(src.data, dtype=np.uint8)
-            binding.check(lib.oake_jpeg_place(base + i * db, off, out_off, C.byref(scratch)))
-            off += _align(len(src.data), 16)
+            # entropy-coded segment without its stuffing bytes -> pinned memory; descriptor i rebased
+            binding.check(lib.oake_jpeg_stage(src.desc, src.data, len(src.data), base + off, off, out_off,
+                                              C.byref(scratch), base + i * db, C.byref(written)))
+            off += _align(int(written.value), 16)
+        total = off
         fresh |= slot.jpeg_scratch.reserve(0, int(scratch.value))
         if slot.jpeg_status is None or slot.jpeg_status.numel() < n:
             slot.jpeg_status = torch.zeros(max(n, 256), dtype=torch.int32, device=self.device)

@@ -54,7 +54,7 @@ def test_coco_sized_files(pipe):
 def test_damaged_file_fails_loudly(pipe):
     _, data = next(iter(ojpeg.corpus(1)))
     src = oake_jpeg.parse(data)
-    cut = oake_jpeg.JpegSource(data[:len(data) * 2 // 3], src.desc)
+    cut = oake_jpeg.parse(data[:len(data) * 2 // 3])  # headers intact, entropy-coded data ends early
     with pytest.raises(binding.OakeError, match='damaged'):
         pipe.decode_jpegs([src, cut])
     with pytest.raises(binding.OakeError, match=r'\[1\]'):

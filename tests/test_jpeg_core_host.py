@@ -4,7 +4,7 @@
    IDCT, fancy upsampling, YCbCr->RGB) compiled with g++ into a throw-away harness
    (tests/jpeg_host_harness.cpp) and held bit-exact to Pillow -- the reference's decoder,
    oadp/oake/base.py:53 -- over oracle.jpeg.corpus().
-2. The host half of the C-ABI (`oake_jpeg_parse` / `oake_jpeg_place`, no GPU involved) through
+2. The host half of the C-ABI (`oake_jpeg_parse` / `oake_jpeg_stage`, no GPU involved) through
    liboake_b200.so: geometry, the unsupported envelope, malformed input, offset rebasing.
 """
 import ctypes
@@ -31,33 +31,49 @@ def harness(tmp_path_factory):
                     str(ROOT / 'tests' / 'jpeg_host_harness.cpp')], check=True)
     lib = ctypes.CDLL(str(so))
     lib.harness_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
-                                   ctypes.POINTER(ctypes.c_int)]
+                                   ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
 
-    def decode(data: bytes):
-        w, h = ctypes.c_int(), ctypes.c_int()
-        rc = lib.harness_decode(data, len(data), None, w, h)
+    def decode(data: bytes, parallel: bool = False):
+        """-> (rc, pixels, rounds the parallel decode needed to synchronise)"""
+        w, h, rounds = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(-1)
+        rc = lib.harness_decode(data, len(data), None, w, h, 0, None)
         if rc:
-            return rc, None
+            return rc, None, -1
         out = np.zeros((h.value, w.value, 3), np.uint8)
-        return lib.harness_decode(data, len(data), out.ctypes.data, w, h), out
+        rc = lib.harness_decode(data, len(data), out.ctypes.data, w, h, int(parallel), rounds)
+        return rc, out, rounds.value
 
     return decode
 
 
-def test_kernel_arithmetic_matches_pillow_bit_for_bit(harness):
+@pytest.mark.parametrize('parallel', [False, True], ids=['serial', 'subsequence-parallel'])
+def test_kernel_arithmetic_matches_pillow_bit_for_bit(harness, parallel):
     n = 0
     for label, data in ojpeg.corpus(0):
-        rc, got = harness(data)
+        rc, got, _ = harness(data, parallel)
         assert rc == 0, label
         assert np.array_equal(got, ojpeg.decode(data)), label
         n += 1
     assert n > 300
 
 
+def test_parallel_decode_synchronises_in_a_few_rounds(harness):
+    """COCO-sized files: hundreds to thousands of subsequences, yet the entry states settle in a handful of rounds."""
+    from oadp_b200 import synth
+    for i, (quality, sub) in enumerate(((90, 2), (75, 0), (98, 1), (30, 2))):
+        w, h = synth.COCO_SIZES[i]
+        buf = io.BytesIO()
+        PIL.Image.fromarray(synth.image(w, h, 11 + i)).save(buf, 'JPEG', quality=quality, subsampling=sub)
+        data = buf.getvalue()
+        rc, got, rounds = harness(data, True)
+        assert rc == 0 and np.array_equal(got, ojpeg.decode(data))
+        assert len(data) * 8 // 1024 > 20 and 1 <= rounds <= 24, (len(data), rounds)
+
+
 def test_damaged_entropy_data_is_reported(harness):
     _, data = next(iter(ojpeg.corpus(1)))
-    rc, _ = harness(data[:len(data) * 2 // 3])
-    assert rc == 3
+    for parallel in (False, True):
+        assert harness(data[:len(data) * 2 // 3], parallel)[0] == 3
     for label, data in ojpeg.outside_envelope():
         assert harness(data)[0] == oake_jpeg.UNSUPPORTED, label
 
@@ -85,17 +101,34 @@ def test_parse_geometry_and_envelope(lib):
         oake_jpeg.parse(buf.getvalue()[:100])  # ends inside the tables
 
 
-def test_place_rebases_offsets(lib):
+def test_stage_strips_stuffing_and_rebases_offsets(lib):
+    rng = np.random.default_rng(5)
     buf = io.BytesIO()
-    PIL.Image.fromarray(np.zeros((16, 16, 3), np.uint8)).save(buf, 'JPEG')
-    src = oake_jpeg.parse(buf.getvalue())
-    raw = ctypes.create_string_buffer(src.desc, len(src.desc))
+    PIL.Image.fromarray(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)).save(buf, 'JPEG', quality=100,
+                                                                                  restart_marker_blocks=2)
+    data = buf.getvalue()
+    src = oake_jpeg.parse(data)
     scan_off0, scan_len0 = struct.unpack_from('<2Q', src.desc, 40)
-    scratch = ctypes.c_uint64(1000)  # not aligned on purpose
-    assert lib.oake_jpeg_place(raw, 4096, 123, ctypes.byref(scratch)) == 0
-    scan_off, scan_len, out_off, scratch_bytes = struct.unpack_from('<4Q', raw.raw, 40)
-    assert (scan_off, scan_len, out_off) == (scan_off0 + 4096, scan_len0, 123)
+    assert scan_off0 + scan_len0 == len(data)
+    assert lib.oake_jpeg_stream_bound(src.desc) == src.stream_bound
+    dst = ctypes.create_string_buffer(b'\xaa' * (src.stream_bound + 8), src.stream_bound + 8)
+    placed = ctypes.create_string_buffer(len(src.desc))
+    scratch, written = ctypes.c_uint64(1000), ctypes.c_uint64(0)  # scratch offset not aligned on purpose
+    assert lib.oake_jpeg_stage(src.desc, data, len(data), dst, 4096, 123, ctypes.byref(scratch), placed,
+                               ctypes.byref(written)) == 0
+    scan_off, scan_len, out_off, scratch_bytes = struct.unpack_from('<4Q', placed.raw, 40)
+    assert (scan_off, out_off) == (4096, 123)
     assert scratch.value == 1024 + scratch_bytes and scratch_bytes == src.scratch_bytes
+    # the clean stream: stuffed zeros gone, RSTn markers kept, EOI cut, zero padding, nothing beyond
+    scan = data[scan_off0:]
+    assert scan.count(b'\xff\x00') > 0
+    want = scan[:scan.rindex(b'\xff\xd9')].replace(b'\xff\x00', b'\xff')
+    assert scan_len == len(want) and dst.raw[:scan_len] == want and b'\xff\xd0' in want
+    assert written.value == (scan_len + 3) // 4 * 4 + 16 <= src.stream_bound
+    assert dst.raw[scan_len:written.value] == bytes(written.value - scan_len)
+    assert dst.raw[written.value:] == b'\xaa' * (len(dst.raw) - written.value)
+    assert lib.oake_jpeg_stage(src.desc, data, len(data) - 1, dst, 0, 0, ctypes.byref(scratch), placed,
+                               ctypes.byref(written)) != 0  # not the file the descriptor came from
 
 
 def test_load_falls_back_to_pillow_outside_the_envelope(lib, tmp_path):

@@ -65,6 +65,9 @@ def main():
                               compressed_mb_per_s=round(sum(len(f) for f in files[:n]) / 1e6 / ms * 1e3, 1),
                               pixel_gb_per_s=round(sum(s.size for s in sources) / 1e9 / ms * 1e3, 2))), flush=True)
 
+    if '--decode-only' in sys.argv:
+        return
+
     # -- Pillow on the host: one thread, and every core
     t = time.perf_counter()
     for f in files[:128]:
