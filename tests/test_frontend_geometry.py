@@ -43,15 +43,15 @@ def test_clip_window_matches_torchvision():
         cw, ch = int(rng.integers(5, 2000)), int(rng.integers(5, 2000))
         if max(cw, ch) / min(cw, ch) > 30:
             continue
-        ow, oh, wx, wy = [int(v) for v in frontend.clip_resize_window(np.array([cw]), np.array([ch]))]
+        ow, oh, wx, wy = [int(v[0]) for v in frontend.clip_resize_window(np.array([cw]), np.array([ch]))]
         im = PIL.Image.new('RGB', (cw, ch))
         r = T.Resize(224, interpolation=T.InterpolationMode.BICUBIC)(im)
         assert r.size == (ow, oh), (cw, ch)
         # CenterCrop offsets: torchvision int(round((n - 224) / 2.0))
         assert wx == int(round((ow - 224) / 2.0)) and wy == int(round((oh - 224) / 2.0))
     # half-to-even cases
-    assert [int(v) for v in frontend.clip_resize_window(np.array([224]), np.array([225]))][2:] == [0, 0]
-    assert [int(v) for v in frontend.clip_resize_window(np.array([224]), np.array([227]))][2:] == [0, 2]
+    assert [int(v[0]) for v in frontend.clip_resize_window(np.array([224]), np.array([225]))][2:] == [0, 0]
+    assert [int(v[0]) for v in frontend.clip_resize_window(np.array([224]), np.array([227]))][2:] == [0, 2]
 
 
 def test_objects_plan_matches_oracle():
