@@ -11,7 +11,7 @@
 //   serial kernel    files WITH restart markers (rare; the marker positions depend on the MCU count, which
 //                    a thread entering mid-stream does not know): one warp per image, lane 0 decodes.
 //   idct kernel      one thread per 8x8 block: dequantise, islow IDCT, range limit -> uint8 planes.
-//   colour kernel    one thread per pixel pair: fancy chroma upsampling + YCbCr -> RGB, HWC stores.
+//   colour kernel    one thread per four pixels: fancy chroma upsampling + YCbCr -> RGB, HWC stores.
 #include <cuda_runtime.h>
 #include <stddef.h>
 
@@ -227,24 +227,38 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(const oake_jpeg_desc* __
   for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(dst + static_cast<uint64_t>(r) * pitch) = reinterpret_cast<const uint2*>(px)[r];
 }
 
+// one thread per four pixels of a row: 12 output bytes, stored as three words when they are aligned
 __global__ void __launch_bounds__(256) jpeg_colour_kernel(const oake_jpeg_desc* __restrict__ descs,
                                                           const uint8_t* __restrict__ scratch,
                                                           uint8_t* __restrict__ out) {
   const oake_jpeg_desc& d = descs[blockIdx.y];
-  const uint32_t pairs_w = (d.width + 1) / 2;
+  const uint32_t quads_w = (d.width + 3) / 4;
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= pairs_w * d.height) return;
-  const uint32_t Y = p / pairs_w, X = (p - Y * pairs_w) * 2;
+  if (p >= quads_w * d.height) return;
+  const uint32_t Y = p / quads_w, X = (p - Y * quads_w) * 4;
+  const uint32_t valid = min(4u, d.width - X);
+  uint8_t rgb[12];
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q) {
+    if (q < valid) jpeg::pixel_rgb(d, scratch, X + q, Y, rgb + 3 * q);
+    else rgb[3 * q] = rgb[3 * q + 1] = rgb[3 * q + 2] = 0;
+  }
   uint8_t* dst = out + d.out_off + (static_cast<uint64_t>(Y) * d.width + X) * 3;
-  uint8_t rgb[6];
-  jpeg::pixel_rgb(d, scratch, X, Y, rgb);
-  const bool two = X + 1 < d.width;
-  if (two) jpeg::pixel_rgb(d, scratch, X + 1, Y, rgb + 3);
+  if (valid == 4 && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(dst);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) dst[i] = rgb[i];
-  if (two) {
+    for (int i = 0; i < 3; ++i)
+      w[i] = rgb[4 * i] | (static_cast<uint32_t>(rgb[4 * i + 1]) << 8) | (static_cast<uint32_t>(rgb[4 * i + 2]) << 16) |
+             (static_cast<uint32_t>(rgb[4 * i + 3]) << 24);
+  } else {
 #pragma unroll
-    for (int i = 3; i < 6; ++i) dst[i] = rgb[i];
+    for (uint32_t q = 0; q < 4; ++q) {
+      if (q < valid) {
+        dst[3 * q] = rgb[3 * q];
+        dst[3 * q + 1] = rgb[3 * q + 1];
+        dst[3 * q + 2] = rgb[3 * q + 2];
+      }
+    }
   }
 }
 
@@ -282,7 +296,7 @@ int oake_jpeg_decode(const uint8_t* bytes, const oake_jpeg_desc* descs_host, con
   if (n == 0) return 0;
   if (n > 65535) return fail_msg("at most 65535 images per call");
   if (!bytes || !descs_host || !descs_dev || !scratch || !out || !status) return fail_msg("NULL buffer");
-  uint32_t max_blocks = 0, max_pairs = 0;
+  uint32_t max_blocks = 0, max_quads = 0;
   int n_plain = 0;  // files without restart markers
   for (int i = 0; i < n; ++i) {
     const oake_jpeg_desc& d = descs_host[i];
@@ -290,15 +304,15 @@ int oake_jpeg_decode(const uint8_t* bytes, const oake_jpeg_desc* descs_host, con
       return fail_msg("descriptor %d was not produced by oake_jpeg_parse", i);
     n_plain += d.restart_interval == 0 ? 1 : 0;
     max_blocks = d.total_blocks > max_blocks ? d.total_blocks : max_blocks;
-    const uint32_t pairs = ((d.width + 1) / 2) * d.height;
-    max_pairs = pairs > max_pairs ? pairs : max_pairs;
+    const uint32_t quads = ((d.width + 3) / 4) * d.height;
+    max_quads = quads > max_quads ? quads : max_quads;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* scr = static_cast<uint8_t*>(scratch);
   if (n_plain) jpeg_entropy_par_kernel<<<n, kParThreads, 0, st>>>(bytes, descs_dev, scr, status);
   if (n_plain < n) jpeg_entropy_serial_kernel<<<n, 32, 0, st>>>(bytes, descs_dev, scr, status);
   jpeg_idct_kernel<<<dim3((max_blocks + 127) / 128, n), 128, 0, st>>>(descs_dev, scr);
-  jpeg_colour_kernel<<<dim3((max_pairs + 255) / 256, n), 256, 0, st>>>(descs_dev, scr, out);
+  jpeg_colour_kernel<<<dim3((max_quads + 255) / 256, n), 256, 0, st>>>(descs_dev, scr, out);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : fail_msg("oake_jpeg_decode launch: %s", cudaGetErrorString(e));
 }

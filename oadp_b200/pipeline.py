@@ -72,28 +72,48 @@ class _Slot:
         self.out_host: Optional[torch.Tensor] = None
         self.event = torch.cuda.Event()
         self.busy = False
+        self.ticket: Optional['Pending'] = None  # the uncollected batch that lives in this slot
 
 
 class Pending:
-    """Handle of a submitted batch; `result()` waits for the GPU and returns what `encode_*` returns."""
+    """Handle of a submitted batch; `result()` waits for the GPU and returns what `encode_*` returns.
+
+    The batch lives in one of the pipeline's two slots until it is collected.  Submitting a third batch
+    while two are outstanding collects the oldest one first (its result -- or its error -- is then kept
+    in the handle), so a handle stays valid however late `result()` is called."""
 
     def __init__(self, pipe: 'OakePipeline', slot: _Slot, host: torch.Tensor, finish) -> None:
         self._pipe, self._slot, self._host, self._finish = pipe, slot, host, finish
+        self._jpeg_count = slot.jpeg_count
         self._done = None
+        self._error: Optional[Exception] = None
+        self._collected = False
+
+    def collect(self) -> None:
+        """Waits for the GPU side and moves the result out of the slot's buffers (idempotent)."""
+        if self._collected:
+            return
+        self._collected = True
+        slot = self._slot
+        slot.event.synchronize()
+        slot.busy = False
+        slot.ticket = None
+        if int(slot.err_host.item()) != 0:
+            slot.err.zero_()
+            self._error = binding.OakeError('oake_resize_u8: a crop exceeded the resize kernel limits')
+            return
+        if self._jpeg_count:
+            bad = slot.jpeg_status_host[:self._jpeg_count].nonzero().flatten().tolist()
+            if bad:
+                self._error = binding.OakeError(f'oake_jpeg_decode: damaged or truncated entropy-coded data in '
+                                                f'compressed image(s) {bad} of the batch')
+                return
+        self._done = self._finish(self._host.clone())
 
     def result(self):
-        if self._done is None:
-            self._slot.event.synchronize()
-            self._slot.busy = False
-            if int(self._slot.err_host.item()) != 0:
-                self._slot.err.zero_()
-                raise binding.OakeError('oake_resize_u8: a crop exceeded the resize kernel limits')
-            if self._slot.jpeg_count:
-                bad = self._slot.jpeg_status_host[:self._slot.jpeg_count].nonzero().flatten().tolist()
-                if bad:
-                    raise binding.OakeError(f'oake_jpeg_decode: damaged or truncated entropy-coded data in '
-                                            f'compressed image(s) {bad} of the batch')
-            self._done = self._finish(self._host.clone())
+        self.collect()
+        if self._error is not None:
+            raise self._error
         return self._done
 
 
@@ -136,8 +156,8 @@ class OakePipeline:
         """stage -> H2D -> kernels -> D2H, all asynchronous on the current stream."""
         nxt = self._cur ^ 1
         slot = self._slots[nxt]
-        if slot.busy:  # its previous batch has not been collected yet: wait for the GPU side of it
-            slot.event.synchronize()
+        if slot.ticket is not None:  # its previous batch has not been collected yet: do that now
+            slot.ticket.collect()
         self._cur = nxt
         job = self.stage(*plan_args)
         self.upload(job)
@@ -155,7 +175,8 @@ class OakePipeline:
             slot.jpeg_status_host[:slot.jpeg_count].copy_(slot.jpeg_status[:slot.jpeg_count], non_blocking=True)
             slot.event.record(torch.cuda.current_stream(self.device))
             self.d2h_bytes += 4 * slot.jpeg_count
-        return Pending(self, slot, host, finish)
+        slot.ticket = Pending(self, slot, host, finish)
+        return slot.ticket
 
     def _run(self, *plan_args) -> torch.Tensor:
         """Synchronous form: returns the HOST fp16 (n_crops, 512) tensor."""
@@ -420,8 +441,8 @@ class OakePipeline:
         offs, img_bytes = self._place_images(sources)
         self._cur ^= 1
         slot = self._slot
-        if slot.busy:
-            slot.event.synchronize()
+        if slot.ticket is not None:
+            slot.ticket.collect()
         fresh = slot.arena.reserve(1, img_bytes)
         jj = self._stage_jpeg(list(zip(sources, offs)), fresh)
         slot.jpeg_count = 0

@@ -83,9 +83,10 @@ def test_pipeline_takes_compressed_and_decoded_images_alike(pipe):
     for a, b in zip(pipe.encode_objects(compressed, props), o_ref):
         assert torch.equal(a['embeddings'], b['embeddings'])
     # back-to-back submissions (two slots in flight, decode on the side stream)
-    tickets = [pipe.submit_blocks(compressed[i:i + 2]) for i in (0, 2)] + [pipe.submit_blocks(compressed[:2])]
-    outs = [t.result() for t in tickets]
-    for a, b in zip(outs[0] + outs[1] + outs[2], ref + ref[:2]):
+    # -- and more submissions than slots before anything is collected: handles stay valid
+    tickets = [pipe.submit_blocks(compressed[i:i + 2]) for i in (0, 2)] + [pipe.submit_blocks(mixed[1:3])]
+    outs = [t.result() for t in reversed(tickets)][::-1]
+    for a, b in zip(outs[0] + outs[1] + outs[2], ref + ref[1:3]):
         assert torch.equal(a['embeddings'], b['embeddings'])
 
 
