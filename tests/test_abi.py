@@ -51,3 +51,18 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(binding, 'LIB_PATH', tmp_path / 'nope.so')
     with pytest.raises(binding.OakeError):
         binding.load()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under oadp_b200/ or the oadp/ alias package may import it
+    (only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs do)."""
+    offenders = []
+    for pkg in ('oadp_b200', 'oadp'):
+        for f in (ROOT / pkg).rglob('*.py'):
+            if re.search(r'^\s*(from|import)\s+oracle\b', f.read_text(), flags=re.M):
+                offenders.append(str(f.relative_to(ROOT)))
+    assert offenders == []
+    bench = (ROOT / 'bench.py').read_text()
+    # in bench.py the oracle is only reachable from the CPU-baseline function
+    assert len(re.findall(r'^\s*(?:from|import)\s+oracle\b', bench, flags=re.M)) == 2
+    assert bench.index('def cpu_') < bench.index('from oracle import frontend')
