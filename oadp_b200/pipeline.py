@@ -16,6 +16,7 @@ Results per image have exactly the reference's layouts:
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -30,6 +31,59 @@ CROP_BYTES = frontend.SIZE * frontend.SIZE * 3
 
 def _align(v: int, a: int = 256) -> int:
     return (v + a - 1) // a * a
+
+
+_STAGE_POOL = None
+
+
+def _stage_pool():
+    global _STAGE_POOL
+    if _STAGE_POOL is None:
+        import concurrent.futures
+        import os
+        _STAGE_POOL = concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1),
+                                                            thread_name_prefix='oake-jpeg-stage')
+    return _STAGE_POOL
+
+
+class _BlocksTemplate:
+    """Everything `plan_blocks` needs for one image size, with offsets relative to the image's slots."""
+    __slots__ = ('plan', 'level_rel', 'level_jobs', 'pyramid_bytes', 'glob_job', 'crops', 'cell_level', 'bboxes_half')
+
+
+@functools.lru_cache(maxsize=4096)
+def _blocks_template(w: int, h: int) -> _BlocksTemplate:
+    t = _BlocksTemplate()
+    t.plan = plan = frontend.blocks_plan(w, h)
+    t.bboxes_half = None
+    rel, off, jobs = [0], 0, []
+    for lv in range(1, len(plan.levels)):
+        (lw, lh), (pw, ph) = plan.levels[lv], plan.levels[lv - 1]
+        rel.append(off)
+        jobs.append(frontend.level_job(0, pw, ph, 0, lw, lh))
+        off += _align(lw * lh * 3)
+    t.level_rel = np.asarray(rel, dtype=np.int64)
+    t.level_jobs = jobs
+    t.pyramid_bytes = off
+    t.glob_job = frontend.crop_jobs(0, w, h, np.array([[0, 0, w, h]], dtype=np.int64), 0)
+    c = np.zeros(1 + len(plan.cells), dtype=frontend.CROP_SRC)
+    c['pitch_px'][0] = frontend.SIZE
+    for i, (lv, x, y) in enumerate(plan.cells):
+        lw = plan.levels[lv][0]
+        c['off'][1 + i] = (y * lw + x) * 3  # inside its level
+        c['pitch_px'][1 + i] = lw
+    t.crops = c
+    t.cell_level = np.asarray([lv for lv, _, _ in plan.cells], dtype=np.int64)
+    return t
+
+
+def _bboxes_half(plan) -> torch.Tensor:
+    t = _blocks_template(*plan.levels[0]) if plan.levels else None
+    if t is None or t.plan is not plan:
+        return torch.tensor(plan.bboxes, dtype=torch.float32).half()
+    if t.bboxes_half is None:
+        t.bboxes_half = torch.tensor(plan.bboxes, dtype=torch.float32).half()
+    return t.bboxes_half
 
 
 class _Staging:
@@ -228,19 +282,32 @@ class OakePipeline:
         """Host only: descriptors (rebased onto this slot's arenas) and entropy-coded streams into pinned memory."""
         slot, lib = self._slot, self.lib
         n, db = len(compressed), oake_jpeg.desc_bytes()
-        streams_off = _align(n * db)
-        total = streams_off + sum(_align(src.stream_bound, 16) for src, _ in compressed)
-        fresh |= slot.jpeg.reserve(total)
-        host = slot.jpeg.host.numpy()
-        base = slot.jpeg.host.data_ptr()
-        off = streams_off
-        scratch, written = C.c_uint64(0), C.c_uint64(0)
-        for i, (src, out_off) in enumerate(compressed):
-            # entropy-coded segment without its stuffing bytes -> pinned memory; descriptor i rebased
-            binding.check(lib.oake_jpeg_stage(src.desc, src.data, len(src.data), base + off, off, out_off,
-                                              C.byref(scratch), base + i * db, C.byref(written)))
-            off += _align(int(written.value), 16)
+        # layout from the parsed headers alone, so that the images can be staged independently: stream i at
+        # stream_off[i] (its upper bound reserved), scratch of image i at scratch_off[i]
+        stream_off, scratch_off = [], []
+        off, scr = _align(n * db), 0
+        for src, _ in compressed:
+            stream_off.append(off)
+            scratch_off.append(scr)
+            off += _align(src.stream_bound, 16)
+            scr += _align(src.scratch_bytes)
         total = off
+        fresh |= slot.jpeg.reserve(total)
+        base = slot.jpeg.host.data_ptr()
+
+        def stage_one(i: int) -> None:
+            # entropy-coded segment without its stuffing bytes -> pinned memory; descriptor i rebased
+            src, out_off = compressed[i]
+            scratch, written = C.c_uint64(scratch_off[i]), C.c_uint64(0)
+            binding.check(lib.oake_jpeg_stage(src.desc, src.data, len(src.data), base + stream_off[i], stream_off[i],
+                                              out_off, C.byref(scratch), base + i * db, C.byref(written)))
+
+        if n >= 16:  # a memcpy-like pass per file: ctypes drops the GIL, a few threads share it
+            list(_stage_pool().map(stage_one, range(n)))
+        else:
+            for i in range(n):
+                stage_one(i)
+        scratch = C.c_uint64(scr)
         fresh |= slot.jpeg_scratch.reserve(0, int(scratch.value))
         if slot.jpeg_status is None or slot.jpeg_status.numel() < n:
             slot.jpeg_status = torch.zeros(max(n, 256), dtype=torch.int32, device=self.device)
@@ -336,16 +403,18 @@ class OakePipeline:
 
     def plan_globals(self, images: Sequence[np.ndarray]) -> tuple:
         offs, img_bytes = self._place_images(images)
-        jobs = []
-        for k, (im, o) in enumerate(zip(images, offs)):
-            h, w = im.shape[:2]
-            jobs.append(frontend.crop_jobs(o, w, h, np.array([[0, 0, w, h]], dtype=np.int64),
-                                           img_bytes + k * CROP_BYTES))
-        jobs = np.concatenate(jobs) if jobs else np.zeros(0, frontend.RESIZE_JOB)
-        crops = np.zeros(len(images), dtype=frontend.CROP_SRC)
+        n = len(images)
+        if n:
+            # one CLIP-transform job per image, built for the whole batch at once
+            wh = np.array([(im.shape[1], im.shape[0]) for im in images], dtype=np.int64)
+            boxes = np.concatenate([np.zeros((n, 2), np.int64), wh], axis=1)
+            jobs = frontend.crop_jobs(np.asarray(offs, dtype=np.int64), wh[:, 0], wh[:, 1], boxes, img_bytes)
+        else:
+            jobs = np.zeros(0, frontend.RESIZE_JOB)
+        crops = np.zeros(n, dtype=frontend.CROP_SRC)
         crops['off'] = jobs['dst_off']
         crops['pitch_px'] = frontend.SIZE
-        return (images, offs, img_bytes, img_bytes + len(images) * CROP_BYTES, [jobs], crops, binding.VARIANT_T50)
+        return (images, offs, img_bytes, img_bytes + n * CROP_BYTES, [jobs], crops, binding.VARIANT_T50)
 
     def encode_blocks(self, images: Sequence[np.ndarray]) -> List[Dict[str, torch.Tensor]]:
         return self.submit_blocks(images).result()
@@ -356,8 +425,7 @@ class OakePipeline:
         def finish(emb: torch.Tensor):
             out, s = [], 0
             for plan, n in zip(plans, counts):
-                out.append(dict(embeddings=emb[s:s + n],
-                                bboxes=torch.tensor(plan.bboxes, dtype=torch.float32).half()))
+                out.append(dict(embeddings=emb[s:s + n], bboxes=_bboxes_half(plan).clone()))
                 s += n
             return out
 
@@ -365,36 +433,32 @@ class OakePipeline:
 
     def plan_blocks(self, images: Sequence[np.ndarray]):
         offs, img_bytes = self._place_images(images)
-        plans = [frontend.blocks_plan(im.shape[1], im.shape[0]) for im in images]
-        off = img_bytes
-        # global crops (packed) first
-        glob_off = off
-        off += len(images) * CROP_BYTES
-        stage_jobs: List[List[np.ndarray]] = [[]]
+        tpls = [_blocks_template(im.shape[1], im.shape[0]) for im in images]
+        plans = [t.plan for t in tpls]
+        counts = [t.crops.shape[0] for t in tpls]
+        # arena: images | global crops (packed) | per image: its pyramid levels 1..
+        glob_off = img_bytes
+        off = img_bytes + len(images) * CROP_BYTES
+        n_stages = max([len(t.level_jobs) for t in tpls] + [0])
+        stage_jobs: List[List[np.ndarray]] = [[] for _ in range(max(n_stages, 1))]
         crops_all = []
-        counts = []
-        for k, (im, o, plan) in enumerate(zip(images, offs, plans)):
-            h, w = im.shape[:2]
-            stage_jobs[0].append(frontend.crop_jobs(o, w, h, np.array([[0, 0, w, h]], dtype=np.int64),
-                                                    glob_off + k * CROP_BYTES))
-            level_off = [o]
-            for lv in range(1, len(plan.levels)):
-                lw, lh = plan.levels[lv]
-                pw, ph = plan.levels[lv - 1]
-                level_off.append(off)
-                while len(stage_jobs) < lv:
-                    stage_jobs.append([])
-                stage_jobs[lv - 1].append(frontend.level_job(level_off[lv - 1], pw, ph, off, lw, lh))
-                off += _align(lw * lh * 3)
-            c = np.zeros(1 + len(plan.cells), dtype=frontend.CROP_SRC)
+        for k, (o, t) in enumerate(zip(offs, tpls)):
+            level_off = t.level_rel + off  # absolute arena offset of every level ...
+            level_off[0] = o  # ... level 0 being the image itself
+            g = t.glob_job.copy()
+            g['src_off'] = o
+            g['dst_off'] = glob_off + k * CROP_BYTES
+            stage_jobs[0].append(g)
+            for lv, job in enumerate(t.level_jobs, start=1):  # level lv is resized from level lv - 1
+                j = job.copy()
+                j['src_off'] = level_off[lv - 1]
+                j['dst_off'] = level_off[lv]
+                stage_jobs[lv - 1].append(j)
+            c = t.crops.copy()
             c['off'][0] = glob_off + k * CROP_BYTES
-            c['pitch_px'][0] = frontend.SIZE
-            for i, (lv, x, y) in enumerate(plan.cells):
-                lw = plan.levels[lv][0]
-                c['off'][1 + i] = level_off[lv] + (y * lw + x) * 3
-                c['pitch_px'][1 + i] = lw
+            c['off'][1:] += level_off[t.cell_level]
             crops_all.append(c)
-            counts.append(c.shape[0])
+            off += t.pyramid_bytes
         stages = [np.concatenate(s) if s else np.zeros(0, frontend.RESIZE_JOB) for s in stage_jobs]
         crops = np.concatenate(crops_all) if crops_all else np.zeros(0, frontend.CROP_SRC)
         return (images, offs, img_bytes, off, stages, crops, binding.VARIANT_T50), plans, counts

@@ -86,27 +86,32 @@ def main():
         oake_jpeg.parse(f)
     print(json.dumps(dict(what='host_parse', images_per_s_1_thread=round(256 / (time.perf_counter() - t), 1))), flush=True)
 
-    # -- blocks task end to end from compressed files (file bytes in host memory -> fp16 rows on the host)
-    def run(decoder, batch_images=64, workers=cores):
+    # -- blocks and globals tasks end to end from compressed files (file bytes in host memory -> fp16 rows on
+    #    the host); the decoder is either the GPU one (host: header parse only) or Pillow on every host thread
+    def run(task, decoder, batch_images, workers=cores):
+        submit = pipe.submit_blocks if task == 'blocks' else pipe.submit_globals
+        count = (lambda res: sum(r['embeddings'].shape[0] for r in res)) if task == 'blocks' else len
         with concurrent.futures.ThreadPoolExecutor(workers) as pool:
             crops, in_flight = 0, None
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for s in range(0, len(files), batch_images):
                 batch = list(pool.map(decoder, files[s:s + batch_images]))
-                ticket = pipe.submit_blocks(batch)
+                ticket = submit(batch)
                 if in_flight is not None:
-                    crops += sum(r['embeddings'].shape[0] for r in in_flight.result())
+                    crops += count(in_flight.result())
                 in_flight = ticket
-            crops += sum(r['embeddings'].shape[0] for r in in_flight.result())
+            crops += count(in_flight.result())
             dt = time.perf_counter() - t0
         return len(files) / dt, crops / dt
 
-    for name, decoder in (('gpu', oake_jpeg.parse), ('pillow', pil_decode)):
-        run(decoder)
-        ips, cps = run(decoder)
-        print(json.dumps(dict(what='blocks_e2e_from_files', decoder=name, host_threads=cores, batch_images=64,
-                              images_per_s=round(ips, 1), crops_per_s=round(cps, 1))), flush=True)
+    for task, batch_images in (('blocks', 64), ('globals', 256)):
+        for name, decoder in (('gpu', oake_jpeg.parse), ('pillow', pil_decode)):
+            run(task, decoder, batch_images)
+            ips, cps = run(task, decoder, batch_images)
+            print(json.dumps(dict(what=f'{task}_e2e_from_files', decoder=name, host_threads=cores,
+                                  batch_images=batch_images, images_per_s=round(ips, 1), crops_per_s=round(cps, 1))),
+                  flush=True)
 
 
 if __name__ == '__main__':
