@@ -34,6 +34,7 @@ def _align(v: int, a: int = 256) -> int:
 
 
 _STAGE_POOL = None
+_STAGE_WORKERS = 8
 
 
 def _stage_pool():
@@ -41,7 +42,7 @@ def _stage_pool():
     if _STAGE_POOL is None:
         import concurrent.futures
         import os
-        _STAGE_POOL = concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1),
+        _STAGE_POOL = concurrent.futures.ThreadPoolExecutor(max_workers=min(_STAGE_WORKERS, os.cpu_count() or 1),
                                                             thread_name_prefix='oake-jpeg-stage')
     return _STAGE_POOL
 
@@ -302,11 +303,18 @@ class OakePipeline:
             binding.check(lib.oake_jpeg_stage(src.desc, src.data, len(src.data), base + stream_off[i], stream_off[i],
                                               out_off, C.byref(scratch), base + i * db, C.byref(written)))
 
-        if n >= 16:  # a memcpy-like pass per file: ctypes drops the GIL, a few threads share it
-            list(_stage_pool().map(stage_one, range(n)))
-        else:
-            for i in range(n):
+        def stage_range(lo: int) -> None:
+            for i in range(lo, min(lo + per, n)):
                 stage_one(i)
+
+        # a memcpy-like pass per file; ctypes drops the GIL, so a few threads share a large batch -- in
+        # a handful of contiguous chunks, not one task per file (every task costs GIL hand-offs)
+        workers = _STAGE_WORKERS if n >= 4 * _STAGE_WORKERS else 1
+        per = (n + workers - 1) // workers
+        if workers > 1:
+            list(_stage_pool().map(stage_range, range(0, n, per)))
+        else:
+            stage_range(0)
         scratch = C.c_uint64(scr)
         fresh |= slot.jpeg_scratch.reserve(0, int(scratch.value))
         if slot.jpeg_status is None or slot.jpeg_status.numel() < n:
