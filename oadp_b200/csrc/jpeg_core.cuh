@@ -308,7 +308,12 @@ OAKE_HD SubResult decode_subsequence(const oake_jpeg_desc& d, const McuMap& map,
 constexpr int kConstBits = 13;
 constexpr int kPass1Bits = 2;
 
-OAKE_HD int32_t descale(int32_t x, int n) { return (x + (1 << (n - 1))) >> n; }
+// The IDCT adds and multiplies modulo 2^32 (unsigned): for a sound file nothing comes near the limits
+// and the values are those of libjpeg's signed arithmetic; for damaged data the sums just wrap instead
+// of being undefined.  Only the final shifts look at the value as a signed number.
+typedef uint32_t idct_t;
+
+OAKE_HD int32_t descale(idct_t x, int n) { return static_cast<int32_t>(x + (1u << (n - 1))) >> n; }
 
 // the sample range-limit table of libjpeg behind the IDCT, as arithmetic: index = (x & 1023)
 OAKE_HD uint8_t idct_range_limit(int32_t x) {
@@ -319,33 +324,35 @@ OAKE_HD uint8_t idct_range_limit(int32_t x) {
   return static_cast<uint8_t>(i - 896);
 }
 
+OAKE_HD idct_t fix(int32_t c) { return static_cast<idct_t>(c); }  // a (possibly negative) constant mod 2^32
+
 // One 1-D pass over eight values (already dequantised / from the workspace); results left unscaled.
-OAKE_HD void idct_1d(const int32_t in[8], int32_t out[8]) {
+OAKE_HD void idct_1d(const idct_t in[8], idct_t out[8]) {
   // even part
-  int32_t z2 = in[2], z3 = in[6];
-  int32_t z1 = (z2 + z3) * 4433;
-  const int32_t e2 = z1 + z3 * (-15137);
-  const int32_t e3 = z1 + z2 * 6270;
+  idct_t z2 = in[2], z3 = in[6];
+  idct_t z1 = (z2 + z3) * fix(4433);
+  const idct_t e2 = z1 + z3 * fix(-15137);
+  const idct_t e3 = z1 + z2 * fix(6270);
   z2 = in[0];
   z3 = in[4];
-  const int32_t e0 = (z2 + z3) * (1 << kConstBits);
-  const int32_t e1 = (z2 - z3) * (1 << kConstBits);
-  const int32_t t10 = e0 + e3, t13 = e0 - e3, t11 = e1 + e2, t12 = e1 - e2;
+  const idct_t e0 = (z2 + z3) << kConstBits;
+  const idct_t e1 = (z2 - z3) << kConstBits;
+  const idct_t t10 = e0 + e3, t13 = e0 - e3, t11 = e1 + e2, t12 = e1 - e2;
   // odd part
-  int32_t o0 = in[7], o1 = in[5], o2 = in[3], o3 = in[1];
+  idct_t o0 = in[7], o1 = in[5], o2 = in[3], o3 = in[1];
   z1 = o0 + o3;
   z2 = o1 + o2;
   z3 = o0 + o2;
-  int32_t z4 = o1 + o3;
-  const int32_t z5 = (z3 + z4) * 9633;
-  o0 *= 2446;
-  o1 *= 16819;
-  o2 *= 25172;
-  o3 *= 12299;
-  z1 *= -7373;
-  z2 *= -20995;
-  z3 *= -16069;
-  z4 *= -3196;
+  idct_t z4 = o1 + o3;
+  const idct_t z5 = (z3 + z4) * fix(9633);
+  o0 *= fix(2446);
+  o1 *= fix(16819);
+  o2 *= fix(25172);
+  o3 *= fix(12299);
+  z1 *= fix(-7373);
+  z2 *= fix(-20995);
+  z3 *= fix(-16069);
+  z4 *= fix(-3196);
   z3 += z5;
   z4 += z5;
   o0 += z1 + z3;
@@ -364,19 +371,20 @@ OAKE_HD void idct_1d(const int32_t in[8], int32_t out[8]) {
 
 // coef: 64 int16 in zig-zag (file) order; quant: 64 uint16 in natural order; dst: 8 rows of 8 bytes.
 OAKE_HD void idct_block(const int16_t* coef, const uint16_t* quant, uint8_t* dst, uint32_t pitch) {
-  int32_t ws[64];
+  idct_t ws[64];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    int32_t in[8], o[8];
+    idct_t in[8], o[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) in[r] = static_cast<int32_t>(coef[zigzag_pos(r * 8 + c)]) * static_cast<int32_t>(quant[r * 8 + c]);
+    for (int r = 0; r < 8; ++r)
+      in[r] = static_cast<idct_t>(static_cast<int32_t>(coef[zigzag_pos(r * 8 + c)])) * static_cast<idct_t>(quant[r * 8 + c]);
     idct_1d(in, o);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) ws[r * 8 + c] = descale(o[r], kConstBits - kPass1Bits);
+    for (int r = 0; r < 8; ++r) ws[r * 8 + c] = static_cast<idct_t>(descale(o[r], kConstBits - kPass1Bits));
   }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    int32_t o[8];
+    idct_t o[8];
     idct_1d(ws + r * 8, o);
 #pragma unroll
     for (int c = 0; c < 8; ++c) dst[r * pitch + c] = idct_range_limit(descale(o[c], kConstBits + kPass1Bits + 3));

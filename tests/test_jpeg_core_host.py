@@ -9,6 +9,7 @@
 """
 import ctypes
 import io
+import os
 import pathlib
 import struct
 import subprocess
@@ -141,3 +142,66 @@ def test_load_falls_back_to_pillow_outside_the_envelope(lib, tmp_path):
     assert isinstance(got, np.ndarray) and np.array_equal(got, ojpeg.decode((tmp_path / 'p.jpg').read_bytes()))
     PIL.Image.fromarray(arr).save(tmp_path / 'b.jpg')
     assert isinstance(oake_jpeg.load(tmp_path / 'b.jpg'), oake_jpeg.JpegSource)
+
+
+def _mutations(seed: int, per_file: int):
+    """Valid files and damaged variants of them: flipped bits, truncation, scribbled headers, stray
+    markers in the scan, absurd frame sizes."""
+    rng = np.random.default_rng(seed)
+    base = []
+    for (w, h), quality, sub, rst in (((64, 48), 90, 2, 0), ((67, 45), 75, 0, 0), ((33, 130), 95, 1, 3),
+                                      ((17, 9), 30, 2, 0), ((120, 80), 85, 2, 5)):
+        coarse = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2, 3), dtype=np.uint8)
+        im = PIL.Image.fromarray(coarse).resize((w, h), PIL.Image.BICUBIC)
+        kw = dict(quality=quality, subsampling=sub)
+        if rst:
+            kw['restart_marker_blocks'] = rst
+        for image in (im, im.convert('L')):
+            buf = io.BytesIO()
+            image.save(buf, 'JPEG', **kw)
+            base.append(buf.getvalue())
+    for data in base:
+        yield data
+        for _ in range(per_file):
+            m = bytearray(data)
+            kind = int(rng.integers(0, 5))
+            if kind == 0:
+                for _ in range(int(rng.integers(1, 8))):
+                    m[int(rng.integers(0, len(m)))] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                m = m[:int(rng.integers(0, len(m)))]
+            elif kind == 2:
+                for _ in range(int(rng.integers(1, 6))):
+                    m[int(rng.integers(0, min(len(m), 700)))] = int(rng.integers(0, 256))
+            elif kind == 3:
+                i = int(rng.integers(len(m) // 2, len(m)))
+                m[i:i] = bytes([0xFF, int(rng.integers(0, 256))])
+            else:
+                j = bytes(m).find(b'\xff\xc0')
+                if j > 0:
+                    m[j + 5:j + 9] = struct.pack('>HH', int(rng.integers(0, 3000)), int(rng.integers(0, 3000)))
+            yield bytes(m)
+
+
+def test_damaged_files_never_touch_memory_out_of_bounds(tmp_path):
+    """The parser, the staging pass and the device-side decode functions under ASAN + UBSAN on ~600 damaged
+    files (the GPU kernels run the same functions on whatever the dataset directory holds)."""
+    exe = tmp_path / 'jpeg_fuzz'
+    build = subprocess.run(['g++', '-O1', '-g', '-std=c++17', '-fsanitize=address,undefined', '-fno-omit-frame-pointer',
+                            '-Wno-unknown-pragmas', '-o', str(exe), str(ROOT / 'tests' / 'jpeg_fuzz_main.cpp')],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and 'sanitize' in build.stderr:
+        pytest.skip('this g++ has no sanitizer runtime')
+    assert build.returncode == 0, build.stderr
+    corpus = tmp_path / 'corpus.bin'
+    n = 0
+    with open(corpus, 'wb') as f:
+        for data in _mutations(1, 60):
+            f.write(struct.pack('<I', len(data)))
+            f.write(data)
+            n += 1
+    run = subprocess.run([str(exe), str(corpus)], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, ASAN_OPTIONS='detect_leaks=0'))
+    assert run.returncode == 0, run.stderr[-2000:]
+    assert 'runtime error' not in run.stderr and 'AddressSanitizer' not in run.stderr, run.stderr[-2000:]
+    assert run.stdout.startswith(f'records {n} decoded ')
