@@ -118,3 +118,27 @@ def test_synthetic_dataset_and_skip_logic(tmp_path):
                                        default_config=dict(grid=14))
     b = oblocks.Dataset(**Config.load(info['configs']['blocks']).train.dataloader.dataset)
     assert [b.cost(i) for i in range(3)] == [27.0, 22.0, 27.0]
+
+
+def test_dataset_hands_out_compressed_files_with_gpu_decode(tmp_path, lib):
+    """`decode='gpu'`: the item is the still-compressed file for JPEGs the GPU decoder covers,
+    Pillow's pixels for everything else -- either way with the shape the planner needs."""
+    import numpy as np
+    import PIL.Image
+    from oadp_b200 import jpeg as oake_jpeg
+    from oadp_b200 import synth
+    from oadp_b200.oake import globals as oglobals
+    info = synth.write_coco_dataset(tmp_path, 3, seed=2, fmt='jpg')
+    cfg = Config.load(info['configs']['globals'])
+    ds = oglobals.Dataset(**cfg.val.dataloader.dataset)
+    assert isinstance(ds[0].image, np.ndarray)  # default: decoded on the host as the reference does
+    ds.gpu_decode = True
+    items = [ds[i] for i in range(3)]
+    assert all(isinstance(it.image, oake_jpeg.JpegSource) for it in items)
+    for it, (w, h) in zip(items, synth.COCO_SIZES):
+        assert it.image.shape == (h, w, 3) and it.image.dtype == np.uint8 and it.image.ndim == 3
+    # a progressive file in the same directory falls back to the reference's loader
+    path = ds.image_path(ds.ids[1])
+    PIL.Image.open(path).save(path, 'JPEG', progressive=True)
+    got = ds[1].image
+    assert isinstance(got, np.ndarray) and np.array_equal(got, np.asarray(PIL.Image.open(path).convert('RGB')))
