@@ -237,6 +237,8 @@ typedef struct {
   uint64_t out_off;       /* RGB HWC output (width * height * 3 bytes): byte offset into `out` */
   uint64_t scratch_bytes; /* coefficients + planes + subsequence table of this image */
   uint64_t sync_off;      /* subsequence table, 24 bytes per slot: byte offset into scratch */
+  uint32_t restart_count; /* restart intervals of the scan: ceil(MCUs / restart_interval), 0 = none */
+  uint32_t _pad;
   oake_jpeg_comp comp[3];
   uint16_t quant[4][64]; /* natural (row-major) order */
   oake_jpeg_huff dc[2], ac[2];
@@ -250,8 +252,10 @@ size_t oake_jpeg_desc_bytes(void); /* sizeof(oake_jpeg_desc), for bindings that 
 int oake_jpeg_parse(const uint8_t* data, size_t len, oake_jpeg_desc* desc);
 /* HOST calls: oake_jpeg_stage copies the entropy-coded segment of `file` (the `len` bytes that were
  * parsed into `parsed`) to `dst` -- normally pinned memory -- without the 0x00 bytes the format stuffs
- * after every 0xFF, cut at the end-of-image marker and zero-padded to a multiple of 4 plus 16 bytes;
- * at most oake_jpeg_stream_bound(parsed) bytes, the count is returned in *written.  `placed` receives
+ * after every 0xFF, cut at the end-of-image marker and zero-padded to a multiple of 4 plus 16 bytes,
+ * followed -- for a file with restart markers -- by a uint32 table of the byte offset at which each
+ * restart interval starts (0xFFFFFFFF for an interval whose marker is missing); at most
+ * oake_jpeg_stream_bound(parsed) bytes, the count is returned in *written.  `placed` receives
  * the descriptor rebased onto the caller's arenas: scan_off = stream_off (the offset `dst` will have
  * in the device `bytes` arena, a multiple of 4), out_off, and coefficient / plane offsets moved behind
  * *scratch_off, which is advanced by the image's (256-byte aligned) scratch size. */

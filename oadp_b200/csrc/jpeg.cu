@@ -8,8 +8,9 @@
 //                    sum of the blocks per subsequence places them, a last pass writes the coefficients,
 //                    a second prefix sum turns DC differences into DC values (jpeg_core.cuh, "parallel
 //                    entropy decode").  ~10^3 threads per COCO-sized file instead of one.
-//   serial kernel    files WITH restart markers (rare; the marker positions depend on the MCU count, which
-//                    a thread entering mid-stream does not know): one warp per image, lane 0 decodes.
+//   restart kernel   files WITH restart markers: the host has located every restart interval while it
+//                    copied the scan, each interval is an independent entry point -> one thread per
+//                    interval, one CTA per image.
 //   idct kernel      one thread per 8x8 block: dequantise, islow IDCT, range limit -> uint8 planes.
 //   colour kernel    one thread per four pixels: fancy chroma upsampling + YCbCr -> RGB, HWC stores.
 #include <cuda_runtime.h>
@@ -29,38 +30,45 @@ using namespace oake;
 
 namespace {
 
-__global__ void __launch_bounds__(32) jpeg_entropy_serial_kernel(const uint8_t* __restrict__ bytes,
-                                                          const oake_jpeg_desc* __restrict__ descs,
-                                                          uint8_t* __restrict__ scratch, int32_t* __restrict__ status) {
+constexpr int kRstThreads = 128;
+
+// Files WITH restart markers: every restart interval is an entry point the host has already located
+// (byte aligned, DC predictions reset), so one thread decodes one interval, serially, with absolute DC
+// values -- no synchronisation rounds and no prefix sums.  One CTA per image.
+__global__ void __launch_bounds__(kRstThreads) jpeg_entropy_rst_kernel(const uint8_t* __restrict__ bytes,
+                                                                      const oake_jpeg_desc* __restrict__ descs,
+                                                                      uint8_t* __restrict__ scratch,
+                                                                      int32_t* __restrict__ status) {
   __shared__ oake_jpeg_huff tables[4];  // dc0 dc1 ac0 ac1
-  // geometry part of the descriptor (everything in front of the quantisation tables): the only part
-  // decode_scan touches, kept next to the tables so that the serial loop never waits on global memory
+  // geometry part of the descriptor (everything in front of the quantisation tables): the only part the
+  // entropy decode touches, kept next to the tables so that the serial loops never wait on global memory
   // for it
   constexpr int kHeadBytes = offsetof(oake_jpeg_desc, quant);
   static_assert(kHeadBytes % 8 == 0, "descriptor layout");
   __shared__ __align__(16) uint8_t head[kHeadBytes];
-  const int lane = threadIdx.x;
-  if (descs[blockIdx.x].restart_interval == 0) return;  // the parallel kernel's share
+  const int tid = threadIdx.x;
+  if (descs[blockIdx.x].restart_interval == 0) return;  // the subsequence-parallel kernel's share
   {
     const oake_jpeg_desc& g = descs[blockIdx.x];
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&g.dc[0]);  // dc[2] and ac[2] are contiguous
     uint32_t* dst = reinterpret_cast<uint32_t*>(tables);
-    for (int i = lane; i < static_cast<int>(sizeof(tables) / 4); i += 32) dst[i] = src[i];
+    for (int i = tid; i < static_cast<int>(sizeof(tables) / 4); i += kRstThreads) dst[i] = src[i];
     const uint32_t* hs = reinterpret_cast<const uint32_t*>(&g);
-    for (int i = lane; i < kHeadBytes / 4; i += 32) reinterpret_cast<uint32_t*>(head)[i] = hs[i];
+    for (int i = tid; i < kHeadBytes / 4; i += kRstThreads) reinterpret_cast<uint32_t*>(head)[i] = hs[i];
   }
-  __syncwarp();
+  __syncthreads();
   const oake_jpeg_desc& d = *reinterpret_cast<const oake_jpeg_desc*>(head);
   for (uint32_t c = 0; c < d.ncomp; ++c) {
     const oake_jpeg_comp& k = d.comp[c];
     uint4* p = reinterpret_cast<uint4*>(scratch + k.coef_off);
     const uint32_t n16 = k.blocks_w * k.blocks_h * 8;  // 128 bytes per block
-    for (uint32_t i = lane; i < n16; i += 32) p[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = tid; i < n16; i += kRstThreads) p[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  __syncwarp();
-  if (lane == 0) {
-    status[blockIdx.x] = jpeg::decode_scan(d, bytes, tables, scratch);
-  }
+  __syncthreads();
+  int bad = 0;
+  for (uint32_t k = tid; k < d.restart_count; k += kRstThreads) bad |= jpeg::decode_interval(d, bytes + d.scan_off, tables, scratch, k);
+  bad = __syncthreads_or(bad);
+  if (tid == 0) status[blockIdx.x] = bad ? 1 : 0;
 }
 
 constexpr int kParThreads = 256;
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(kParThreads) jpeg_entropy_par_kernel(const uin
   __shared__ __align__(16) uint8_t head[kHeadBytes];
   __shared__ int warp_sums[kParThreads / 32];
   const int tid = threadIdx.x;
-  if (descs[blockIdx.x].restart_interval != 0) return;  // the serial kernel's share
+  if (descs[blockIdx.x].restart_interval != 0) return;  // the restart-interval kernel's share
   {
     const oake_jpeg_desc& g = descs[blockIdx.x];
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&g.dc[0]);
@@ -310,7 +318,7 @@ int oake_jpeg_decode(const uint8_t* bytes, const oake_jpeg_desc* descs_host, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* scr = static_cast<uint8_t*>(scratch);
   if (n_plain) jpeg_entropy_par_kernel<<<n, kParThreads, 0, st>>>(bytes, descs_dev, scr, status);
-  if (n_plain < n) jpeg_entropy_serial_kernel<<<n, 32, 0, st>>>(bytes, descs_dev, scr, status);
+  if (n_plain < n) jpeg_entropy_rst_kernel<<<n, kRstThreads, 0, st>>>(bytes, descs_dev, scr, status);
   jpeg_idct_kernel<<<dim3((max_blocks + 127) / 128, n), 128, 0, st>>>(descs_dev, scr);
   jpeg_colour_kernel<<<dim3((max_quads + 255) / 256, n), 256, 0, st>>>(descs_dev, scr, out);
   const cudaError_t e = cudaGetLastError();

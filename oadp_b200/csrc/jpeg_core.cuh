@@ -35,7 +35,7 @@ OAKE_HD constexpr int zigzag_pos(int natural) {
 // ------------------------------------------------------------------------------- entropy decode
 // The scan arrives "clean": the host has already dropped the 0x00 stuffed after every 0xFF data byte
 // and cut the segment at the first marker that is not RSTn (jpeg_parse.h, stage()), the stream starts
-// on a 4-byte boundary and is followed by at least 16 zero bytes.  That turns the refill into one
+// on a 4-byte boundary and is followed by at least 16 zero bytes (and then by the restart table).  That turns the refill into one
 // aligned 32-bit load per 32 consumed bits, requested one refill ahead of its use -- what matters in a
 // loop that is one long dependency chain run by a single thread.
 OAKE_HD uint32_t load_be32(const uint32_t* p) {
@@ -86,15 +86,6 @@ struct BitReader {
   }
   // bits of the stream consumed so far
   OAKE_HD uint64_t consumed() const { return static_cast<uint64_t>(pos - 1) * 32 - static_cast<uint64_t>(cnt); }
-  // end of a restart interval: drop the rest of the current byte, expect RSTn
-  OAKE_HD bool restart() {
-    skip(cnt & 7);  // words are whole bytes, so the misalignment of the read position is cnt mod 8
-    refill();
-    const uint32_t m = top32() >> 16;
-    skip(16);
-    refill();
-    return (m & 0xFFF8u) == 0xFFD0u;
-  }
 };
 
 // One Huffman symbol: returns (code length << 8) | symbol without consuming anything.  A code that is
@@ -119,23 +110,19 @@ OAKE_HD int32_t extend_after(uint32_t top, int len, int s) {
   return v - (static_cast<int32_t>(~t) >> 31 & ((1 << s) - 1));
 }
 
-// Entropy-decodes one whole image into zero-initialised coefficient blocks.  `tables`: the four
-// tables of the descriptor, dc[0], dc[1], ac[0], ac[1] (contiguous there; the kernels copy them to
-// shared memory).  Returns 0, or non-zero if the data was damaged / ran out.
-OAKE_HD int decode_scan(const oake_jpeg_desc& d, const uint8_t* bytes, const oake_jpeg_huff* tables, uint8_t* scratch) {
+// Serial entropy decode of MCUs [mcu_lo, mcu_hi) from a known entry point: byte `start` of the stream,
+// DC predictions zero -- the start of the scan or of a restart interval -- into zero-initialised
+// coefficient blocks.  `tables`: the four tables of the descriptor, dc[0], dc[1], ac[0], ac[1]
+// (contiguous there; the kernels copy them to shared memory).  `limit`: byte offset the data of this
+// range must not reach beyond.  Returns 0, or non-zero if the data was damaged / ran out.
+OAKE_HD int decode_mcu_range(const oake_jpeg_desc& d, const uint8_t* stream, const oake_jpeg_huff* tables,
+                             uint8_t* scratch, uint32_t mcu_lo, uint32_t mcu_hi, uint32_t start, uint32_t limit) {
   BitReader br;
-  br.start(bytes + d.scan_off, d.scan_len);
+  br.start_at(stream, d.scan_len, start * 8u);
   bool bad = false;
   int32_t pred[3] = {0, 0, 0};
-  const uint32_t n_mcus = d.mcus_x * d.mcus_y;
-  uint32_t until_restart = d.restart_interval;
-  uint32_t mx = 0, my = 0;
-  for (uint32_t m = 0; m < n_mcus; ++m) {
-    if (d.restart_interval != 0 && until_restart == 0) {
-      if (!br.restart()) bad = true;
-      pred[0] = pred[1] = pred[2] = 0;
-      until_restart = d.restart_interval;
-    }
+  uint32_t my = mcu_lo / d.mcus_x, mx = mcu_lo - my * d.mcus_x;
+  for (uint32_t m = mcu_lo; m < mcu_hi; ++m) {
     for (uint32_t c = 0; c < d.ncomp; ++c) {
       const oake_jpeg_comp& k = d.comp[c];
       const oake_jpeg_huff* dc = tables + k.dc_tbl;
@@ -172,13 +159,45 @@ OAKE_HD int decode_scan(const oake_jpeg_desc& d, const uint8_t* bytes, const oak
         }
       }
     }
-    --until_restart;
     if (++mx == d.mcus_x) {
       mx = 0;
       ++my;
     }
   }
-  return (bad || br.consumed() > d.scan_len * 8) ? 1 : 0;
+  return (bad || br.consumed() > static_cast<uint64_t>(limit) * 8) ? 1 : 0;
+}
+
+// Restart intervals: the host (jpeg_parse.h, stage()) leaves a table of the byte offset at which every
+// interval starts behind the stream; an interval nobody found is 0xFFFFFFFF.  Each interval is an
+// independent entry point (byte aligned, predictions reset), so one thread decodes one interval.
+constexpr uint32_t kNoInterval = 0xFFFFFFFFu;
+
+OAKE_HD const uint32_t* restart_table(const oake_jpeg_desc& d, const uint8_t* stream) {
+  return reinterpret_cast<const uint32_t*>(stream + ((d.scan_len + 3) & ~static_cast<uint64_t>(3)) + 16);
+}
+
+OAKE_HD int decode_interval(const oake_jpeg_desc& d, const uint8_t* stream, const oake_jpeg_huff* tables,
+                            uint8_t* scratch, uint32_t k) {
+  const uint32_t* table = restart_table(d, stream);
+  const uint32_t n_mcus = d.mcus_x * d.mcus_y;
+  const uint32_t lo = k * d.restart_interval;
+  const uint32_t hi = lo + d.restart_interval < n_mcus ? lo + d.restart_interval : n_mcus;
+  const uint32_t start = table[k];
+  if (start == kNoInterval) return 1;
+  // the data must end in front of the next RSTn marker (2 bytes), the last interval at the end of the scan
+  uint32_t limit = static_cast<uint32_t>(d.scan_len);
+  if (k + 1 < d.restart_count && table[k + 1] != kNoInterval) limit = table[k + 1] - 2;
+  return decode_mcu_range(d, stream, tables, scratch, lo, hi, start, limit);
+}
+
+// The whole image by one thread (CPU harness; the kernels spread intervals / subsequences over threads).
+OAKE_HD int decode_scan(const oake_jpeg_desc& d, const uint8_t* bytes, const oake_jpeg_huff* tables, uint8_t* scratch) {
+  const uint8_t* stream = bytes + d.scan_off;
+  if (d.restart_interval == 0)
+    return decode_mcu_range(d, stream, tables, scratch, 0, d.mcus_x * d.mcus_y, 0, static_cast<uint32_t>(d.scan_len));
+  int bad = 0;
+  for (uint32_t k = 0; k < d.restart_count; ++k) bad |= decode_interval(d, stream, tables, scratch, k);
+  return bad;
 }
 
 // ---------------------------------------------------------------- parallel entropy decode

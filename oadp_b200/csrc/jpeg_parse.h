@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/oake_b200.h"
 
@@ -214,6 +215,7 @@ inline int parse(const uint8_t* p, size_t len, oake_jpeg_desc* d, std::string* w
   d->scan_len = len - pos;
   // one slot per 1024 bits of entropy-coded data (jpeg_core.cuh kSubBits): entry state, exit state,
   // block count, first block -- 24 bytes
+  d->restart_count = d->restart_interval ? (d->mcus_x * d->mcus_y + d->restart_interval - 1) / d->restart_interval : 0;
   d->sync_slots = static_cast<uint32_t>((d->scan_len * 8 + 1023) / 1024 + 1);
   d->sync_off = off;
   off = align256(off + static_cast<uint64_t>(d->sync_slots) * 24);
@@ -223,11 +225,14 @@ inline int parse(const uint8_t* p, size_t len, oake_jpeg_desc* d, std::string* w
 }
 
 // Upper bound of what stage() writes for a file whose parsed descriptor is `d`.
-inline uint64_t stream_bound(const oake_jpeg_desc& d) { return ((d.scan_len + 3) & ~static_cast<uint64_t>(3)) + 16; }
+inline uint64_t stream_bound(const oake_jpeg_desc& d) {
+  return ((d.scan_len + 3) & ~static_cast<uint64_t>(3)) + 16 + 4 * static_cast<uint64_t>(d.restart_count);
+}
 
 // Copies the entropy-coded segment of `file` to `dst` WITHOUT the 0x00 stuffed after each 0xFF data byte,
 // cut at the first marker that is not RSTn and followed by >= 16 zero bytes (what jpeg_core.cuh's
-// BitReader expects), and rebases the descriptor: `placed` = `parsed` with scan_off = stream_off (the
+// BitReader expects) and then by the restart table (byte offset of the start of every restart interval,
+// 0xFFFFFFFF where the marker is missing), and rebases the descriptor: `placed` = `parsed` with scan_off = stream_off (the
 // offset `dst` will have in the device byte arena; a multiple of 4), scan_len = clean length, out_off,
 // and the coefficient / plane offsets moved behind *scratch_off (which is advanced).  Returns the bytes
 // written (a multiple of 4, <= stream_bound()).
@@ -236,6 +241,13 @@ inline uint64_t stage(const oake_jpeg_desc& parsed, const uint8_t* file, uint8_t
   const uint8_t* s = file + parsed.scan_off;
   const uint8_t* end = s + parsed.scan_len;
   uint8_t* o = dst;
+  // interval starts are collected here first: their place in `dst` depends on the clean length
+  std::vector<uint32_t> starts;
+  if (parsed.restart_count) {
+    starts.assign(parsed.restart_count, 0xFFFFFFFFu);
+    starts[0] = 0;
+  }
+  uint32_t next_interval = 1;
   while (s < end) {
     const uint8_t* ff = static_cast<const uint8_t*>(memchr(s, 0xFF, static_cast<size_t>(end - s)));
     const size_t run = static_cast<size_t>((ff ? ff : end) - s);
@@ -251,6 +263,7 @@ inline uint64_t stage(const oake_jpeg_desc& parsed, const uint8_t* file, uint8_t
       *o++ = 0xFF;
       *o++ = next;
       s += 2;
+      if (next_interval < parsed.restart_count) starts[next_interval++] = static_cast<uint32_t>(o - dst);
     } else if (next == 0xFF) {  // fill byte in front of a marker
       s += 1;
     } else {
@@ -258,8 +271,12 @@ inline uint64_t stage(const oake_jpeg_desc& parsed, const uint8_t* file, uint8_t
     }
   }
   const uint64_t clean = static_cast<uint64_t>(o - dst);
-  const uint64_t total = ((clean + 3) & ~static_cast<uint64_t>(3)) + 16;
+  uint64_t total = ((clean + 3) & ~static_cast<uint64_t>(3)) + 16;
   memset(o, 0, static_cast<size_t>(total - clean));
+  if (parsed.restart_count) {
+    memcpy(dst + total, starts.data(), 4 * starts.size());
+    total += 4 * starts.size();
+  }
   if (placed != &parsed) *placed = parsed;
   const uint64_t base = align256(*scratch_off);
   for (uint32_t c = 0; c < placed->ncomp; ++c) {

@@ -38,8 +38,7 @@ class JpegSource:
         width, height = struct.unpack_from('<II', desc, 0)
         self.shape = (height, width, 3)
         self.scratch_bytes = _scratch_bytes(desc)
-        scan_len = struct.unpack_from('<Q', desc, 48)[0]
-        self.stream_bound = (scan_len + 3) // 4 * 4 + 16  # what oake_jpeg_stage writes at most
+        self.stream_bound = int(binding.load().oake_jpeg_stream_bound(desc))  # what oake_jpeg_stage writes at most
 
     @property
     def size(self) -> int:

@@ -15,8 +15,8 @@ using namespace oake;
 extern "C" {
 
 // Returns the parser's code (0 ok, 1 malformed, 2 unsupported), or 3 if the entropy data was damaged.
-// parallel != 0: the subsequence-parallel entropy decode (files without restart markers), else the
-// serial one; *sync_rounds (optional) = rounds step 2 needed.
+// parallel != 0: the subsequence-parallel entropy decode (files without restart markers; files with them
+// are decoded interval by interval either way), else the serial one; *sync_rounds (optional) = rounds step 2 needed.
 // `out` must hold width * height * 3 bytes (call with out == NULL first to get the size).
 int harness_decode(const uint8_t* data, size_t len, uint8_t* out, int* width, int* height, int parallel, int* sync_rounds) {
   oake_jpeg_desc d;

@@ -125,8 +125,28 @@ def test_stage_strips_stuffing_and_rebases_offsets(lib):
     assert scan.count(b'\xff\x00') > 0
     want = scan[:scan.rindex(b'\xff\xd9')].replace(b'\xff\x00', b'\xff')
     assert scan_len == len(want) and dst.raw[:scan_len] == want and b'\xff\xd0' in want
-    assert written.value == (scan_len + 3) // 4 * 4 + 16 <= src.stream_bound
-    assert dst.raw[scan_len:written.value] == bytes(written.value - scan_len)
+    # ... then the restart table: where each of the 16 MCUs / 2 = 8 intervals starts in the clean stream
+    mcus_x, mcus_y, interval = struct.unpack_from('<3I', placed.raw, 20)
+    count = struct.unpack_from('<I', placed.raw, 80)[0]
+    assert (mcus_x * mcus_y, interval, count) == (16, 2, 8)
+    table_at = (scan_len + 3) // 4 * 4 + 16
+    assert written.value == table_at + 4 * count <= src.stream_bound
+    assert dst.raw[scan_len:table_at] == bytes(table_at - scan_len)
+    starts = list(struct.unpack_from('<8I', dst.raw, table_at))
+    # (markers can only be told from data in the raw scan, where a data byte 0xFF is followed by 0x00)
+    markers, i, clean = [], 0, 0
+    while i < len(scan) - 1:
+        if scan[i] == 0xFF and scan[i + 1] == 0x00:
+            i, clean = i + 2, clean + 1
+        elif scan[i] == 0xFF and 0xD0 <= scan[i + 1] <= 0xD7:
+            i, clean = i + 2, clean + 2
+            markers.append(clean)
+        elif scan[i] == 0xFF:
+            break
+        else:
+            i, clean = i + 1, clean + 1
+    assert starts == [0] + markers and len(markers) == 7
+    # a file that lost one of its markers: the interval nobody found is flagged, the decode reports it
     assert dst.raw[written.value:] == b'\xaa' * (len(dst.raw) - written.value)
     assert lib.oake_jpeg_stage(src.desc, data, len(data) - 1, dst, 0, 0, ctypes.byref(scratch), placed,
                                ctypes.byref(written)) != 0  # not the file the descriptor came from
@@ -205,3 +225,14 @@ def test_damaged_files_never_touch_memory_out_of_bounds(tmp_path):
     assert run.returncode == 0, run.stderr[-2000:]
     assert 'runtime error' not in run.stderr and 'AddressSanitizer' not in run.stderr, run.stderr[-2000:]
     assert run.stdout.startswith(f'records {n} decoded ')
+
+
+def test_missing_restart_marker_is_reported(harness):
+    rng = np.random.default_rng(6)
+    buf = io.BytesIO()
+    PIL.Image.fromarray(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)).save(buf, 'JPEG', quality=90,
+                                                                                  restart_marker_blocks=2)
+    data = buf.getvalue()
+    assert harness(data)[0] == 0
+    i = data.index(b'\xff\xd3')
+    assert harness(data[:i] + data[i + 2:])[0] == 3  # RST3 cut out: intervals no longer line up
