@@ -270,6 +270,37 @@ int oake_jpeg_stage(const oake_jpeg_desc* parsed, const uint8_t* file, size_t le
 int oake_jpeg_decode(const uint8_t* bytes, const oake_jpeg_desc* descs_host, const oake_jpeg_desc* descs_dev, int n,
                      void* scratch, uint8_t* out, int32_t* status, void* stream);
 
+/* ---- CLIP text tower (second half; oadp/prompts/vild.py:56-72 `model.encode_text(tokens)`) --
+ * openai/CLIP ViT-B/32 text encoder: width 512, 8 heads, MLP 2048, causal attention over <= 77 tokens,
+ * ln_final, the row of the EOT token (argmax of the ids) times text_projection.  Layer weights use
+ * oake_layer_weights with the text shapes (qkv [1536,512], out [512,512], fc1 [2048,512], fc2 [512,2048];
+ * ln_1 / ln_2 folded as for the image tower).  NOT YET RUN ON A GPU (see oadp_b200/csrc/text.cu). */
+typedef struct oake_text_handle oake_text_handle;
+
+typedef struct {
+  int32_t layers;  /* 12 */
+  int32_t width;   /* 512 */
+  int32_t heads;   /* 8 */
+  int32_t vocab;   /* 49408 */
+  int32_t context; /* rows of `pos`, <= 77 */
+  int32_t out_dim; /* 512 */
+  const float* token_emb;  /* token_embedding.weight   [vocab, 512] fp32 */
+  const float* pos;        /* positional_embedding     [context, 512] fp32 */
+  const float* ln_final_w; /* [512] */
+  const float* ln_final_b; /* [512] */
+  const void* proj_w;      /* text_projection^T        [512, 512] act, row = output feature */
+  const oake_layer_weights* layer; /* host array [layers] of device pointers; copied at create */
+} oake_text_weights;
+
+int oake_text_create(oake_text_handle** out, int device, const oake_text_weights* weights);
+void oake_text_destroy(oake_text_handle* h);
+int oake_text_workspace_bytes(const oake_text_handle* h, int max_sequences, int length, size_t* out_bytes);
+/* tokens: device int32 [B, L] (L <= context; SOT ... EOT, zero padded, as clip.tokenize produces them);
+ * out_f32: device fp32 [B, out_dim], NOT normalised (the prompt builder normalises per template and
+ * averages, prompts/vild.py:66-71). */
+int oake_encode_text(oake_text_handle* h, const int32_t* tokens, int B, int L, float* out_f32, void* ws,
+                     size_t ws_bytes, void* stream);
+
 /* Error string of the last failing call on this thread ("" if none). */
 const char* oake_last_error(void);
 /* "f16" or "bf16": element type of `act` tensors. */

@@ -29,6 +29,12 @@ class Weights(C.Structure):
     ] + [('layer', C.POINTER(LayerWeights))]
 
 
+class TextWeights(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('layers', 'width', 'heads', 'vocab', 'context', 'out_dim')] + [
+        (n, C.c_void_p) for n in ('token_emb', 'pos', 'ln_final_w', 'ln_final_b', 'proj_w')
+    ] + [('layer', C.POINTER(LayerWeights))]
+
+
 # name -> (restype, argtypes); every symbol include/oake_b200.h declares
 SIGNATURES = {
     'oake_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Weights)]),
@@ -68,6 +74,11 @@ SIGNATURES = {
     'oake_jpeg_stage': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_uint64,
                                   C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]),
     'oake_jpeg_decode': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    'oake_text_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(TextWeights)]),
+    'oake_text_destroy': (None, [C.c_void_p]),
+    'oake_text_workspace_bytes': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    'oake_encode_text': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                    C.c_void_p]),
     'oake_last_error': (C.c_char_p, []),
     'oake_act_dtype': (C.c_char_p, []),

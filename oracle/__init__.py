@@ -22,6 +22,8 @@ oadp/base/globals_.py) with importlib on stand-ins for the third-party packages
   (objects.py:198-314) driving ``model.visual(o, m)``: max-abs < 3e-5 at full depth.
 * ``vit.encode_image`` against ``model.encode_image`` as called by globals.py:57 / blocks.py:129.
 * ``classifier`` against ``BaseClassifier`` / ``Classifier`` / ``ViLDClassifier``.
+* ``text.encode_text`` (the CLIP text tower behind oadp/prompts/vild.py:56-72) against HuggingFace
+  ``CLIPTextModelWithProjection`` under ``text.to_hf_state_dict`` (``tests/test_oracle_text.py``).
 * ``jpeg.decode`` IS the reference's loader (``PIL.Image.open(f).convert('RGB')``, base.py:53):
   Pillow runs here and on the GPU box, so that row needs no restatement.
 
