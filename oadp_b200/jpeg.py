@@ -20,6 +20,9 @@ import numpy as np
 from . import binding
 
 UNSUPPORTED = 2
+# Pillow warns above Image.MAX_IMAGE_PIXELS (89 478 485) and raises above twice that; a header claiming more
+# than the warning threshold is not worth a GPU arena
+MAX_PIXELS = 89_478_485
 
 
 def desc_bytes() -> int:
@@ -59,7 +62,10 @@ def parse(data: bytes) -> Optional[JpegSource]:
     if rc == UNSUPPORTED:
         return None
     binding.check(rc)
-    return JpegSource(data, buf.raw)
+    src = JpegSource(data, buf.raw)
+    if src.shape[0] * src.shape[1] > MAX_PIXELS:
+        return None  # left to Pillow, whose decompression-bomb check then speaks (as in the reference)
+    return src
 
 
 def load(path) -> Union[JpegSource, np.ndarray]:

@@ -236,3 +236,12 @@ def test_missing_restart_marker_is_reported(harness):
     assert harness(data)[0] == 0
     i = data.index(b'\xff\xd3')
     assert harness(data[:i] + data[i + 2:])[0] == 3  # RST3 cut out: intervals no longer line up
+
+
+def test_absurd_frame_size_is_left_to_pillow(lib):
+    buf = io.BytesIO()
+    PIL.Image.fromarray(np.zeros((16, 16, 3), np.uint8)).save(buf, 'JPEG')
+    data = bytearray(buf.getvalue())
+    j = bytes(data).find(b'\xff\xc0')
+    data[j + 5:j + 9] = struct.pack('>HH', 60000, 60000)  # 3.6 gigapixels in the header, 16 x 16 of data
+    assert oake_jpeg.parse(bytes(data)) is None
