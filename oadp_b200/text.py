@@ -6,9 +6,8 @@ kernels, oadp_b200/csrc/text.cu); `build_prompts` reproduces the loop of prompts
 template: format every category name, tokenize, encode, `F.normalize`; then the mean over the templates
 -- and returns the `{embeddings, names}` dict the classifiers load (oadp/dp/classifiers.py:27-41).
 
-STATUS: written after round 1's GPU budget was spent -- compiled, weights packing and host logic tested on
-the CPU, the oracle (oracle/text.py) pinned against HuggingFace CLIP; tests/test_gpu_text.py has not run
-on a B200 yet and is opt-in (OAKE_TEXT_TOWER=1) until it has.
+Parity: tests/test_gpu_text.py (1, 2 and 12 layers, context 16 / 20 / 77) against oracle/text.py, which is
+pinned to HuggingFace CLIP; first B200 run, memcheck and timing in profiles/r2_01_text_tower_*.
 
 The tokenizer is not part of this package (CLIP's BPE vocabulary cannot be fetched offline): pass
 `clip.tokenize` / the fork's `clip.adaptively_tokenize`, or any callable texts -> int tensor (B, L <= 77).
@@ -103,6 +102,7 @@ class OakeTextModel:
             setattr(w, k, base + offsets[k])
         w.layer = C.cast(self._layer_array, C.POINTER(binding.LayerWeights))
         self.context = context
+        self.vocab = vocab
         handle = C.c_void_p()
         binding.check(self.lib.oake_text_create(C.byref(handle), self.device.index, C.byref(w)))
         self._handle = handle
@@ -126,6 +126,9 @@ class OakeTextModel:
         """tokens (B, L <= 77) integer -> (B, 512) fp32 on the device, un-normalised."""
         if tokens.dim() != 2 or not 1 <= tokens.shape[1] <= self.context:
             raise ValueError(f'tokens must be (B, L) with 1 <= L <= {self.context}, got {tuple(tokens.shape)}')
+        if tokens.numel() and bool(((tokens < 0) | (tokens >= self.vocab)).any()):
+            # an id outside the embedding table is a tokenizer / vocabulary mismatch, never data
+            raise ValueError(f'token ids must lie in [0, {self.vocab}); got [{int(tokens.min())}, {int(tokens.max())}]')
         tokens = tokens.to(self.device, torch.int32).contiguous()
         n, length = tokens.shape
         out = torch.empty(n, OUT_DIM, dtype=torch.float32, device=self.device)
