@@ -39,9 +39,21 @@ GFLOP_T50 = 8.818  # algorithmic GFLOP per crop, T=50
 GFLOP_T197 = 33.552  # T=197 + side stream with shared K/V
 WEIGHT_SEED = 1234
 PROPOSALS_PER_IMAGE = 300
-# dram__bytes_read.sum + dram__bytes_write.sum of one c_fc launch at M = 94 644 (478 objects crops), from
-# profiles/r1_04_ncu_gemm_summary.txt; algorithmic bytes of that launch: 145 MB (A) + 4.7 MB (W) + 581 MB (out)
-NCU_TRAFFIC_FC1 = 685.8e6
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class, averaged
+# over the launches of ONE step of this same command under `ncu --set full` restricted to the class's NVTX range
+# (tools/gpu_profile.sh -> tools/ncu_traffic.py -> profiles/ncu_traffic.json).  Used only if the capture saw the
+# same average rows per launch as this run (same step mix); otherwise null.
+NCU_TRAFFIC_FILE = ROOT / 'profiles' / 'ncu_traffic.json'
+
+
+def ncu_traffic(kernel_class: str, flops_per_launch: float):
+    try:
+        ent = json.loads(NCU_TRAFFIC_FILE.read_text())[kernel_class]
+        if abs(ent['flops_per_launch'] - flops_per_launch) <= 0.01 * flops_per_launch:
+            return float(ent['dram_bytes_per_launch'])
+    except Exception:
+        pass
+    return None
 
 
 def peaks():
@@ -157,6 +169,109 @@ def workload_counts(imgs, props):
     return dict(globals=len(imgs), blocks=blocks, objects=objects)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# library_baseline: the strongest existing GPU implementation on the same box
+# ------------------------------------------------------------------------------------------------
+def library_baseline(counts, kinds, steps: int, warmup: int, dev):
+    """The oracle tower (oracle/vit.py, unchanged code) in fp16 on THIS GPU under PyTorch eager: cuDNN
+    conv, cuBLAS linears, ATen LayerNorm / softmax -- what the reference's `model.half().cuda()` runs --
+    and the same with the attention product routed through `F.scaled_dot_product_attention` (flash /
+    cuDNN kernels), the better of the two reported.  A baseline leg like `cpu_baseline`: the only other
+    place this file executes `oracle/`.  Inputs are synthetic CLIP-normalised pixel tensors of the step's
+    shapes (the tower's time does not depend on pixel values); all crops of a kind travel as ONE batch
+    (objects in chunks of 512, objects.py:323-327) -- more favourable to the library than the reference's
+    own B=1 / per-image batches.  `device`: pixels resident in HBM as fp16.  `e2e`: pinned fp32 pixels
+    (what the reference's DataLoader hands over, 602 KB per crop) -> H2D -> tower -> fp16 rows -> host."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import vit
+    p16 = {k: v.to(dev, torch.float16) for k, v in vit.init_visual_params(WEIGHT_SEED).items()}
+    p197 = vit.objects_surgery(p16)
+    g = torch.Generator(device='cpu').manual_seed(5)
+    eager_attend = vit._attend
+
+    def sdpa_attend(q, k, v, bias=None):
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=None if bias is None else bias.to(q.dtype).expand(
+            q.shape[0], q.shape[1], q.shape[2], k.shape[2]))
+        b, h, nq, dh = o.shape
+        return o.transpose(1, 2).reshape(b, nq, h * dh)
+
+    # `vit.encode_image` / `vit.encode_objects` with their `.float()` casts removed -- the same block, side
+    # stream and head functions of oracle/vit.py, driven in the parameters' dtype (fp16)
+    @torch.no_grad()
+    def encode_image(px):
+        x = vit.embed(p16, px, stride=vit.PATCH, padding=0)
+        for i in range(vit.num_layers(p16)):
+            x = vit._block(x, p16, i)
+        return vit.head(p16, x[:, 0])
+
+    @torch.no_grad()
+    def encode_objects(px, masks):
+        x = vit.embed(p197, px, stride=vit.PATCH // 2, padding=(vit.PATCH - 1) // 2)
+        bias = vit.mask_to_bias(masks)[:, None, None, :].to(x.dtype)
+        y = x[:, :1]
+        for i in range(vit.num_layers(p197)):
+            pre = f'transformer.resblocks.{i}.'
+            z = vit._ln(torch.cat([x[:, 1:], y], dim=1), p197, pre + 'ln_1')
+            qkv = z @ p197[pre + 'attn.in_proj_weight'].T + p197[pre + 'attn.in_proj_bias']
+            q, k, v = qkv.split(vit.WIDTH, dim=-1)
+            o = vit._attend(vit._heads(q[:, -1:]), vit._heads(k), vit._heads(v), bias)
+            y = y + o @ p197[pre + 'attn.out_proj.weight'].T + p197[pre + 'attn.out_proj.bias']
+            y = y + vit._mlp(vit._ln(y, p197, pre + 'ln_2'), p197, pre)
+            x = vit._block(x, p197, i)
+        return vit.head(p197, y[:, 0])
+
+    def run(kind, px, masks):
+        if kind == 'objects':
+            out = [vit.normalize_half(encode_objects(px[s:s + 512], masks[s:s + 512]))
+                   for s in range(0, px.shape[0], 512)]
+            return torch.cat(out)
+        return vit.normalize_half(encode_image(px))
+
+    def timed(fn, n):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / n
+
+    out = {}
+    try:
+        for kind in kinds:
+            n = counts[kind]
+            host = torch.randn(n, 3, 224, 224, generator=g).pin_memory()
+            masks_host = (torch.rand(n, 1, 14, 14, generator=g) < 0.5).float().pin_memory()
+            px = host.to(dev, torch.float16)
+            masks = masks_host.to(dev, torch.float16)
+
+            def device_fn():
+                return run(kind, px, masks)
+
+            def e2e_fn():
+                x = host.to(dev, non_blocking=True).half()
+                m = masks_host.to(dev, non_blocking=True).half()
+                return run(kind, x, m).cpu()
+
+            res = {}
+            for name, attend in (('eager', eager_attend), ('sdpa', sdpa_attend)):
+                vit._attend = attend
+                n_steps = max(2, min(steps, 5))
+                res[name] = dict(device=n / timed(device_fn, n_steps), e2e=n / timed(e2e_fn, n_steps))
+            best = max(res, key=lambda k: res[k]['device'])
+            out[kind] = dict(crops=n, device=res[best]['device'], e2e=max(r['e2e'] for r in res.values()), best=best,
+                             eager=res['eager'], sdpa=res['sdpa'])
+            del host, masks_host, px, masks
+            torch.cuda.empty_cache()
+    finally:
+        vit._attend = eager_attend
+    return out
+
 # ------------------------------------------------------------------------------------------------
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -167,6 +282,7 @@ def main() -> None:
     ap.add_argument('--workload', default='oake', choices=['oake', 'globals', 'blocks', 'objects'])
     ap.add_argument('--images', type=int, default=8, help='images per step per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-library-baseline', action='store_true')
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -340,7 +456,8 @@ def main() -> None:
         achieved = d['flops'] / (d['ms'] * 1e-3) / 1e12
         all_ach = sum(v['flops'] for v in gemm.values()) / (sum(v['ms'] for v in gemm.values()) * 1e-3) / 1e12
         roof = dict(bound='tensor', kernel=f'gemm_tcgen05_kernel ({dom})', achieved=achieved, peak=pk['tflops_sustained'],
-                    unit='TFLOP/s', frac=achieved / pk['tflops_sustained'], traffic=NCU_TRAFFIC_FC1,
+                    unit='TFLOP/s', frac=achieved / pk['tflops_sustained'],
+                    traffic=ncu_traffic(dom, d['flops'] / d['launches']),
                     peak_source=f"{pk['source']} bf16 cuBLAS, sustained (kernel timed inside a long step)",
                     flops_per_launch=d['flops'] / d['launches'], us_per_launch=d['ms'] / d['launches'] * 1e3,
                     share_of_step=d['ms'] / tot_ms,
@@ -358,6 +475,54 @@ def main() -> None:
             dist.destroy_process_group()
         return
 
+    # ---------------------------------------------------------------- library baseline (N=1, rank 0)
+    library = None
+    if not args.no_library_baseline and world == 1:
+        def ours_kind(k, n):
+            for _ in range(2):
+                pipes[k].launch(jobs[k])
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                pipes[k].launch(jobs[k])
+            b.record()
+            torch.cuda.synchronize()
+            dev_cps = counts[k] * n / (a.elapsed_time(b) * 1e-3)
+            sub = dict(globals=lambda: pipes[k].submit_globals(imgs), blocks=lambda: pipes[k].submit_blocks(imgs),
+                       objects=lambda: pipes[k].submit_objects(imgs, props))[k]
+            sub().result()
+            t0_ = time.perf_counter()
+            pend = None
+            for _ in range(n):
+                new = sub()
+                if pend is not None:
+                    pend.result()
+                pend = new
+            pend.result()
+            e2e_cps = counts[k] * n / (time.perf_counter() - t0_)
+            jobs[k] = pipes[k].stage(*plan(k))
+            pipes[k].upload(jobs[k])
+            torch.cuda.synchronize()
+            return dev_cps, e2e_cps
+
+        lib = library_baseline(counts, kinds, args.steps, 2, dev)
+        per = {}
+        for k in kinds:
+            o_dev, o_e2e = ours_kind(k, max(3, min(args.steps, 10)))
+            per[k] = dict(crops_per_step=counts[k], ours=o_dev, library=lib[k]['device'], ratio=o_dev / lib[k]['device'],
+                          ours_e2e=o_e2e, library_e2e=lib[k]['e2e'], ratio_e2e=o_e2e / lib[k]['e2e'],
+                          library_best=lib[k]['best'], library_eager=lib[k]['eager'], library_sdpa=lib[k]['sdpa'])
+        lib_step_s = sum(counts[k] / lib[k]['device'] for k in kinds)
+        lib_e2e_s = sum(counts[k] / lib[k]['e2e'] for k in kinds)
+        library = dict(kind='torch %s eager fp16 on the same GPU: oracle/vit.py blocks (cuDNN conv, cuBLAS linears, '
+                            'ATen LayerNorm/softmax or SDPA), all crops of a kind in one batch' % torch.__version__,
+                       value=crops_per_step / lib_step_s, unit='crops/s', e2e=crops_per_step / lib_e2e_s,
+                       ratio=value / (crops_per_step / lib_step_s), ratio_e2e=e2e_value / (crops_per_step / lib_e2e_s),
+                       front_end='none: pixel tensors are given (the reference prepares them with PIL on the host); '
+                                 'ours includes crop + resize + normalise from the uint8 images',
+                       per_workload=per)
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         ref = cpu_reference(args.workload, args.images, 3, 1)
@@ -367,7 +532,7 @@ def main() -> None:
     line = dict(metric='OAKE crops/sec (ViT-B/32, 224^2, synthetic COCO proposals)', value=value, unit='crops/s',
                 n_gpus=world, steps=args.steps, warmup=warmup, ms_per_step=ms / args.steps, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f16', data='synthetic', config=cfg, roofline=roof,
-                cpu_baseline=cpu,
+                cpu_baseline=cpu, library_baseline=library,
                 e2e=dict(value=e2e_value, unit='crops/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          steps=e2e_steps),
                 gpu_launches=launches, clocks=clocks)

@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/oake_b200.h"
 #include "kernels.cuh"
 
@@ -167,7 +169,11 @@ struct Launcher {
       pe.b = get_event(h);
       cudaEventRecord(pe.a, st);
     }
+    // one NVTX range per kernel class: `ncu --nvtx --nvtx-include "gemm_fc1/"` / nsys timelines can tell the
+    // QKV and c_fc launches of the one GEMM instantiation apart (header-only NVTX3: a no-op without a tool)
+    nvtxRangePushA(kClassNames[cls]);
     err = f();
+    nvtxRangePop();
     if (err != cudaSuccess) where = kClassNames[cls];
     h->launches += 1;
     if (h->profiling) {

@@ -318,7 +318,9 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
 
 // ------------------------------------------------------------------------------------------------
 // objects.py:129-155 masks.  box = the expanded square (float xyxy), fg = proposal - box.lt.
-// x = arange(x2 - x1) (ceil(double width) float samples), inside iff fg0 <= x <= fg2; the bool mask
+// x = arange(x2 - x1): the reference iterates todd BBoxes, which yields PYTHON floats (PIL's `crop` needs
+// them: round(Tensor) raises), so x2 - x1 is a double difference of two fp32 values and arange takes its
+// ceiling -- ceil(double width) samples, not ceilf of an fp32 difference.  Inside iff fg0 <= x <= fg2; the bool mask
 // is resampled to 14x14 by F.interpolate(mode='nearest'): src = min(floor(dst * (n / 14.f)), n - 1).
 // Output 1 = background.
 // ------------------------------------------------------------------------------------------------

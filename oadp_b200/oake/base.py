@@ -109,8 +109,11 @@ def parse_args(argv: Optional[Sequence[str]] = None) -> argparse.Namespace:
 
 def default_params() -> Dict[str, torch.Tensor]:
     """Stand-in for `clip.load_default`: a ViT-B/32 state dict named by $OAKE_CLIP_WEIGHTS
-    (OpenAI `visual.*` names, e.g. exported from the official checkpoint), else seeded random
-    weights -- no CLIP checkpoint exists in this offline environment."""
+    (OpenAI `visual.*` names, e.g. exported from the official checkpoint).  Without it the call FAILS,
+    as `clip.load_default` does when the checkpoint is missing -- features of random weights written
+    into a real output directory would be taken for finished work by every later resume.  Seeded
+    random weights (no CLIP checkpoint exists offline) are an explicit opt-in for tests, the bench
+    and dry runs: `DRY_RUN=True` or `OAKE_ALLOW_RANDOM_WEIGHTS=1`."""
     import os
     path = os.environ.get('OAKE_CLIP_WEIGHTS')
     if path:
@@ -119,8 +122,11 @@ def default_params() -> Dict[str, torch.Tensor]:
         return {k[len('visual.'):] if k.startswith('visual.') else k: v.float() for k, v in sd.items()
                 if k.startswith('visual.') or k in ('proj', 'class_embedding', 'positional_embedding') or
                 k.startswith(('conv1.', 'ln_pre.', 'ln_post.', 'transformer.'))}
+    if not (Store.DRY_RUN or os.environ.get('OAKE_ALLOW_RANDOM_WEIGHTS') == '1'):
+        raise RuntimeError('OAKE_CLIP_WEIGHTS is not set: point it at a CLIP ViT-B/32 state dict (visual.* names). '
+                           'Set OAKE_ALLOW_RANDOM_WEIGHTS=1 (or DRY_RUN=True) to run on seeded random weights.')
     from .. import synth
-    print('OAKE_CLIP_WEIGHTS is not set: using seeded random ViT-B/32 weights', flush=True)
+    print('OAKE_CLIP_WEIGHTS is not set: using seeded random ViT-B/32 weights (explicit opt-in)', flush=True)
     return synth.visual_params(0)
 
 

@@ -109,6 +109,18 @@ class _Staging:
     def upload(self, nbytes: int) -> None:
         self.dev[:nbytes].copy_(self.host[:nbytes], non_blocking=True)
 
+    def upload_ranges(self, ranges: Sequence[Tuple[int, int]]) -> int:
+        """Copies only [lo, hi) byte ranges (adjacent ones merged); -> bytes sent."""
+        merged: List[List[int]] = []
+        for lo, hi in sorted(ranges):
+            if merged and lo <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], hi)
+            else:
+                merged.append([lo, hi])
+        for lo, hi in merged:
+            self.dev[lo:hi].copy_(self.host[lo:hi], non_blocking=True)
+        return sum(hi - lo for lo, hi in merged)
+
 
 class _Slot:
     """One in-flight batch: its staging buffers, its result buffer and the event that ends it."""
@@ -163,7 +175,9 @@ class Pending:
                 self._error = binding.OakeError(f'oake_jpeg_decode: damaged or truncated entropy-coded data in '
                                                 f'compressed image(s) {bad} of the batch')
                 return
-        self._done = self._finish(self._host.clone())
+        # `finish` copies what it keeps out of the slot's pinned buffer: one tensor with its OWN storage per
+        # stored item (torch.save writes the whole storage behind a view)
+        self._done = self._finish(self._host)
 
     def result(self):
         self.collect()
@@ -235,7 +249,7 @@ class OakePipeline:
 
     def _run(self, *plan_args) -> torch.Tensor:
         """Synchronous form: returns the HOST fp16 (n_crops, 512) tensor."""
-        return self._submit(plan_args, lambda emb: emb).result()
+        return self._submit(plan_args, lambda emb: emb.clone()).result()
 
     # The three phases are public so that bench.py can time the device-resident part alone.
     def stage(self, images, img_offs, img_bytes, arena_bytes, stages, crops, variant, fg=None, box=None) -> dict:
@@ -266,16 +280,17 @@ class OakePipeline:
         for o, b in parts:
             mh[o:o + b.size] = b
         ah = self._arena.host.numpy()
-        compressed = []
+        compressed, raw_ranges = [], []
         for im, o in zip(images, img_offs):
             if isinstance(im, oake_jpeg.JpegSource):
                 compressed.append((im, o))
             else:
                 ah[o:o + im.size] = im.reshape(-1)
+                raw_ranges.append((o, _align(o + im.size)))
         jpeg_job = self._stage_jpeg(compressed, fresh) if compressed else None
         self._slot.jpeg_count = len(compressed)
         return dict(n=n, variant=variant, img_bytes=img_bytes, meta_host_bytes=meta_host_bytes, jpeg=jpeg_job,
-                    raw_images=len(images) - len(compressed),
+                    raw_images=len(images) - len(compressed), raw_ranges=raw_ranges if compressed else None,
                     stages=[(j.size, frontend.max_tiles(j), o) for j, o in zip(stages, stage_offs)],
                     crops_off=crops_off, fg_off=fg_off, box_off=box_off, masks_off=masks_off)
 
@@ -326,8 +341,15 @@ class OakePipeline:
     def upload(self, job: dict) -> None:
         self.h2d_bytes = job['meta_host_bytes']
         if job['raw_images']:  # (a batch of compressed files only has nothing to send here)
-            self._arena.upload(job['img_bytes'])
-            self.h2d_bytes += job['img_bytes']
+            if job.get('raw_ranges'):
+                # Mixed batch (`jpeg.load` hands progressive / CMYK / non-JPEG files over as Pillow-decoded
+                # arrays): the decode stream writes the other images' pixels into this same arena, unordered
+                # against the main stream, so only the byte ranges of the raw images may be copied here --
+                # a whole-arena copy could land after the decode and bury it under stale staging bytes.
+                self.h2d_bytes += self._arena.upload_ranges(job['raw_ranges'])
+            else:
+                self._arena.upload(job['img_bytes'])
+                self.h2d_bytes += job['img_bytes']
         if job['meta_host_bytes']:
             self._meta.upload(job['meta_host_bytes'])
         jj = job['jpeg']
@@ -407,7 +429,7 @@ class OakePipeline:
 
     def submit_globals(self, images: Sequence[np.ndarray]) -> Pending:
         n = len(images)
-        return self._submit(self.plan_globals(images), lambda emb: [emb[i] for i in range(n)])
+        return self._submit(self.plan_globals(images), lambda emb: [emb[i].clone() for i in range(n)])
 
     def plan_globals(self, images: Sequence[np.ndarray]) -> tuple:
         offs, img_bytes = self._place_images(images)
@@ -433,7 +455,7 @@ class OakePipeline:
         def finish(emb: torch.Tensor):
             out, s = [], 0
             for plan, n in zip(plans, counts):
-                out.append(dict(embeddings=emb[s:s + n], bboxes=_bboxes_half(plan).clone()))
+                out.append(dict(embeddings=emb[s:s + n].clone(), bboxes=_bboxes_half(plan).clone()))
                 s += n
             return out
 
@@ -483,7 +505,7 @@ class OakePipeline:
             out, s = [], 0
             for plan in plans:
                 n = plan.bboxes.shape[0]
-                out.append(dict(embeddings=emb[s:s + n], bboxes=torch.from_numpy(plan.bboxes).half(),
+                out.append(dict(embeddings=emb[s:s + n].clone(), bboxes=torch.from_numpy(plan.bboxes).half(),
                                 objectness=torch.from_numpy(plan.objectness).half()))
                 s += n
             return out

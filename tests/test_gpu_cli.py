@@ -20,6 +20,12 @@ def dataset(tmp_path_factory, lib):
     return synth.write_coco_dataset(tmp_path_factory.mktemp('coco'), 5, seed=2, n_proposals=20)
 
 
+@pytest.fixture(autouse=True)
+def random_weights_opt_in(monkeypatch):
+    # no CLIP checkpoint exists offline: the CLI runs on seeded random weights only when told to
+    monkeypatch.setenv('OAKE_ALLOW_RANDOM_WEIGHTS', '1')
+
+
 def cos_ok(got, want):
     return float((1 - F.cosine_similarity(got.float(), want.float(), dim=-1)).max()) < 1e-3
 
@@ -43,6 +49,9 @@ def test_cli_all_tasks(dataset, monkeypatch):
         assert [f.stem for f in files] == [f'{i:012d}' for i in dataset['ids']]
     g = torch.load(root / 'oake' / 'globals' / 'val' / f'{id0:012d}.pth')
     assert g.shape == (512, ) and g.dtype == torch.float16
+    # each file holds its own rows only, not the storage of the whole batch behind a view
+    assert g.untyped_storage().nbytes() == 1024
+    assert (root / 'oake' / 'globals' / 'val' / f'{id0:012d}.pth').stat().st_size < 4096
     assert cos_ok(g[None], vit.normalize_half(vit.encode_image(p, ofe.globals_preprocess(pil)[None])))
 
     cli_blocks.Validator.main(['t', dataset['configs']['blocks']])
@@ -51,6 +60,7 @@ def test_cli_all_tasks(dataset, monkeypatch):
     assert set(b) == {'embeddings', 'bboxes'} and b['embeddings'].dtype == torch.float16
     assert torch.equal(b['bboxes'], rb.bboxes.half())
     assert cos_ok(b['embeddings'], vit.normalize_half(vit.encode_image(p, rb.blocks)))
+    assert b['embeddings'].untyped_storage().nbytes() == b['embeddings'].numel() * 2
 
     cli_objects.Validator.main(['t', dataset['configs']['objects']])
     o = torch.load(root / 'oake' / 'objects' / 'val' / f'{id0:012d}.pth')
@@ -58,6 +68,9 @@ def test_cli_all_tasks(dataset, monkeypatch):
     assert set(o) == {'embeddings', 'bboxes', 'objectness'}
     assert o['objectness'].shape == (ro.objectness.shape[0], 1) and torch.equal(o['bboxes'], ro.bboxes.half())
     assert cos_ok(o['embeddings'], vit.normalize_half(vit.encode_objects(p197, ro.objects, ro.masks)))
+    assert o['embeddings'].untyped_storage().nbytes() == o['embeddings'].numel() * 2
+    size = (root / 'oake' / 'objects' / 'val' / f'{id0:012d}.pth').stat().st_size
+    assert size < o['embeddings'].numel() * 2 + 8192
 
     # resume: everything is on disk, a second run must not rewrite a single file
     victim = root / 'oake' / 'objects' / 'val' / f'{dataset["ids"][2]:012d}.pth'
@@ -103,3 +116,13 @@ def test_cli_packed_store_matches_pth(dataset, monkeypatch, tmp_path):
     again = store.PackedStore(str(out), 'val')
     assert len(again) == len(packed)
     assert sum(1 for _ in (out / 'val').glob('*.idx.json')) == 2  # the second run's (empty) shard
+
+
+def test_cli_refuses_random_weights_unless_told(dataset, monkeypatch):
+    """`clip.load_default` fails without a checkpoint; so does this CLI (no silent random features)."""
+    monkeypatch.delenv('DRY_RUN', raising=False)
+    monkeypatch.delenv('OAKE_CLIP_WEIGHTS', raising=False)
+    monkeypatch.delenv('OAKE_ALLOW_RANDOM_WEIGHTS', raising=False)
+    import oadp.oake.globals as cli_globals
+    with pytest.raises(RuntimeError, match='OAKE_CLIP_WEIGHTS'):
+        cli_globals.Validator.main(['t', dataset['configs']['globals']])

@@ -90,8 +90,36 @@ def test_pipeline_takes_compressed_and_decoded_images_alike(pipe):
         assert torch.equal(a['embeddings'], b['embeddings'])
 
 
+def test_mixed_batch_survives_stale_staging_bytes_and_a_busy_main_stream(pipe):
+    """A batch mixing decoded arrays with compressed files: the decode stream writes the compressed images'
+    pixels into the arena while the main stream is still busy with earlier work.  The main stream must not
+    copy the staging bytes of those images over them (only the raw images' ranges travel)."""
+    files = []
+    for i, (w, h) in enumerate(synth.COCO_SIZES[:4]):
+        buf = io.BytesIO()
+        PIL.Image.fromarray(synth.image(w, h, 90 + i)).save(buf, 'JPEG', quality=90)
+        files.append(buf.getvalue())
+    decoded = [ojpeg.decode(f) for f in files]
+    compressed = [oake_jpeg.parse(f) for f in files]
+    ref = pipe.encode_globals(decoded)
+    for _ in range(2):  # both slots
+        pipe._cur ^= 1
+        slot = pipe._slots[pipe._cur]
+        if slot.ticket is not None:
+            slot.ticket.collect()
+        if slot.arena.host is not None:
+            slot.arena.host.fill_(0xA5)  # poison: whatever a whole-arena copy would carry
+    busy = torch.randn(8192, 8192, device='cuda')
+    for _ in range(20):  # ~100 ms of queued main-stream work ahead of the next submission
+        busy = (busy @ busy).clamp_(-1, 1)
+    mixed = [compressed[0], decoded[1], compressed[2], decoded[3]]
+    for a, b in zip(pipe.encode_globals(mixed), ref):
+        assert torch.equal(a, b)
+
+
 def test_cli_decode_gpu_writes_the_same_files(tmp_path_factory, lib, monkeypatch):
     monkeypatch.delenv('DRY_RUN', raising=False)
+    monkeypatch.setenv('OAKE_ALLOW_RANDOM_WEIGHTS', '1')
     monkeypatch.delenv('OAKE_CLIP_WEIGHTS', raising=False)
     import oadp.oake.blocks as cli_blocks
     ds = synth.write_coco_dataset(tmp_path_factory.mktemp('coco_jpg'), 5, seed=4, n_proposals=10, fmt='jpg')

@@ -1,6 +1,7 @@
 #!/bin/bash
 # 2-GPU checks: torchrun bench, the CLI test tier, and a 2-rank `oadp.oake.objects` run with packed output.
 mkdir -p gpurun_out
+export OAKE_ALLOW_RANDOM_WEIGHTS=1  # no CLIP checkpoint offline: the CLI needs the explicit opt-in
 timeout 900 python -c "import torch; torch.zeros(1).cuda(); print(torch.cuda.device_count())"
 python -m oadp_b200.build > gpurun_out/build.log 2>&1
 echo "== 2-GPU bench (torchrun)"
