@@ -274,7 +274,7 @@ int oake_jpeg_decode(const uint8_t* bytes, const oake_jpeg_desc* descs_host, con
  * openai/CLIP ViT-B/32 text encoder: width 512, 8 heads, MLP 2048, causal attention over <= 77 tokens,
  * ln_final, the row of the EOT token (argmax of the ids) times text_projection.  Layer weights use
  * oake_layer_weights with the text shapes (qkv [1536,512], out [512,512], fc1 [2048,512], fc2 [512,2048];
- * ln_1 / ln_2 folded as for the image tower).  NOT YET RUN ON A GPU (see oadp_b200/csrc/text.cu). */
+ * ln_1 / ln_2 folded as for the image tower).  Parity: tests/test_gpu_text.py. */
 typedef struct oake_text_handle oake_text_handle;
 
 typedef struct {

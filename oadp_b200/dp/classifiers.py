@@ -9,8 +9,8 @@ distiller forward hooks of configs/dp/models/*.py keep working unchanged.
 On a CUDA device both halves run on liboake_b200 (tcgen05 GEMMs + fused row kernels, forward and
 backward); there is no PyTorch fallback on CUDA.  CPU tensors raise: the reference's CPU debug mode
 is out of scope for this library (use the oracle in tests).
-Registered in mmdet's `LINEAR_LAYERS` when mmdet is importable, else in a local registry with the
-same decorator form.
+Registered in mmdet's `LINEAR_LAYERS` when mmdet is importable, else in the registry of the same
+name in `oadp_b200.registry` (same decorator form, same `build_linear_layer`).
 """
 from __future__ import annotations
 
@@ -21,28 +21,10 @@ import torch
 import torch.nn as nn
 
 from .. import binding
+from ..registry import LINEAR_LAYERS
 from .categories import Globals
 
-try:  # pragma: no cover - mmdet is not installed in this environment
-    from mmdet.models.utils.builder import LINEAR_LAYERS
-except Exception:
-
-    class _Registry:
-
-        def __init__(self) -> None:
-            self.module_dict: Dict[str, type] = {}
-
-        def register_module(self, name: Optional[str] = None, force: bool = False, module: Optional[type] = None):
-            def deco(cls: type) -> type:
-                self.module_dict[name or cls.__name__] = cls
-                return cls
-            return deco(module) if module is not None else deco
-
-        def build(self, cfg: Dict[str, Any], **default_args: Any) -> Any:
-            cfg = dict(default_args, **cfg)
-            return self.module_dict[cfg.pop('type')](**cfg)
-
-    LINEAR_LAYERS = _Registry()
+__all__ = ['BaseClassifier', 'Classifier', 'ViLDClassifier', 'NormalizedLinear']
 
 DIM = 512
 
@@ -146,6 +128,9 @@ class _CosineLogitsFn(torch.autograd.Function):
         dl[:, :k] = dlogits
         dh = torch.empty(n, DIM, device=h32.device, dtype=torch.float32)
         want_bg = has_bg and ctx.needs_input_grad[2]
+        bg_dead = has_bg and ninf_lo <= num_all < ninf_hi  # the background column was forced to -inf: no gradient
+        if want_bg and bg_dead:
+            want_bg = False
         dbg = torch.empty(DIM, device=h32.device) if want_bg else None
         ws = _Workspace.get(h32.device, n, 1024, k_pad)
         binding.check(lib.oake_cosine_logits_bwd(h32.data_ptr(), text32.data_ptr(),
@@ -153,6 +138,8 @@ class _CosineLogitsFn(torch.autograd.Function):
                                                  k_pad, alpha, ninf_lo, ninf_hi, dh.data_ptr(),
                                                  dbg.data_ptr() if want_bg else None, ws.data_ptr(), ws.numel(),
                                                  _stream(dl)))
+        if has_bg and ctx.needs_input_grad[2] and bg_dead:
+            return dh, None, torch.zeros(bg_shape, device=h32.device), None, None, None, None
         return dh, None, (dbg.reshape(bg_shape) if want_bg else None), None, None, None, None
 
 
@@ -185,6 +172,9 @@ class BaseClassifier(nn.Module):
         self.register_buffer('_embeddings', embeddings, persistent=False)
         self._bg_embedding = bg_embedding
         self._linear = NormalizedLinear(in_features, embeddings.shape[1])
+        # set by `ObjectMixin` (bbox_heads.py:57-60 writes -inf into the last column after every forward):
+        # the background column then leaves the logits kernel as -inf -- the same values, one launch fewer
+        self.disable_bg_column = False
 
     @property
     def embeddings(self) -> torch.Tensor:
@@ -198,9 +188,12 @@ class BaseClassifier(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         h = self._linear(x)  # through __call__: forward hooks see the normalised tensor
+        num_all = Globals.categories.num_all
         lo = hi = 0
         if Globals.training:  # novel categories are invisible while training (classifiers.py:62-67)
-            lo, hi = Globals.categories.num_bases, Globals.categories.num_all
+            lo, hi = Globals.categories.num_bases, num_all
+        if self.disable_bg_column and self._bg_embedding is not None:
+            lo, hi = (lo if hi else num_all), num_all + 1  # [novels |] background: one contiguous -inf range
         alpha, shift = self._affine()
         return _CosineLogitsFn.apply(h, self._embeddings, self._bg_embedding, alpha, shift, lo, hi)
 

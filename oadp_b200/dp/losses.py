@@ -8,6 +8,11 @@ gradient with respect to the first argument; backward only scales that gradient.
 float or a `WarmupScheduler`-style dict `{'type': 'WarmupScheduler', 'gain': g, 'end': e}` -- todd's
 scheduler is not visible from the reference; it is taken as a linear ramp `g * min(step / e, 1)`
 driven by `loss.step(i)` (default: fully warmed up).  CUDA tensors only.
+
+Registered in todd's `LossRegistry` when todd is importable (its own `L1Loss` / `MSELoss` then keep their names:
+only `AsymmetricLoss` / `RKDLoss` are added, as oadp/base/losses.py:10,68 does), else in the registry of the same
+name in `oadp_b200.registry`, so that `LossRegistry.build(dict(type='AsymmetricLoss', ...))` of
+oadp/dp/bbox_heads.py:31 and the distiller's loss configs resolve.
 """
 from __future__ import annotations
 
@@ -18,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from .. import binding
+from ..registry import LossRegistry
 
 _WS: Dict[int, torch.Tensor] = {}
 
@@ -93,6 +99,15 @@ class _LossFn(torch.autograd.Function):
         return (g * dloss).to(ctx.in_dtype), None, None, None, None
 
 
+def _register_unless_present(cls):
+    """todd ships `L1Loss` / `MSELoss` itself: with the real registry those names stay todd's."""
+    try:
+        LossRegistry.register()(cls)
+    except Exception:
+        pass
+    return cls
+
+
 class BaseLoss(nn.Module):
 
     def __init__(self, reduction: str = 'mean', weight: Union[float, Dict[str, Any]] = 1.0, **_: Any) -> None:
@@ -118,18 +133,21 @@ class BaseLoss(nn.Module):
         return self.weight / numel if self._reduction == 'mean' else self.weight
 
 
+@_register_unless_present
 class L1Loss(BaseLoss):
 
     def forward(self, pred: torch.Tensor, target: torch.Tensor, *_: Any, **__: Any) -> torch.Tensor:
         return _LossFn.apply(pred, target, 'l1', self._scale(pred.numel()), ())
 
 
+@_register_unless_present
 class MSELoss(BaseLoss):
 
     def forward(self, pred: torch.Tensor, target: torch.Tensor, *_: Any, **__: Any) -> torch.Tensor:
         return _LossFn.apply(pred, target, 'mse', self._scale(pred.numel()), ())
 
 
+@LossRegistry.register()
 class RKDLoss(BaseLoss):
     """oadp/base/losses.py:68-108."""
 
@@ -138,6 +156,7 @@ class RKDLoss(BaseLoss):
         return _LossFn.apply(preds, targets, 'rkd', self._scale(n * n), ())
 
 
+@LossRegistry.register()
 class AsymmetricLoss(BaseLoss):
     """oadp/base/losses.py:10-65; `x` are probabilities (callers pass `logits.sigmoid()`), `y` bool."""
 

@@ -12,6 +12,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+__all__ = ['MultilabelTopKRecall', 'NormalizedLinear']
+
 
 class MultilabelTopKRecall(nn.Module):
 
@@ -32,3 +34,12 @@ class MultilabelTopKRecall(nn.Module):
         # no label at all: the reference's macro average over an empty label set is NaN -- kept
         recall = torch.where(present, per_label, torch.zeros_like(per_label)).sum() / n_present
         return (recall * 100).to(logits.dtype)
+
+
+def __getattr__(name: str):
+    # `NormalizedLinear` is listed in the reference's oadp/dp/utils.py:47-51; here it lives next to the
+    # autograd functions it calls (classifiers.py) -- resolved lazily, the two modules import each other
+    if name == 'NormalizedLinear':
+        from .classifiers import NormalizedLinear
+        return NormalizedLinear
+    raise AttributeError(name)

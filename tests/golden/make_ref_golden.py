@@ -146,7 +146,7 @@ def classifier_inputs():
 
 
 # ------------------------------------------------------------------------------ reference loading
-def _load_reference_modules():
+def _load_reference_modules(with_heads: bool = False):
     sys.path.insert(0, str(HERE))
     import ref_stubs
     ref_stubs.install()
@@ -175,6 +175,10 @@ def _load_reference_modules():
     base = sys.modules[f'{PKG}.base']
     base.coco, base.lvis = globals_.coco, globals_.lvis  # `from ..base import Globals, coco, lvis`
     m['datasets'] = load('dp.datasets', 'oadp/dp/datasets.py')
+    if with_heads:  # make_ref_heads_golden.py
+        sys.modules[f'{PKG}.base'].globals_ = globals_
+        m['bbox_heads'] = load('dp.bbox_heads', 'oadp/dp/bbox_heads.py')
+        m['roi_heads'] = load('dp.roi_heads', 'oadp/dp/roi_heads.py')
     return m
 
 

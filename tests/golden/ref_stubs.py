@@ -324,6 +324,142 @@ class _MMRegistry:
         return deco if module is None else deco(module)
 
 
+
+# ----------------------------------------------------- mmdet heads (oadp/dp/bbox_heads.py, roi_heads.py)
+# Restated from mmdet 2.25's published `ConvFCBBoxHead` / `StandardRoIHead`: module names and the call
+# conventions the reference's mixins rely on (`self.fc_cls`, `forward -> (cls_score, bbox_pred)`,
+# `_bbox_forward -> dict(cls_score, bbox_pred, bbox_feats)`, `HEADS.build(cfg, default_args=...)`).
+
+
+def _mm_build(registry, cfg, default_args=None):
+    args = dict(default_args or {})
+    args.update(cfg)
+    return registry.module_dict[args.pop('type')](**args)
+
+
+class _MMBuildRegistry(_MMRegistry):
+
+    def build(self, cfg, default_args=None):
+        return _mm_build(self, cfg, default_args)
+
+
+def _build_linear_layer(cfg, *args, **kwargs):
+    cfg = dict(cfg or dict(type='Linear'))
+    kind = cfg.pop('type')
+    if kind == 'Linear':
+        return nn.Linear(*args, **kwargs, **cfg)
+    return sys.modules['mmdet.models.utils.builder'].LINEAR_LAYERS.module_dict[kind](*args, **kwargs, **cfg)
+
+
+class _MMConvModule(nn.Module):
+
+    def __init__(self, cin, cout, norm_cfg):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 3, padding=1, bias=norm_cfg is None)
+        if norm_cfg is not None:
+            self.bn = nn.BatchNorm2d(cout)
+        self._has_norm = norm_cfg is not None
+
+    def forward(self, x):
+        x = self.conv(x)
+        return F.relu(self.bn(x) if self._has_norm else x)
+
+
+class _MMBBoxHead(nn.Module):
+
+    def __init__(self, with_avg_pool=False, with_cls=True, with_reg=True, roi_feat_size=7, in_channels=256,
+                 num_classes=80, bbox_coder=None, reg_class_agnostic=False, reg_decoded_bbox=False,
+                 reg_predictor_cfg=None, cls_predictor_cfg=None, loss_cls=None, loss_bbox=None, init_cfg=None):
+        super().__init__()
+        self.with_avg_pool, self.with_cls, self.with_reg = with_avg_pool, with_cls, with_reg
+        self.roi_feat_area = roi_feat_size * roi_feat_size
+        self.in_channels, self.num_classes, self.reg_class_agnostic = in_channels, num_classes, reg_class_agnostic
+        self.reg_predictor_cfg = reg_predictor_cfg or dict(type='Linear')
+        self.cls_predictor_cfg = cls_predictor_cfg or dict(type='Linear')
+
+
+class _MMConvFCBBoxHead(_MMBBoxHead):
+
+    def __init__(self, num_shared_convs=0, num_shared_fcs=0, conv_out_channels=256, fc_out_channels=1024,
+                 norm_cfg=None, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.shared_convs = nn.ModuleList()
+        last = self.in_channels
+        for _ in range(num_shared_convs):
+            self.shared_convs.append(_MMConvModule(last, conv_out_channels, norm_cfg))
+            last = conv_out_channels
+        last *= self.roi_feat_area
+        self.shared_fcs = nn.ModuleList()
+        for _ in range(num_shared_fcs):
+            self.shared_fcs.append(nn.Linear(last, fc_out_channels))
+            last = fc_out_channels
+        if self.with_cls:
+            self.fc_cls = _build_linear_layer(self.cls_predictor_cfg, in_features=last, out_features=self.num_classes + 1)
+        if self.with_reg:
+            self.fc_reg = _build_linear_layer(self.reg_predictor_cfg, in_features=last,
+                                              out_features=4 if self.reg_class_agnostic else 4 * self.num_classes)
+
+    def forward(self, x):
+        for conv in self.shared_convs:
+            x = conv(x)
+        x = x.flatten(1)
+        for fc in self.shared_fcs:
+            x = F.relu(fc(x))
+        return (self.fc_cls(x) if self.with_cls else None), (self.fc_reg(x) if self.with_reg else None)
+
+
+class _MMShared2FCBBoxHead(_MMConvFCBBoxHead):
+
+    def __init__(self, fc_out_channels=1024, *args, **kwargs):
+        super().__init__(num_shared_convs=0, num_shared_fcs=2, fc_out_channels=fc_out_channels, *args, **kwargs)
+
+
+class _MMShared4Conv1FCBBoxHead(_MMConvFCBBoxHead):
+
+    def __init__(self, fc_out_channels=1024, *args, **kwargs):
+        super().__init__(num_shared_convs=4, num_shared_fcs=1, fc_out_channels=fc_out_channels, *args, **kwargs)
+
+
+class _MMBaseRoIExtractor(nn.Module):
+    pass
+
+
+class _FixtureRoIExtractor(_MMBaseRoIExtractor):
+    """The fixture hands over RoI features directly: `feats[0]` holds one (C, 7, 7) feature per RoI, picked
+    by the row order of `rois` (RoIAlign is mmcv's arithmetic, not the reference's)."""
+    num_inputs = 1
+
+    def forward(self, feats, rois):
+        assert feats[0].shape[0] == rois.shape[0]
+        return feats[0]
+
+
+class _MMStandardRoIHead(nn.Module):
+
+    def __init__(self, bbox_roi_extractor=None, bbox_head=None, mask_roi_extractor=None, mask_head=None,
+                 shared_head=None, train_cfg=None, test_cfg=None, pretrained=None, init_cfg=None):
+        super().__init__()
+        heads = sys.modules['mmdet.models'].HEADS
+        self.bbox_roi_extractor = _mm_build(heads, bbox_roi_extractor)
+        self.bbox_head = _mm_build(heads, bbox_head)
+
+    with_shared_head = property(lambda self: False)
+
+    def _bbox_forward(self, x, rois):
+        bbox_feats = self.bbox_roi_extractor(x[:self.bbox_roi_extractor.num_inputs], rois)
+        cls_score, bbox_pred = self.bbox_head(bbox_feats)
+        return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)
+
+
+def _bbox2roi(bbox_list):
+    return torch.cat([torch.cat([b.new_full((b.shape[0], 1), i), b[:, :4]], dim=-1) for i, b in enumerate(bbox_list)], 0)
+
+
+class _AttrDict(dict):
+    """todd.Config / mmcv.ConfigDict as roi_heads.py uses them: `bbox_head.num_classes` get and set."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
 # ----------------------------------------------------------------------- clip (openai layout)
 
 
@@ -481,6 +617,16 @@ def install() -> None:
     for name in ('mmdet', 'mmdet.models', 'mmdet.models.utils', 'mmdet.models.utils.builder', 'mmcv', 'mmcv.runner'):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules['mmdet.models.utils.builder'].LINEAR_LAYERS = _MMRegistry()
+    mm = sys.modules['mmdet.models']
+    mm.HEADS = _MMBuildRegistry()
+    mm.BBoxHead, mm.Shared2FCBBoxHead, mm.Shared4Conv1FCBBoxHead = _MMBBoxHead, _MMShared2FCBBoxHead, _MMShared4Conv1FCBBoxHead
+    mm.BaseRoIExtractor, mm.StandardRoIHead = _MMBaseRoIExtractor, _MMStandardRoIHead
+    for cls in (_MMShared2FCBBoxHead, _MMShared4Conv1FCBBoxHead, _FixtureRoIExtractor):
+        mm.HEADS.module_dict[cls.__name__.replace('_MM', '').lstrip('_')] = cls
+    core = types.ModuleType('mmdet.core')
+    core.bbox2roi = _bbox2roi
+    sys.modules['mmdet.core'] = core
+    sys.modules['mmcv'].ConfigDict = _AttrDict
     sys.modules['mmcv.runner'].force_fp32 = _force_fp32
     # mmdet.datasets / lvis: only names that oadp/dp/datasets.py imports at module level
     md = types.ModuleType('mmdet.datasets')
