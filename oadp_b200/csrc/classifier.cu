@@ -318,7 +318,8 @@ int oake_normalized_linear_bwd(const float* x, const float* w, const float* h, c
                                size_t ws_bytes, void* stream) {
   if (N == 0) return 0;
   if (!x || !w || !h || !inv_norm || !dh || !ws) return fail_msg("NULL buffer");
-  if (in_features % 64 != 0) return fail_msg("in_features must be a multiple of 64");
+  // dx / dw are GEMMs whose OUTPUT width is in_features (tiles of 128 columns)
+  if (in_features % 128 != 0) return fail_msg("the backward pass needs in_features to be a multiple of 128");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int np = pad64(N);
   Carver c(ws, ws_bytes);

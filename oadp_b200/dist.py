@@ -23,6 +23,15 @@ def rank_world() -> Tuple[int, int]:
     return int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
 
 
+def broadcast_object(obj, src: int = 0):
+    """Rank `src`'s python object on every rank (identity without a process group)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return obj
+    box = [obj if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def balanced_partition(costs: Sequence[float], world: int) -> List[List[int]]:
     """Longest-processing-time greedy: indices sorted by decreasing cost, each to the lightest rank.
     Deterministic (ties by index), every index assigned exactly once, each shard sorted ascending."""
@@ -37,7 +46,7 @@ def balanced_partition(costs: Sequence[float], world: int) -> List[List[int]]:
 
 
 def all_gather_embeddings(emb: torch.Tensor, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Collates per-rank (n_r, 512) fp16 embeddings and their int64 row ids on every rank.
+    """Collates per-rank (n_r, C) rows (fp16 embeddings, or any 2-D tensor) and their int64 row ids on every rank.
 
     One all_gather of the counts, then one all_gather_into_tensor of the padded payload: 1 KiB per
     crop, so even 8 GPUs x 20k crops/s is < 0.2 GB/s of NVLink traffic."""

@@ -103,12 +103,19 @@ class ObjectsPlan:
     boxes_int: np.ndarray  # (No,4) i64 PIL-rounded crop rectangles
 
 
-def expand_adaptive(xyxy: np.ndarray, image_wh: Tuple[int, int]) -> np.ndarray:
-    """objects.py:76-114, ExpandMode.ADAPTIVE, fp32 arithmetic throughout."""
+def expand_adaptive(xyxy: np.ndarray, image_wh: Tuple[int, int], mode: str = 'ADAPTIVE') -> np.ndarray:
+    """objects.py:76-114, fp32 arithmetic throughout.  ExpandMode.ADAPTIVE: square of side sqrt(8 w h)
+    (:94-99); ExpandMode.CONSTANT: side 224 (:92-93).  The other two modes cannot run in the reference
+     and are refused by the dataset."""
     xyxy = xyxy.astype(np.float32)
     lt, rb = xyxy[:, :2], xyxy[:, 2:]
     wh = rb - lt
-    side = np.sqrt(wh[:, 0] * wh[:, 1] * np.float32(8))[:, None]
+    if mode == 'CONSTANT':
+        side = np.full((xyxy.shape[0], 1), 224, dtype=np.float32)
+    elif mode == 'ADAPTIVE':
+        side = np.sqrt(wh[:, 0] * wh[:, 1] * np.float32(8))[:, None]
+    else:
+        raise ValueError(f'expand mode {mode}')
     center = (lt + rb) / np.float32(2)
     swh = np.concatenate([side, side], axis=1)
     half = swh / np.float32(2)
@@ -122,7 +129,8 @@ def expand_adaptive(xyxy: np.ndarray, image_wh: Tuple[int, int]) -> np.ndarray:
     return np.concatenate([center - half, center + half], axis=1).astype(np.float32)
 
 
-def objects_plan(proposals: np.ndarray, image_wh: Tuple[int, int], dry_run: bool = False) -> ObjectsPlan:
+def objects_plan(proposals: np.ndarray, image_wh: Tuple[int, int], dry_run: bool = False,
+                 expand_mode: str = 'ADAPTIVE') -> ObjectsPlan:
     """objects.py:157-186 without the pixels."""
     proposals = np.asarray(proposals, dtype=np.float32).reshape(-1, 5)
     boxes, objectness = proposals[:, :4], proposals[:, 4:]
@@ -131,7 +139,7 @@ def objects_plan(proposals: np.ndarray, image_wh: Tuple[int, int], dry_run: bool
     if dry_run:
         keep[5:] = False
     boxes, objectness = boxes[keep], objectness[keep]
-    expanded = expand_adaptive(boxes, image_wh)
+    expanded = expand_adaptive(boxes, image_wh, expand_mode)
     foregrounds = boxes - np.tile(expanded[:, :2], (1, 2))
     boxes_int = np.rint(expanded.astype(np.float64)).astype(np.int64)  # PIL crop: int(round(x))
     return ObjectsPlan(boxes, objectness, expanded, foregrounds.astype(np.float32), boxes_int)

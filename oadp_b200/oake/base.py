@@ -6,6 +6,11 @@ Kept from the reference (the drop-in contract):
     skipped, `auto_fix=True` re-loads them to detect truncated files (base.py:28-54)
   * `BaseValidator.main()`: build the model once, run the `val` split, then `train` (base.py:115-152)
   * `torch.save(result, output)` per image (base.py:106-113)
+  * the validator class surface: `_build_model() -> (model, preprocess)`,
+    `_build_dataloader(config)`, `_control_run_iter(batch, memo)`, `_run_iter(batch, memo) -> Tensor`,
+    per-task `Batch` NamedTuples with the reference's field names, `Dataset._preprocess(id_, output, image)`
+    (base.py:56-63,78-113).  `_run_iter` encodes ONE batch synchronously like the reference's; `run()` drives
+    the same datasets through the asynchronous, multi-image form of the same call (`_submit`)
 Changed on purpose (B200-first):
   * the dataset item is the decoded uint8 image (+ proposals); cropping / resizing / normalising
     happen on the GPU (`oadp_b200.pipeline`), not with PIL in DataLoader workers
@@ -23,11 +28,12 @@ from __future__ import annotations
 import argparse
 import collections
 import concurrent.futures
+import enum
 import itertools
 import pathlib
 import time
 from abc import ABC, abstractmethod
-from typing import Any, Dict, Generic, Iterator, List, NamedTuple, Optional, Sequence, Tuple, TypeVar
+from typing import Any, Dict, Generic, Iterable, Iterator, List, Optional, Protocol, Sequence, Tuple, TypeVar
 
 import numpy as np
 import torch
@@ -40,14 +46,29 @@ from ..pipeline import OakePipeline
 from ..store import PackedStore, PackedWriter, key_of
 
 
-class Item(NamedTuple):
-    id_: int
-    output: pathlib.Path
-    image: Any  # uint8 HWC RGB array, or the still-compressed file (`jpeg.JpegSource`) with decode='gpu'
-    extra: Any = None
+class Control(enum.Enum):
+    """todd.utils.Control: what `_control_run_iter` may answer."""
+    BREAK = enum.auto()
+    CONTINUE = enum.auto()
 
 
-T = TypeVar('T')
+Memo = dict  # todd.utils.Memo
+
+
+class Batch(Protocol):
+    """What a dataset item must offer the loop (base.py:18-23); the tasks define NamedTuples with the
+    reference's field names (globals.py:19-21, blocks.py:19-22, objects.py:24-29)."""
+
+    @property
+    def output(self) -> pathlib.Path:
+        ...
+
+
+def key_of_batch(batch: Batch) -> str:
+    return batch.output.stem  # f'{image_id:012d}'
+
+
+T = TypeVar('T', bound=Batch)
 
 
 class BaseDataset(CocoImages, ABC, Generic[T]):
@@ -81,7 +102,13 @@ class BaseDataset(CocoImages, ABC, Generic[T]):
             print(f'Fixing {output}', flush=True)
             return False
 
-    def __getitem__(self, index: int) -> Optional[Item]:
+    def exists(self, id_: int) -> bool:
+        """Cheap form of `is_done` (no `auto_fix` re-load): which items the shard leaves out."""
+        if getattr(self, '_packed_done', None) is not None:
+            return key_of(id_) in self._packed_done
+        return self.output_path(id_).exists()
+
+    def __getitem__(self, index: int) -> Optional[T]:
         id_ = self.ids[index]
         if self.is_done(id_):
             return None
@@ -89,10 +116,14 @@ class BaseDataset(CocoImages, ABC, Generic[T]):
             image = oake_jpeg.load(self.image_path(id_))
         else:
             image = np.asarray(self._load_image(id_), dtype=np.uint8)
-        return Item(id_, self.output_path(id_), image, self._extra(id_))
+        return self._preprocess(id_, self.output_path(id_), image)
 
-    def _extra(self, id_: int) -> Any:
-        return None
+    @abstractmethod
+    def _preprocess(self, id_: int, output: pathlib.Path, image: Any) -> T:
+        """base.py:56-63.  `image` is the decoded uint8 HWC array (or the still-compressed
+        `jpeg.JpegSource` with decode='gpu'), not a PIL image: cropping / resizing / normalising are the
+        pipeline's kernels, so the batch carries the image itself in the field the reference fills with
+        preprocessed tensors."""
 
     def cost(self, index: int) -> float:
         """Relative amount of GPU work of item `index` (for the balanced shard)."""
@@ -130,29 +161,67 @@ def default_params() -> Dict[str, torch.Tensor]:
     return synth.visual_params(0)
 
 
-class BaseValidator(ABC, Generic[T]):
-    """One split of one task: iterate images, encode on the GPU, write `.pth` files."""
+class DataLoader(Generic[T]):
+    """What `_build_dataloader` returns -- the role of `torch.utils.data.DataLoader(batch_size=None, sampler=
+    DistributedSampler(shuffle=False), num_workers=...)` at base.py:78-89: iterating yields the rank's items
+    in order, `None` for those already on disk.  Items are decoded ahead of the GPU by `num_workers` host
+    threads (PIL and the JPEG stager release the GIL) instead of worker processes: the PIL crop / resize work
+    that made processes necessary lives on the GPU here.  `num_workers=0`: no threads (DRY_RUN, base.py:82-83).
+    The rank's share is a crop-count balanced partition of the items still to do (`oadp_b200.dist`), not the
+    sampler's round robin with wrap-around duplicates."""
 
-    DATASET = BaseDataset
+    def __init__(self, dataset: BaseDataset, indices: Sequence[int], num_workers: int = 2, prefetch: int = 16) -> None:
+        self.dataset = dataset
+        self.indices = list(indices)
+        self.num_workers = int(num_workers)
+        self.prefetch = int(prefetch)
+
+    def __len__(self) -> int:
+        return len(self.indices)
+
+    def __iter__(self) -> Iterator[Optional[T]]:
+        if self.num_workers <= 0:
+            for i in self.indices:
+                yield self.dataset[i]
+            return
+        depth = max(self.prefetch, 2 * self.num_workers)
+        with concurrent.futures.ThreadPoolExecutor(max_workers=self.num_workers) as pool:
+            window: 'collections.deque' = collections.deque()
+            it = iter(self.indices)
+            for i in itertools.islice(it, depth):
+                window.append(pool.submit(self.dataset.__getitem__, i))
+            while window:
+                item = window.popleft().result()
+                nxt = next(it, None)
+                if nxt is not None:
+                    window.append(pool.submit(self.dataset.__getitem__, nxt))
+                yield item
+
+
+class BaseValidator(ABC, Generic[T]):
+    """One split of one task: iterate images, encode on the GPU, write `.pth` files (base.py:75-113)."""
 
     def __init__(self, name: str, model: OakeModel, *, dataloader: Config, log: Optional[Config] = None,
-                 batch_images: int = 8, store: str = 'pth', decode: str = 'pillow', **_: Any) -> None:
+                 batch_images: int = 8, store: str = 'pth', decode: str = 'pillow', collate: bool = False,
+                 **_: Any) -> None:
         self._name = name
         self._model = model
         self._pipeline = OakePipeline(model.engine)
         self._log_interval = int((log or {}).get('interval', 50))
         self._batch_images = 1 if Store.DRY_RUN else int(batch_images)
-        self._dataset = self._build_dataset(Config(dataloader.dataset))
         if decode not in ('pillow', 'gpu'):
             raise ValueError(f"decode must be 'pillow' or 'gpu', not {decode!r}")
-        self._dataset.gpu_decode = decode == 'gpu'
         if store not in ('pth', 'packed'):
             raise ValueError(f"store must be 'pth' or 'packed', not {store!r}")
+        self._decode, self._store = decode, store
+        self._collate = bool(collate)
+        self._manifest: List[Tuple[int, int, Optional[torch.Tensor]]] = []  # (image id, rows, global embedding)
         self._packed: Optional[PackedWriter] = None
+        dataloader = Config(dataloader)
         workers = int(dataloader.get('num_workers', 2)) or 1
-        self._decode_workers = 0 if Store.DRY_RUN else int(dataloader.get('num_workers', 2))
+        self._dataloader: DataLoader[T] = self._build_dataloader(dataloader)
+        self._dataset: BaseDataset = self._dataloader.dataset
         if store == 'packed':
-            self._dataset.use_packed()
             out_dir = self._dataset._output_dir
             rank, _world = oake_dist.rank_world()
             serial = len(list(out_dir.glob(f'shard-{rank:05d}-*.idx.json')))
@@ -160,92 +229,101 @@ class BaseValidator(ABC, Generic[T]):
             workers = 1  # appends to one file, in order
         self._writer = concurrent.futures.ThreadPoolExecutor(max_workers=workers)
 
-    def _write(self, result: Any, item: Item) -> None:
+    def _write(self, result: Any, batch: T) -> None:
         if self._packed is not None:
-            self._packed.add(key_of(item.id_), result)
+            self._packed.add(key_of_batch(batch), result)
         else:
-            torch.save(result, item.output)
+            torch.save(result, batch.output)
 
-    # ------------------------------------------------------------------ to be provided per task
+    # ------------------------------------------------------------------ the reference's class surface
     @classmethod
     def _build_model(cls) -> Tuple[OakeModel, Any]:
-        """(model, preprocess) like the reference; preprocess is None: it lives on the GPU."""
+        """(model, preprocess) like the reference (base.py:91-94); preprocess is None: it lives on the GPU."""
         return OakeModel(default_params(), 'cuda'), None
 
-    def _build_dataset(self, config: Config) -> BaseDataset:
-        config.pop('transform', None)
-        return self.DATASET(**config)
+    def _build_dataloader(self, config: Config) -> DataLoader[T]:
+        """base.py:78-89.  `config.dataset` is the built dataset (the task's override does that, as the
+        reference's do); DRY_RUN forces `num_workers = 0`; the rank's share replaces the DistributedSampler."""
+        if Store.DRY_RUN:
+            config.num_workers = 0
+        dataset: BaseDataset = config.dataset
+        dataset.gpu_decode = self._decode == 'gpu'
+        if self._store == 'packed':
+            dataset.use_packed()
+        workers = int(config.get('num_workers', 2))
+        return DataLoader(dataset, self._shard(dataset), workers, prefetch=2 * self._batch_images)
+
+    def _control_run_iter(self, batch: Optional[T], memo: Memo) -> Optional[Control]:
+        """base.py:96-104: an item that is already on disk comes back as None and is skipped."""
+        if batch is None:
+            return Control.CONTINUE
+        return None
+
+    def _run_iter(self, batch: T, memo: Memo) -> torch.Tensor:
+        """base.py:106-113: the task's override has put the record to store in `memo['result']`."""
+        self._write(memo['result'], batch)
+        return torch.tensor(0.0)
 
     @abstractmethod
-    def _submit(self, items: List[Item]):
-        """-> a `Pending` whose result() is one entry per item, in the layout the reference stores."""
+    def _submit(self, batches: List[T]):
+        """Asynchronous multi-image form of `_run_iter`: -> a `Pending` whose result() is one record per
+        batch, in the layout the reference stores."""
 
     # ---------------------------------------------------------------------------------- the loop
-    def _shard(self) -> List[int]:
+    def _shard(self, dataset: BaseDataset) -> List[int]:
+        """This rank's indices: the items NOT yet on disk, partitioned by crop count.  Rank 0 decides and
+        broadcasts, so that all ranks cut the same list even if some of them start after others have
+        already written files.  (`auto_fix` keeps existing files in the list: they are re-loaded.)"""
         rank, world = oake_dist.rank_world()
-        todo = list(range(len(self._dataset)))
+        todo = list(range(len(dataset)))
         if world == 1:
             return todo
-        costs = [self._dataset.cost(i) for i in todo]
-        return oake_dist.balanced_partition(costs, world)[rank]
+        if not dataset._auto_fix:
+            todo = [i for i in todo if not dataset.exists(dataset.ids[i])]
+        todo = oake_dist.broadcast_object(todo)
+        costs = [dataset.cost(i) for i in todo]
+        return [todo[j] for j in oake_dist.balanced_partition(costs, world)[rank]]
 
-    def _items(self, indices: List[int]) -> Iterator[Optional[Item]]:
-        """Dataset items in order, decoded ahead of the GPU by a few host threads (PIL releases the
-        GIL while it decodes) -- the role of the reference's DataLoader workers (base.py:78-89), minus
-        the PIL crop / resize work, which lives on the GPU here.  DRY_RUN: no threads (base.py:82-83)."""
-        if self._decode_workers <= 0:
-            for i in indices:
-                yield self._dataset[i]
-            return
-        depth = max(2 * self._batch_images, 2 * self._decode_workers)
-        with concurrent.futures.ThreadPoolExecutor(max_workers=self._decode_workers) as pool:
-            window: 'collections.deque' = collections.deque()
-            it = iter(indices)
-            for i in itertools.islice(it, depth):
-                window.append(pool.submit(self._dataset.__getitem__, i))
-            while window:
-                item = window.popleft().result()
-                nxt = next(it, None)
-                if nxt is not None:
-                    window.append(pool.submit(self._dataset.__getitem__, nxt))
-                yield item
-
-    def _batches(self, indices: List[int]) -> Iterator[List[Item]]:
-        batch: List[Item] = []
-        for item in self._items(indices):
-            if item is None:  # already on disk (base.py:45-47)
+    def _batches(self) -> Iterator[List[T]]:
+        group: List[T] = []
+        memo: Memo = Memo()
+        for batch in self._dataloader:
+            if self._control_run_iter(batch, memo) is Control.CONTINUE:  # already on disk (base.py:45-47)
                 continue
-            batch.append(item)
-            if len(batch) == self._batch_images:
-                yield batch
-                batch = []
-        if batch:
-            yield batch
+            group.append(batch)
+            if len(group) == self._batch_images:
+                yield group
+                group = []
+        if group:
+            yield group
 
     def run(self) -> int:
-        indices = self._shard()
+        total = len(self._dataloader)
         if Store.DRY_RUN:
-            indices = indices[:3]
+            self._dataloader.indices = self._dataloader.indices[:3]
         done, t0, pending = 0, time.perf_counter(), []
-        in_flight = None  # (batch, Pending): the GPU works on it while the next batch is decoded / staged
+        in_flight = None  # (batches, Pending): the GPU works on it while the next group is decoded / staged
 
         def drain(entry):
-            batch_, ticket = entry
-            for item, result in zip(batch_, ticket.result()):
-                pending.append(self._writer.submit(self._write, result, item))
+            batches_, ticket = entry
+            for batch, result in zip(batches_, ticket.result()):
+                pending.append(self._writer.submit(self._write, result, batch))
+                if self._collate:
+                    rows = result['embeddings'].shape[0] if isinstance(result, dict) else 1
+                    self._manifest.append((int(key_of_batch(batch)), rows, None if isinstance(result, dict) else result))
 
         try:
-            for batch in itertools.chain(self._batches(indices), [None]):
-                nxt = (batch, self._submit(batch)) if batch is not None else None
+            for group in itertools.chain(self._batches(), [None]):
+                nxt = (group, self._submit(group)) if group is not None else None
                 if in_flight is not None:
                     drain(in_flight)
                 in_flight = nxt
-                if batch is None:
+                if group is None:
                     break
-                done += len(batch)
-                if done % max(self._log_interval, 1) < len(batch):
+                done += len(group)
+                if done % max(self._log_interval, 1) < len(group):
                     dt = time.perf_counter() - t0
-                    print(f'[{self._name}] {done}/{len(indices)} images, {done / dt:.1f} img/s', flush=True)
+                    print(f'[{self._name}] {done}/{total} images, {done / dt:.1f} img/s', flush=True)
                 still = []
                 for f in pending:
                     if f.done():
@@ -260,7 +338,39 @@ class BaseValidator(ABC, Generic[T]):
             self._writer.shutdown(wait=True)
             if self._packed is not None:
                 self._packed.close()
+        if self._collate:
+            self.collate()
         return done
+
+    def collate(self) -> Optional[Dict[str, torch.Tensor]]:
+        """`--override .collate:True`: the ranks' outputs collated with ONE exchange at the end of the split --
+        `dist.all_gather_embeddings` (NCCL on GPUs: an all_gather of the counts + all_gather_into_tensor of the
+        padded rows) over (image id, rows written[, the 512-d global embedding]).  Rank 0 writes
+        `{output_dir}/manifest.pth` = {ids (N,) int64 ascending, rows (N,) int64[, embeddings (N,512) f16]}: for
+        the globals task that is the whole feature table in one file, for blocks / objects the index of what the
+        per-image files (or packed shards) hold.  The per-image outputs themselves never travel."""
+        dev = self._pipeline.device if hasattr(self._pipeline, 'device') else torch.device('cpu')
+        ids = torch.tensor([m[0] for m in self._manifest], dtype=torch.int64, device=dev)
+        rows = torch.tensor([m[1] for m in self._manifest], dtype=torch.int64, device=dev).reshape(-1, 1)
+        with_emb = self._manifest[0][2] is not None if self._manifest else self._collate_embeddings()
+        all_rows, all_ids = oake_dist.all_gather_embeddings(rows, ids)
+        out: Dict[str, torch.Tensor] = dict()
+        if with_emb:
+            emb = (torch.stack([m[2] for m in self._manifest]) if self._manifest else torch.zeros(0, 512, dtype=torch.float16)).to(dev)
+            all_emb, _ = oake_dist.all_gather_embeddings(emb, ids)
+        order = torch.argsort(all_ids)
+        out['ids'], out['rows'] = all_ids[order].cpu(), all_rows[order, 0].cpu()
+        if with_emb:
+            out['embeddings'] = all_emb[order].cpu()
+        rank, _ = oake_dist.rank_world()
+        if rank == 0:
+            torch.save(out, self._dataset._output_dir / 'manifest.pth')
+        self._manifest = []
+        return out if rank == 0 else None
+
+    def _collate_embeddings(self) -> bool:
+        """Whether this task's manifest carries the embeddings themselves (globals: one row per image)."""
+        return False
 
     @classmethod
     def main(cls, argv: Optional[Sequence[str]] = None) -> None:

@@ -8,16 +8,29 @@ positional table and the mask-attended CLS side stream (objects.py:43-186,198-33
 from __future__ import annotations
 
 import enum
-import os
 import pathlib
 import pickle
-from typing import Any, Dict, List, Tuple
+from typing import Any, Dict, List, NamedTuple, Optional, Tuple
 
 import numpy as np
+import torch
 
 from ..compat import Config, Store
 from ..model import OakeModel
-from .base import BaseDataset, BaseValidator, Item, default_params
+from .base import BaseDataset, BaseValidator, DataLoader, Memo, default_params
+
+
+class Batch(NamedTuple):
+    """objects.py:24-29.  Native form: `objects` = the uint8 HWC image (or `jpeg.JpegSource`), `bboxes` /
+    `objectness` = the image's UNFILTERED proposals (N,4) / (N,1), `masks=None` -- the min_wh filter, the
+    expansion, the crops and the 14x14 masks are the pipeline's (objects.py:157-186 on the GPU).  The
+    reference's form -- float (No,3,224,224) crops, filtered boxes, (No,1,14,14) masks -- is accepted by
+    `_run_iter` as well."""
+    output: pathlib.Path
+    objects: Any
+    bboxes: Any
+    objectness: Any
+    masks: Optional[torch.Tensor]
 
 
 class ExpandMode(enum.Enum):
@@ -46,24 +59,27 @@ class DatasetRegistry:
 
 
 @DatasetRegistry.register()
-class COCODataset(BaseDataset):
+class COCODataset(BaseDataset[Batch]):
 
     def __init__(self, *args, grid: int, expand_mode: str = 'ADAPTIVE', proposal_file: str,
                  proposal_sorted: bool, **kwargs) -> None:
         super().__init__(*args, **kwargs)
         self._grid = grid
         self._expand_mode = ExpandMode[expand_mode]
-        if self._expand_mode is not ExpandMode.ADAPTIVE:
-            # the reference's LONGEST_EDGE / RECTANGLE branches cannot run and no
-            # shipped config selects CONSTANT
-            raise NotImplementedError(f'expand_mode={expand_mode}: only ADAPTIVE is built')
+        if self._expand_mode not in (ExpandMode.ADAPTIVE, ExpandMode.CONSTANT):
+            # the reference's LONGEST_EDGE / RECTANGLE branches cannot run (objects.py:90-91,100-101:
+            # a (values, indices) tuple as length / an always-true assert)
+            raise NotImplementedError(f'expand_mode={expand_mode}: only ADAPTIVE and CONSTANT can run upstream')
         with open(proposal_file, 'rb') as f:
             proposals = pickle.load(f)
         ids = self.ids if proposal_sorted else list(self.imgs.keys())
         self._proposals = {id_: np.asarray(p, dtype=np.float32) for id_, p in zip(ids, proposals)}
 
-    def _extra(self, id_: int) -> np.ndarray:
-        return self._proposals[id_]
+    expand_mode = property(lambda self: self._expand_mode.name)
+
+    def _preprocess(self, id_: int, output: pathlib.Path, image: Any) -> Batch:
+        proposals = self._proposals[id_].reshape(-1, 5)
+        return Batch(output, image, proposals[:, :4], proposals[:, 4:], None)
 
     def cost(self, index: int) -> float:
         return float(len(self._proposals[self.ids[index]]))
@@ -77,7 +93,7 @@ class LVISDataset(COCODataset):
         return self.root / url.replace('http://images.cocodataset.org/', '')
 
 
-class Validator(BaseValidator):
+class Validator(BaseValidator[Batch]):
 
     def __init__(self, *args, mini_batch_size: int = 512, **kwargs) -> None:
         # the tower chunks by its own SM-aligned size; results do not depend on the chunking
@@ -88,13 +104,31 @@ class Validator(BaseValidator):
     def _build_model(cls, upsample: int = 2) -> Tuple[OakeModel, Any]:
         return OakeModel(default_params(), 'cuda').for_objects(upsample), None
 
-    def _build_dataset(self, config: Config) -> BaseDataset:
-        config.pop('transform', None)
-        return DatasetRegistry.build(config, default_config=dict(grid=self._model.visual.grid))
+    def _build_dataloader(self, config: Config) -> DataLoader[Batch]:
+        """objects.py:275-283: the dataset type comes from the config, the grid from the model."""
+        dataset = Config(config.dataset)
+        dataset.pop('transform', None)
+        config.dataset = DatasetRegistry.build(dataset, default_config=dict(grid=self._model.visual.grid))
+        return super()._build_dataloader(config)
 
-    def _submit(self, items: List[Item]):
-        return self._pipeline.submit_objects([it.image for it in items], [it.extra for it in items],
-                                             dry_run=Store.DRY_RUN)
+    @staticmethod
+    def _proposals(batch: Batch) -> np.ndarray:
+        return np.concatenate([np.asarray(batch.bboxes, dtype=np.float32).reshape(-1, 4),
+                               np.asarray(batch.objectness, dtype=np.float32).reshape(-1, 1)], axis=1)
+
+    def _run_iter(self, batch: Batch, memo: Memo) -> torch.Tensor:
+        """objects.py:316-338 for one image."""
+        if torch.is_tensor(batch.objects):  # the reference's batch: crops, filtered boxes, masks
+            emb = self._model.embed(batch.objects, batch.masks)
+            memo['result'] = dict(embeddings=emb.cpu(), bboxes=batch.bboxes.half(), objectness=batch.objectness.half())
+        else:
+            memo['result'] = self._pipeline.encode_objects([batch.objects], [self._proposals(batch)], Store.DRY_RUN,
+                                                           self._dataset.expand_mode)[0]
+        return super()._run_iter(batch, memo)
+
+    def _submit(self, batches: List[Batch]):
+        return self._pipeline.submit_objects([b.objects for b in batches], [self._proposals(b) for b in batches],
+                                             dry_run=Store.DRY_RUN, expand_mode=self._dataset.expand_mode)
 
 
 if __name__ == '__main__':

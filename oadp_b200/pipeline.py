@@ -493,13 +493,13 @@ class OakePipeline:
         crops = np.concatenate(crops_all) if crops_all else np.zeros(0, frontend.CROP_SRC)
         return (images, offs, img_bytes, off, stages, crops, binding.VARIANT_T50), plans, counts
 
-    def encode_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray],
-                       dry_run: bool = False) -> List[Dict[str, torch.Tensor]]:
-        return self.submit_objects(images, proposals, dry_run).result()
+    def encode_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray], dry_run: bool = False,
+                       expand_mode: str = 'ADAPTIVE') -> List[Dict[str, torch.Tensor]]:
+        return self.submit_objects(images, proposals, dry_run, expand_mode).result()
 
-    def submit_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray],
-                       dry_run: bool = False) -> Pending:
-        args, plans = self.plan_objects(images, proposals, dry_run)
+    def submit_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray], dry_run: bool = False,
+                       expand_mode: str = 'ADAPTIVE') -> Pending:
+        args, plans = self.plan_objects(images, proposals, dry_run, expand_mode)
 
         def finish(emb: torch.Tensor):
             out, s = [], 0
@@ -512,9 +512,11 @@ class OakePipeline:
 
         return self._submit(args, finish)
 
-    def plan_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray], dry_run: bool = False):
+    def plan_objects(self, images: Sequence[np.ndarray], proposals: Sequence[np.ndarray], dry_run: bool = False,
+                     expand_mode: str = 'ADAPTIVE'):
         offs, img_bytes = self._place_images(images)
-        plans = [frontend.objects_plan(p, (im.shape[1], im.shape[0]), dry_run) for im, p in zip(images, proposals)]
+        plans = [frontend.objects_plan(p, (im.shape[1], im.shape[0]), dry_run, expand_mode)
+                 for im, p in zip(images, proposals)]
         total = sum(p.bboxes.shape[0] for p in plans)
         jobs, s = [], 0
         for im, o, plan in zip(images, offs, plans):

@@ -97,13 +97,18 @@ def min_wh_indices(xyxy: torch.Tensor, min_wh: Tuple[float, float] = (4, 4)) -> 
     return (wh >= torch.tensor(min_wh, dtype=wh.dtype)).all(-1)
 
 
-def expand_adaptive(xyxy: torch.Tensor, image_wh: torch.Tensor) -> torch.Tensor:
-    """objects.py:76-114, ExpandMode.ADAPTIVE: square of side sqrt(8*area) pushed inside
-    the image when it fits.  fp32 throughout; cxcywh -> xyxy as c -/+ wh/2 [unseen]."""
+def expand_adaptive(xyxy: torch.Tensor, image_wh: torch.Tensor, mode: str = 'ADAPTIVE') -> torch.Tensor:
+    """objects.py:76-114.  ExpandMode.ADAPTIVE (:94-99): square of side sqrt(8*area); ExpandMode.CONSTANT
+    (:92-93): side 224; either pushed inside the image when it fits.  fp32 throughout; cxcywh -> xyxy as
+    c -/+ wh/2 [unseen]."""
     lt, rb = xyxy[:, :2], xyxy[:, 2:]
     wh = rb - lt
     area = wh[:, 0] * wh[:, 1]
-    side = torch.sqrt(area * 8).unsqueeze(-1)
+    if mode == 'CONSTANT':
+        side = torch.full((xyxy.shape[0], 1), 224, dtype=xyxy.dtype)
+    else:
+        assert mode == 'ADAPTIVE', mode
+        side = torch.sqrt(area * 8).unsqueeze(-1)
     center = (lt + rb) / 2
     swh = torch.cat([side, side], dim=-1)
     e_lt = center - swh / 2
@@ -136,7 +141,7 @@ class ObjectsBatch(NamedTuple):
 
 
 def objects_preprocess(image: PIL.Image.Image, proposals: torch.Tensor, grid: int = 14,
-                       dry_run: bool = False) -> ObjectsBatch:
+                       dry_run: bool = False, expand_mode: str = 'ADAPTIVE') -> ObjectsBatch:
     """objects.py:157-186.  ``proposals`` is (N,5) f32: xyxy + objectness."""
     proposals = proposals.float()
     boxes, objectness = proposals.split((4, 1), dim=-1)
@@ -144,7 +149,7 @@ def objects_preprocess(image: PIL.Image.Image, proposals: torch.Tensor, grid: in
     if dry_run:
         keep[5:] = False
     boxes, objectness = boxes[keep], objectness[keep]
-    expanded = expand_adaptive(boxes, torch.tensor(image.size))
+    expanded = expand_adaptive(boxes, torch.tensor(image.size), expand_mode)
     lt2 = expanded[:, :2].repeat(1, 2)
     foregrounds = boxes - lt2
     crops, masks = [], []

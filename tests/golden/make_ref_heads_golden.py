@@ -28,7 +28,7 @@ sys.path.insert(0, str(HERE))
 
 import make_ref_golden as base  # noqa: E402
 
-N_ROIS, CHANNELS, FC = 37, 8, 64
+N_ROIS, CHANNELS, FC = 37, 8, 128  # FC: the classifier kernels' backward wants in_features % 128 == 0
 
 
 def head_config(prompts_path: str) -> dict:
@@ -85,7 +85,7 @@ def main() -> None:
     ppath = HERE / '_ref_prompts.tmp.pth'
     torch.save(prompts, ppath)
     out = dict(reference_files=['oadp/dp/bbox_heads.py', 'oadp/dp/roi_heads.py', 'oadp/dp/classifiers.py',
-                                'oadp/dp/utils.py', 'oadp/base/losses.py', 'oadp/base/globals_.py'])
+                                'oadp/dp/utils.py', 'oadp/base/losses.py', 'oadp/base/globals_.py', 'oadp/oake/objects.py'])
     try:
         cfg = head_config(str(ppath))
         cfg = {k: stubs._AttrDict(v) if isinstance(v, dict) else v for k, v in cfg.items()}
@@ -125,6 +125,23 @@ def main() -> None:
     h1.remove()
     h2.remove()
     G.Globals.training = False
+
+    # ---- objects.py: ExpandMode.CONSTANT (objects.py:92-93), expansion + preprocessing by the reference itself
+    import PIL.Image
+    from torchvision.datasets.vision import StandardTransform
+    ods = m['objects'].COCODataset.__new__(m['objects'].COCODataset)
+    ods._grid = 14
+    ods._expand_mode = m['objects'].ExpandMode['CONSTANT']
+    ods.transforms = StandardTransform(stubs.clip_transform(224), None)
+    images, proposals = base.ref_inputs()
+    out['expand_constant'] = []
+    for arr, prop in zip(images[:2], proposals[:2]):
+        pil = PIL.Image.fromarray(arr)
+        ods._proposals = {1: torch.tensor(prop, dtype=torch.float32)}
+        ob = ods._preprocess(1, pathlib.Path('x.pth'), pil)
+        expanded = ods._expand(stubs._BBoxesXYXY(ob.bboxes), torch.tensor(pil.size)).to_tensor()
+        out['expand_constant'].append(dict(bboxes=ob.bboxes, expanded=expanded, masks=ob.masks.to(torch.uint8),
+                                           pixels=base.checksums(ob.objects)))
     torch.save(out, HERE / 'ref_heads_golden.pt')
     print(f'wrote ref_heads_golden.pt ({(HERE / "ref_heads_golden.pt").stat().st_size / 1024:.0f} KiB); '
           f'eval cls_score {tuple(out["eval_cls_score"].shape)}, block loss {float(out["block_loss"]):.6f}, '

@@ -126,3 +126,68 @@ def test_cli_refuses_random_weights_unless_told(dataset, monkeypatch):
     import oadp.oake.globals as cli_globals
     with pytest.raises(RuntimeError, match='OAKE_CLIP_WEIGHTS'):
         cli_globals.Validator.main(['t', dataset['configs']['globals']])
+
+
+def test_run_iter_is_the_single_image_form_of_run(dataset, monkeypatch, tmp_path):
+    """The reference's loop body `_run_iter(batch, memo)` (base.py:106-113) and the batched `run()` write the
+    same bytes; a batch preprocessed the reference's way (float crops + masks) goes through the same tower."""
+    monkeypatch.delenv('DRY_RUN', raising=False)
+    from oadp_b200.compat import Config
+    from oadp_b200.oake import base as obase
+    from oadp_b200.oake import objects as oobjects
+    cfg = Config.load(dataset['configs']['objects'])
+    model, preprocess = oobjects.Validator._build_model()
+    assert preprocess is None and model.visual.grid == 14
+    outs = {}
+    for name in ('single', 'batched'):
+        split = Config(cfg.val)
+        split.dataloader.dataset.output_dir = str(tmp_path / name)
+        v = oobjects.Validator('t', model, **split, **{k: v for k, v in cfg.items() if k not in ('train', 'val')})
+        if name == 'single':
+            for batch in v._dataloader:
+                memo = obase.Memo()
+                if v._control_run_iter(batch, memo) is obase.Control.CONTINUE:
+                    continue
+                assert float(v._run_iter(batch, memo)) == 0.0 and set(memo['result']) == {'embeddings', 'bboxes', 'objectness'}
+        else:
+            assert v.run() == len(dataset['ids'])
+        outs[name] = {p.name: torch.load(p) for p in sorted((tmp_path / name).glob('*.pth'))}
+    assert outs['single'].keys() == outs['batched'].keys() and len(outs['single']) == len(dataset['ids'])
+    for k, a in outs['single'].items():
+        for field in ('embeddings', 'bboxes', 'objectness'):
+            assert torch.equal(a[field], outs['batched'][k][field])
+    # the reference's own batch layout: PIL-preprocessed crops, filtered boxes, 14x14 masks (objects.py:157-186)
+    root = pathlib.Path(dataset['root'])
+    id0 = dataset['ids'][0]
+    pil = PIL.Image.open(root / 'images' / f'{id0:012d}.png').convert('RGB')
+    ro = ofe.objects_preprocess(pil, torch.from_numpy(synth.proposals(*pil.size, 20, seed=2 * 7919 + 0)))
+    ref_batch = oobjects.Batch(tmp_path / 'ref_style.pth', ro.objects, ro.bboxes, ro.objectness, ro.masks)
+    memo = obase.Memo()
+    v._run_iter(ref_batch, memo)
+    stored = torch.load(tmp_path / 'ref_style.pth')
+    native = outs['batched'][f'{id0:012d}.pth']
+    assert torch.equal(stored['bboxes'], native['bboxes']) and torch.equal(stored['objectness'], native['objectness'])
+    assert cos_ok(stored['embeddings'], native['embeddings'])  # PIL pixels vs GPU pixels: same crops up to fp16 rounding
+
+
+def test_cli_expand_mode_constant(dataset, monkeypatch, tmp_path):
+    """`expand_mode='CONSTANT'` (objects.py:92-93): 224-px squares instead of sqrt(8 w h)."""
+    monkeypatch.delenv('DRY_RUN', raising=False)
+    import oadp.oake.objects as cli_objects
+    root = pathlib.Path(dataset['root'])
+    out = tmp_path / 'const'
+    cli_objects.Validator.main(['t', dataset['configs']['objects'], '--override',
+                                '.val.dataloader.dataset.expand_mode::CONSTANT', '.train.dataloader.dataset.expand_mode::CONSTANT',
+                                f'.val.dataloader.dataset.output_dir::{out}/val',
+                                f'.train.dataloader.dataset.output_dir::{out}/train'])
+    id0 = dataset['ids'][0]
+    pil = PIL.Image.open(root / 'images' / f'{id0:012d}.png').convert('RGB')
+    props = torch.from_numpy(synth.proposals(*pil.size, 20, seed=2 * 7919 + 0))
+    ro = ofe.objects_preprocess(pil, props, expand_mode='CONSTANT')
+    p197 = vit.objects_surgery(vit.init_visual_params(0))
+    o = torch.load(out / 'val' / f'{id0:012d}.pth')
+    assert torch.equal(o['bboxes'], ro.bboxes.half())
+    assert cos_ok(o['embeddings'], vit.normalize_half(vit.encode_objects(p197, ro.objects, ro.masks)))
+    adaptive = torch.load(root / 'oake' / 'objects' / 'val' / f'{id0:012d}.pth') if (root / 'oake' / 'objects' / 'val').exists() else None
+    if adaptive is not None:
+        assert not torch.equal(adaptive['embeddings'], o['embeddings'])
