@@ -19,7 +19,8 @@ pytestmark = pytest.mark.gpu
 GOLDEN = torch.load(pathlib.Path(__file__).parent / 'golden' / 'vit_golden.pt')
 
 COS_TOL = 1e-3  # north_star: "within 1e-3 cosine"
-REL_L2_TOL = 3e-2
+REL_L2_TOL = 5e-3  # measured 1.3e-3 (fp16 operands and residual stream, fp32 accumulation)
+CENTRED_TOL = 2e-3  # 1 - cosine after removing the direction all crops of a random tower share
 
 
 def check_close(got: torch.Tensor, want: torch.Tensor, what: str):
@@ -58,17 +59,51 @@ def test_t197_matches_golden(model):
     check_close(emb, vit.normalize_half(GOLDEN['t197']), 't197 normalised')
 
 
+def centred(got: torch.Tensor, want: torch.Tensor, what: str) -> float:
+    """Seeded random towers map every crop near ONE common direction, so the plain cosine is blind (2e-7 while
+    the relative L2 error is 1e-3).  Remove the oracle's mean row from both sides and compare what is left:
+    the part of the embedding that actually depends on the crop."""
+    got, want = got.float().cpu(), want.float().cpu()
+    mu = want.mean(0, keepdim=True)
+    cos = F.cosine_similarity(got - mu, want - mu, dim=-1)
+    spread = ((want - mu).norm(dim=-1) / want.norm(dim=-1)).mean().item()
+    worst = (1 - cos).max().item()
+    print(f'{what}: centred 1-cos {worst:.2e} (crop-dependent part = {spread:.1%} of the row norm)')
+    return worst
+
+
 def test_centered_agreement(model):
-    """Random towers map every crop near a common direction; remove it so that the comparison is
-    not dominated by that shared component."""
     g = torch.Generator().manual_seed(99)
     pixels = torch.randn(24, 3, 224, 224, generator=g) * 1.2
     p = vit.init_visual_params(GOLDEN['weight_seed'])
     want = vit.encode_image(p, pixels)
-    got = model.encode_image(pixels.cuda()).cpu()
-    mu = want.mean(0, keepdim=True)
-    cos = F.cosine_similarity(got - mu, want - mu, dim=-1)
-    assert (1 - cos).max() < 5e-3, (1 - cos).max().item()
+    got = model.encode_image(pixels.cuda())
+    assert centred(got, want, 't50') < CENTRED_TOL
+    check_close(got, want, 't50 random crops')
+
+
+def test_centered_agreement_t197_side_stream(model):
+    """The same for the objects tower: T = 197 tokens and the mask-attended side stream (objects.py:198-266),
+    with masks of every kind -- empty, full, and random foreground boxes."""
+    g = torch.Generator().manual_seed(98)
+    n = 12
+    pixels = torch.randn(n, 3, 224, 224, generator=g) * 1.2
+    masks = torch.ones(n, 1, 14, 14)
+    for i in range(n):
+        x0, y0 = torch.randint(0, 10, (2, ), generator=g).tolist()
+        w, h = torch.randint(2, 14, (2, ), generator=g).tolist()
+        masks[i, 0, y0:y0 + h, x0:x0 + w] = 0  # 0 = foreground
+    masks[0] = 0
+    masks[1] = 1
+    p197 = vit.objects_surgery(vit.init_visual_params(GOLDEN['weight_seed']))
+    want = vit.encode_objects(p197, pixels, masks)
+    model.for_objects()
+    got = model.visual(pixels.cuda(), masks.cuda())
+    assert centred(got, want, 't197 + side stream') < CENTRED_TOL
+    check_close(got, want, 't197 random crops')
+    # the side stream really is in play: the same crops with opposite masks give different rows
+    other = model.visual(pixels.cuda(), (1 - masks).cuda()).cpu()
+    assert (F.cosine_similarity(other - want.mean(0, keepdim=True), want - want.mean(0, keepdim=True), dim=-1) < 0.999).any()
 
 
 def test_batch_composition_is_invisible(model):
