@@ -50,6 +50,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
     extra_flags = list(extra_flags or [])
     if os.environ.get('OAKE_USE_BF16') == '1':
         extra_flags.append('-DOAKE_USE_BF16')
+    extra_flags += os.environ.get('OAKE_NVCC_FLAGS', '').split()  # developer A/B builds (-DOAKE_ATTN_POLY=0 ...)
     stamp = OBJ_DIR / 'stamp'
     digest = _digest(extra_flags)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:

@@ -37,6 +37,21 @@ namespace {
 
 using namespace attn;
 
+// -DOAKE_ATTN_TRACE: block 0 records clock64() at the hand-over points of the first 32 tiles (developer builds
+// only: tools/gpu_attn_trace.sh); otherwise the macro vanishes.
+#ifdef OAKE_ATTN_TRACE
+__device__ long long g_attn_trace[8 * 32 * 4];
+#define OAKE_TRACE(role, k, ev)                                                                        \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (role) < 7 && (k) < 32)                          \
+      g_attn_trace[((role) * 32 + (k)) * 4 + ((ev) & 3)] = clock64();                                        \
+  } while (0)
+#else
+#define OAKE_TRACE(role, k, ev) \
+  do {                          \
+  } while (0)
+#endif
+
 template <bool SIDE>
 struct CCfg {
   static constexpr int P = 196;
@@ -65,7 +80,23 @@ struct CCfg {
   static constexpr int kLoaderWarp = 12;
   static constexpr int kMmaWarp = 13;
   static constexpr int kThreads = 32 * 14;
+  // Register-resident form (RS): 16 warps = four warpgroups, the unit `setmaxnreg` works on.  At launch every
+  // thread owns 128 registers (64 K / 512); the two softmax warpgroups then grow to kRegsSoftmax (a half row of
+  // S, 96 / 112 scores, lives in registers from one TMEM read to the exponentials), paid for by the drain
+  // warpgroup (kRegsDrain) and the loader / MMA / two idle warps (kRegsMisc): 2*176 + 104 + 56 = 512 = 4 * 128.
+  static constexpr int kThreadsRS = 32 * 16;
+  static constexpr int kRegsSoftmax = 176, kRegsDrain = 104, kRegsMisc = 56;
 };
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;\n" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return d;
+}
 
 // How a softmax warp biases its scores.
 //   kPlain: main-stream rows only.  Keys 0..196 (patches, class) valid, no bias.
@@ -88,6 +119,10 @@ __device__ __noinline__ void pair_sync(int q) {
     default: asm volatile("bar.sync 4, 64;\n" ::: "memory"); break;
   }
 }
+
+// RS kernels: the same barrier without the call (an ABI call with a half row of scores live in registers would
+// move them around the callee-saved set); the id is a register operand.
+__device__ __forceinline__ void pair_sync_inline(int q) { asm volatile("bar.sync %0, 64;\n" ::"r"(q + 1) : "memory"); }
 
 // One half (HI = 0: keys 0..95, HI = 1: keys 96..207) of one query row.  The arithmetic of a
 // main-stream row is the same in every mode (bias added after the fma), so a row gets bit-identical
@@ -172,9 +207,9 @@ struct HalfRow {
         for (int e = 0; e < 2; ++e) {
           const int jj = 2 * j + e;
           if (MODE == kPlain) {
-            p[e] = ex2(fmaf(__uint_as_float(ra[jj]), scale, neg_mx));
+            p[e] = ex2_sel(fmaf(__uint_as_float(ra[jj]), scale, neg_mx), use_poly(j));
           } else {  // bias added after the fma: same bits as kPlain for a main-stream row (bias 0)
-            p[e] = ex2(fmaf(__uint_as_float(ra[jj]), scale, neg_mx) + patch_bias(k0 + c * 32 + jj, jj, wa));
+            p[e] = ex2_sel(fmaf(__uint_as_float(ra[jj]), scale, neg_mx) + patch_bias(k0 + c * 32 + jj, jj, wa), use_poly(j));
           }
         }
         s4[j & 3] += p[0] + p[1];
@@ -217,8 +252,161 @@ __device__ __forceinline__ void softmax_half(uint32_t t_row, bool is_y, uint32_t
   *xsum_mine = h.pass_exp(-mx);
 }
 
-template <bool SIDE>
-__global__ void __launch_bounds__(CCfg<SIDE>::kThreads, 1)
+// ------------------------------------------------------------------------------------------------
+// Register-resident half row (RS kernels).  What bounds the two-pass form above is not a pipe but the
+// tcgen05.ld itself: one 32x32b.x32 load occupies a warp for >= 110 cycles however many are queued
+// (tools/probes/tmem_probe.cu: 37 B/clk for one warp, 66 for the two of a sub-partition), and a half row was
+// swept twice -- seven or eight loads per tile with the MUFU pipe idle under each.  Here the half row is read
+// ONCE: all loads are issued back to back into registers, the maximum, the exchange with the other half's warp
+// and the exponentials then run from registers.  As the exponentials consume a 32-score chunk its registers are
+// refilled with the SAME chunk of the warp's next tile (whose S has long been complete: the PV -> drain -> S
+// chain of a tile is shorter than the softmax of the other one), so in steady state a tile starts with its
+// scores already in registers and the MUFU pipe sees one gap per tile (maximum + exchange) instead of eight.
+// Same arithmetic per element as HalfRow, so batch composition stays invisible; kLoad masks (non 0 / 1 values)
+// keep the two-pass form.
+// ------------------------------------------------------------------------------------------------
+template <bool SIDE, int HI>
+struct RegRow {
+  using C = CCfg<SIDE>;
+  static constexpr float scale = 0.125f * kLog2e;
+  static constexpr float kNegB = -100.0f * kLog2e;
+  static constexpr int k0 = HI ? C::kSplit : 0;
+  static constexpr int kTail = 192;
+  static constexpr int pbase = HI ? C::kPHi : 0;
+
+  __device__ static __forceinline__ void issue_chunk(uint32_t t_row, int c, uint32_t (&a)[32]) {
+    tmem_ld_32x32(t_row + k0 + c * 32, a);
+  }
+  __device__ static __forceinline__ void issue_tail(uint32_t t_row, uint32_t (&tail)[16]) {
+    if (HI) tmem_ld_32x16(t_row + kTail, tail);
+  }
+};
+
+// One tile of one half row from registers.  The scores arrive biased already (`bias_side_row`), so there is one
+// form for every row.  `pre`: refill the consumed chunks from `t_next`.  Returns the partial row sum.
+template <bool SIDE, int HI>
+__device__ __forceinline__ float softmax_regs(uint32_t (&a0)[32], uint32_t (&a1)[32], uint32_t (&a2)[32],
+                                              uint32_t (&tail)[16], uint32_t t_row, uint32_t t_next, uint64_t* next_full,
+                                              uint32_t next_parity, uint32_t& have, int q, float* xmax_mine,
+                                              const float* xmax_other, int trace_role = 7, int trace_k = 0) {
+  using R = RegRow<SIDE, HI>;
+  using C = CCfg<SIDE>;
+  constexpr float scale = R::scale;
+  constexpr int kTailLive = C::TQ - R::kTail;  // keys 192 .. 196 (, 197): what is not padding
+
+  // ---- maximum of the raw scores (the scale is positive: max(s) * scale == max(s * scale))
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  auto max_chunk = [&](const uint32_t (&a)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(a[j]), __uint_as_float(a[j + 1]));
+  };
+  max_chunk(a0);
+  max_chunk(a1);
+  max_chunk(a2);
+  float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  if (HI) {
+#pragma unroll
+    for (int j = 0; j < kTailLive; ++j) mx = fmaxf(mx, __uint_as_float(tail[j]));
+  }
+  mx *= scale;
+  *xmax_mine = mx;
+  pair_sync_inline(q);
+  const float neg_mx = -fmaxf(mx, *xmax_other);
+  OAKE_TRACE(trace_role, trace_k, 2);  // softmax: maximum exchanged
+
+  // ---- exponentials -> packed fp16 P behind the reads.  A consumed chunk's registers are refilled with the same
+  // chunk of the warp's next tile as soon as that tile's S is complete (`next_full`; nullptr = no next tile):
+  // asked again before every refill, so a tile whose S lands in the middle of this phase still gets its later
+  // chunks early.  `have` collects which chunks (bit c; bit 3 = tail) are on their way.
+  have = 0u;
+  bool ready = false;
+  auto poll = [&]() {
+    if (next_full != nullptr && !ready) {
+      ready = __all_sync(0xffffffffu, mbar_test_wait(next_full, next_parity));
+      if (ready) tc_fence_after();
+    }
+  };
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  auto exp_chunk = [&](uint32_t (&a)[32], int c) {
+    uint32_t pa[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      // (all on the MUFU pipe here: with the polynomial mixed in, this fully unrolled phase ran 50 % SLOWER)
+      const float p0 = ex2(fmaf(__uint_as_float(a[2 * j]), scale, neg_mx));
+      const float p1 = ex2(fmaf(__uint_as_float(a[2 * j + 1]), scale, neg_mx));
+      s4[j & 3] += p0 + p1;
+      pa[j] = pack2(p0, p1);
+    }
+    tmem_st_32x16(t_row + R::pbase + c * 16, pa);
+    poll();
+    if (ready) {
+      R::issue_chunk(t_next, c, a);
+      have |= 1u << c;
+    }
+  };
+  exp_chunk(a0, 0);
+  exp_chunk(a1, 1);
+  exp_chunk(a2, 2);
+  if (HI) {
+    uint32_t pt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) p[e] = 2 * j + e < kTailLive ? ex2(fmaf(__uint_as_float(tail[2 * j + e]), scale, neg_mx)) : 0.f;
+      s4[j & 3] += p[0] + p[1];
+      pt[j] = pack2(p[0], p[1]);
+    }
+    tmem_st_32x8(t_row + R::pbase + 48, pt);
+    poll();
+    if (ready) {
+      R::issue_tail(t_next, tail);
+      have |= 8u;
+    }
+  }
+  return (s4[0] + s4[1]) + (s4[2] + s4[3]);
+}
+
+// SIDE kernels, after the scores of a tile have landed in registers: what distinguishes the side row from the
+// main-stream rows is added to the raw scores once (objects.py:204-247) -- for the side row -100 mask[key] on
+// the patches (in score units: / 0.125) and -inf on the class key (it sees itself instead); for every other row
+// -inf on the side token's key.  Main-stream rows add exactly 0 to their patch scores, so a row's bits do not
+// depend on whether the side row shares its warp.  Any fp32 mask values are honoured (0 / 1 in the reference).
+template <bool SIDE, int HI>
+__device__ __forceinline__ void bias_side_row(uint32_t (&a0)[32], uint32_t (&a1)[32], uint32_t (&a2)[32],
+                                              uint32_t (&tail)[16], bool warp_y, bool is_y, uint32_t ymask_addr) {
+  using R = RegRow<SIDE, HI>;
+  using C = CCfg<SIDE>;
+  if (!SIDE) return;
+  constexpr float kPerMask = -100.0f / 0.125f;
+  if (warp_y) {  // warp-uniform: only the warp pair that holds the side row pays for the mask row
+    auto add = [&](uint32_t (&a)[32], int c) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float m = lds_f32(ymask_addr + (R::k0 + c * 32 + j) * 4);  // same address in every lane: a broadcast
+        a[j] = __float_as_uint(__uint_as_float(a[j]) + (is_y ? kPerMask * m : 0.f));
+      }
+    };
+    add(a0, 0);
+    add(a1, 1);
+    add(a2, 2);
+    if (HI) {
+#pragma unroll
+      for (int j = 0; j < C::P - R::kTail; ++j) {
+        const float m = lds_f32(ymask_addr + (R::kTail + j) * 4);
+        tail[j] = __float_as_uint(__uint_as_float(tail[j]) + (is_y ? kPerMask * m : 0.f));
+      }
+    }
+  }
+  if (HI) {
+    constexpr int jc = C::P - R::kTail, js = C::T - R::kTail;  // class key, side key
+    tail[jc] = is_y ? __float_as_uint(-INFINITY) : tail[jc];
+    tail[js] = is_y ? tail[js] : __float_as_uint(-INFINITY);
+  }
+}
+
+template <bool SIDE, bool RS>
+__global__ void __launch_bounds__(RS ? CCfg<SIDE>::kThreadsRS : CCfg<SIDE>::kThreads, 1)
 attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], box {64, 128}
                     const __grid_constant__ CUtensorMap tmQ1,  // qkv [R, 3W], box {64, 68}
                     const __grid_constant__ CUtensorMap tmKV,  // qkv [R, 3W], box {64, 196}
@@ -272,7 +460,11 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == C::kLoaderWarp) {
+  // RS: register hand-over between the warpgroups.  Each `setmaxnreg` sits at the top of the code its
+  // warpgroup runs (ptxas budgets registers per region: after a join of regions it assumes the smallest).
+  if (warp >= C::kLoaderWarp) {
+   if (RS) setmaxnreg_dec<C::kRegsMisc>();
+   if (warp == C::kLoaderWarp) {
     // ================================================================== loader
     for (int n = 0; n < N; ++n) {
       const int s = n & 1, u = n >> 1;
@@ -327,40 +519,40 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
       cp_async_arrive_noinc(&v_full[s]);
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");  // nothing of this warp in flight at exit
-  } else if (warp == C::kMmaWarp) {
+   } else if (warp == C::kMmaWarp) {
     // ================================================================== MMA issue
     constexpr uint32_t idesc_s = make_idesc_f16(128, C::NK);
     constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, kDh);
+    // every operand below derives from warp-uniform values: all 32 lanes run this loop, the election of the
+    // issuing lane happens inside the *_warp wrappers
     const uint32_t smem_base = smem_u32(smem);
-    auto issue_s = [&](int n, int t) {  // lane 0 only
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    auto issue_s = [&](int n, int t) {
       const uint32_t stg = smem_base + (n & 1) * C::kStage;
       const uint32_t q_addr = stg + t * C::kQTile, k_addr = stg + 2 * C::kQTile;
 #pragma unroll
       for (int k = 0; k < kDh / 16; ++k)
-        umma_f16(tmem_base + t * C::kBufCols, make_smem_desc_k_sw128(q_addr + k * 32),
-                 make_smem_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(&s_full[t]);
+        umma_f16_ss_warp(tmem_u + t * C::kBufCols, make_smem_desc_k_sw128(q_addr + k * 32),
+                         make_smem_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+      umma_commit_warp(&s_full[t]);
     };
-    auto issue_pv = [&](int n, int t) {  // lane 0 only
+    auto issue_pv = [&](int n, int t) {
       const uint32_t v_addr = smem_base + (n & 1) * C::kStage + 2 * C::kQTile + C::kKV;
-      const uint32_t buf = tmem_base + t * C::kBufCols;
+      const uint32_t buf = tmem_u + t * C::kBufCols;
 #pragma unroll
       for (int k = 0; k < C::kUnits; ++k) {
         const uint32_t p_col = k * 16 < C::kSplit ? k * 8 : C::kPHi + (k - C::kSplit / 16) * 8;
-        umma_f16_ts(buf + C::kOCol, buf + p_col, make_smem_desc_mn_sw128(v_addr + k * 2048), idesc_o, k != 0 ? 1u : 0u);
+        umma_f16_ts_warp(buf + C::kOCol, buf + p_col, make_smem_desc_mn_sw128(v_addr + k * 2048), idesc_o, k != 0 ? 1u : 0u);
       }
-      umma_commit(&o_full[t]);
+      umma_commit_warp(&o_full[t]);
     };
     if (N > 0) {
       mbar_wait(&qk_full[0], 0);
       fence_proxy_async();  // the loader's cp.async rows (generic proxy) -> tensor core reads
       tc_fence_after();
-      if (lane == 0) {
-        issue_s(0, 0);
-        issue_s(0, 1);
-        umma_commit(&qk_free[0]);
-      }
-      __syncwarp();
+      issue_s(0, 0);
+      issue_s(0, 1);
+      umma_commit_warp(&qk_free[0]);
     }
     for (int n = 0; n < N; ++n) {
       const int s = n & 1, u = n >> 1;
@@ -369,30 +561,109 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         mbar_wait(&p_ready[t], n & 1);
+        OAKE_TRACE(1, 2 * n + t, 0);  // mma: p_ready seen
         tc_fence_after();
-        if (lane == 0) {
-          issue_pv(n, t);
-          if (t == 1) umma_commit(&v_free[s]);
-        }
-        __syncwarp();
+        issue_pv(n, t);
+        OAKE_TRACE(1, 2 * n + t, 1);  // mma: PV issued
+        if (t == 1) umma_commit_warp(&v_free[s]);
         if (n + 1 < N) {
           if (t == 0) {
             mbar_wait(&qk_full[s ^ 1], ((n + 1) >> 1) & 1);
             fence_proxy_async();
           }
           mbar_wait(&o_free[t], n & 1);
+          OAKE_TRACE(1, 2 * n + t, 2);  // mma: o_free seen
           tc_fence_after();
-          if (lane == 0) {
-            issue_s(n + 1, t);
-            if (t == 1) umma_commit(&qk_free[s ^ 1]);
-          }
-          __syncwarp();
+          issue_s(n + 1, t);
+          OAKE_TRACE(1, 2 * n + t, 3);  // mma: S(n+1, t) issued
+          if (t == 1) umma_commit_warp(&qk_free[s ^ 1]);
         }
       }
     }
+   }  // (RS: warps 14 and 15 only complete the fourth warpgroup)
+  } else if (RS && warp < C::kDrainWarp0) {
+    // ================================================================== softmax warps, register-resident form
+    setmaxnreg_inc<C::kRegsSoftmax>();
+    const int q = warp & 3;
+    const int hi = warp >> 2;
+    const int r = q * 32 + lane;
+    uint32_t a0[32], a1[32], a2[32], tail[16];
+    uint32_t have = 0u;  // chunks of the current tile that are already in (or on their way to) the registers
+    constexpr uint32_t kAll = 15u;
+    auto tile_rows = [&](int n_, int t_, bool& live_, bool& is_y_) {
+      const int shift1 = (t_ == 1 && (n_ & 1)) ? C::kShift : 0;
+      const int rr = r - shift1;
+      live_ = t_ == 0 || (rr >= 0 && rr < C::kRows1);
+      is_y_ = SIDE && live_ && t_ * 128 + rr == C::T;
+    };
+    bool live, is_y;
+    tile_rows(0, 0, live, is_y);
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1, u = n >> 1;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const bool warp_live = __any_sync(0xffffffffu, live);
+        const bool warp_y = SIDE && __any_sync(0xffffffffu, is_y);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * C::kBufCols;
+        float* xm = xmax + (t * 2) * 128 + r;
+        float* xs = xsum + (t * 2) * 128 + r;
+        OAKE_TRACE(warp == 0 ? 5 : (warp == 6 ? 6 : 7), 2 * n + t, have);  // (debug: slot = chunks prefetched)
+        if (have == 0u) {  // (a tile with refilled chunks has already seen this phase of s_full complete)
+          mbar_wait(&s_full[t], n & 1);
+          tc_fence_after();
+        }
+        OAKE_TRACE(warp == 0 ? 0 : (warp == 6 ? 4 : 7), 2 * n + t, 0);  // softmax: s_full seen (or prefetched)
+        // the warp's next tile
+        const int n2 = t == 0 ? n : n + 1, t2 = t ^ 1;
+        bool live2 = false, is_y2 = false;
+        if (n2 < N) tile_rows(n2, t2, live2, is_y2);
+        if (warp_live) {
+          uint32_t ymask_addr = 0u;
+          if (warp_y) {
+            mbar_wait(&v_full[s], u & 1);  // the crop's mask row lands with the V stage
+            ymask_addr = smem_u32(ymask + s * C::kMaskFloats);
+          }
+          if (hi == 0) {
+            if (!(have & 1u)) RegRow<SIDE, 0>::issue_chunk(t_row, 0, a0);
+            if (!(have & 2u)) RegRow<SIDE, 0>::issue_chunk(t_row, 1, a1);
+            if (!(have & 4u)) RegRow<SIDE, 0>::issue_chunk(t_row, 2, a2);
+          } else {
+            if (!(have & 1u)) RegRow<SIDE, 1>::issue_chunk(t_row, 0, a0);
+            if (!(have & 2u)) RegRow<SIDE, 1>::issue_chunk(t_row, 1, a1);
+            if (!(have & 4u)) RegRow<SIDE, 1>::issue_chunk(t_row, 2, a2);
+            if (!(have & 8u)) RegRow<SIDE, 1>::issue_tail(t_row, tail);
+          }
+          // refill from the next tile only if this warp has rows there
+          uint64_t* next_full = (n2 < N && __any_sync(0xffffffffu, live2)) ? &s_full[t2] : nullptr;
+          const uint32_t t_next = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t2 * C::kBufCols;
+          tmem_ld_wait();
+          OAKE_TRACE(warp == 0 ? 0 : (warp == 6 ? 4 : 7), 2 * n + t, 1);  // softmax: scores in registers
+          if (hi == 0) {
+            bias_side_row<SIDE, 0>(a0, a1, a2, tail, warp_y, is_y, ymask_addr);
+            *xs = softmax_regs<SIDE, 0>(a0, a1, a2, tail, t_row, t_next, next_full, n2 & 1, have, q, xm, xm + 128,
+                                        warp == 0 ? 0 : 7, 2 * n + t);
+          } else {
+            bias_side_row<SIDE, 1>(a0, a1, a2, tail, warp_y, is_y, ymask_addr);
+            xs[128] = softmax_regs<SIDE, 1>(a0, a1, a2, tail, t_row, t_next, next_full, n2 & 1, have, q, xm + 128, xm,
+                                            warp == 6 ? 4 : 7, 2 * n + t);
+          }
+          tmem_st_wait();
+        } else {
+          have = 0u;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[t]);
+        OAKE_TRACE(warp == 0 ? 0 : (warp == 6 ? 4 : 7), 2 * n + t, 3);  // softmax: p_ready arrived
+        live = live2;
+        is_y = is_y2;
+      }
+    }
+    (void)kAll;
   } else {
-    // ================================================================== softmax and drain warps
-    const bool drain = warp >= C::kDrainWarp0;
+    // ================================================================== softmax and drain warps (RS: drain only)
+    if (RS) setmaxnreg_dec<C::kRegsDrain>();
+    const bool drain = RS ? true : warp >= C::kDrainWarp0;
     const int q = warp & 3;                    // TMEM lane quarter (== warp % 4 for both roles)
     const int hi = drain ? 0 : (warp >> 2);    // softmax: which half of the keys
     const int r = q * 32 + lane;               // lane of the tile
@@ -454,6 +725,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
             mbar_wait(&p_ready[t], n & 1);  // all eight softmax warps done: the row sums are in place
             const float sum = xs[0] + xs[128];
             mbar_wait(&o_full[t], n & 1);
+            OAKE_TRACE(warp == 8 ? 2 : 7, 2 * n + t, 0);  // drain: o_full seen
             tc_fence_after();
             uint32_t o0[32], o1[32];
             tmem_ld_32x32(t_row + C::kOCol, o0);
@@ -464,6 +736,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_free[t]);
+            OAKE_TRACE(warp == 8 ? 2 : 7, 2 * n + t, 1);  // drain: O in registers, o_free arrived
             const uint32_t stg = smem_u32(out_stage + (warp - C::kDrainWarp0) * C::kOutStage);
             {
               const float inv = 1.0f / sum;
@@ -510,10 +783,22 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
   }
 }
 
-template <bool SIDE>
+// OAKE_ATTN=rs selects the register-resident kernel (RS).  Measured on B200 it is exactly as fast as the two-pass
+// form: both are bound by the exponentials of the slower (upper-half) softmax warp of a lane quarter, not by the
+// tcgen05.ld sweeps RS removes (profiles/r2_05_attention_analysis.txt).  The two-pass kernel stays the default.
+bool attention_rs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OAKE_ATTN");
+    v = (e != nullptr && e[0] == 'r') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <bool SIDE, bool RS>
 cudaError_t launch_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int heads, int rows) {
   using C = CCfg<SIDE>;
-  if (cudaError_t e = ensure_dynamic_smem<attention_cs_kernel<SIDE>>(C::kSmemBytes); e != cudaSuccess) return e;
+  if (cudaError_t e = ensure_dynamic_smem<attention_cs_kernel<SIDE, RS>>(C::kSmemBytes); e != cudaSuccess) return e;
   int dev = 0, num_sms = 0;
   if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
   if (cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); e != cudaSuccess) return e;
@@ -524,7 +809,8 @@ cudaError_t launch_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_
     return cudaErrorInvalidValue;
   const int items = B * heads;
   const int grid = items < num_sms ? items : num_sms;
-  attention_cs_kernel<SIDE><<<grid, C::kThreads, C::kSmemBytes, st>>>(tmQ0, tmQ1, tmKV, qkv, mask, out, B, heads);
+  attention_cs_kernel<SIDE, RS><<<grid, RS ? C::kThreadsRS : C::kThreads, C::kSmemBytes, st>>>(tmQ0, tmQ1, tmKV, qkv, mask, out,
+                                                                                              B, heads);
   return cudaGetLastError();
 }
 
@@ -542,6 +828,12 @@ bool attention_use_tc(int P, int side_only) {
   return v == 1 && P == 196 && !side_only;
 }
 
+#ifdef OAKE_ATTN_TRACE
+extern "C" int oake_debug_attn_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(g_attn_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 cudaError_t launch_attention_cs(cudaStream_t st, const act_t* qkv, const float* mask, act_t* out, int B, int P,
                                 int heads, int with_side, int side_only) {
   if (B <= 0) return cudaSuccess;
@@ -549,9 +841,11 @@ cudaError_t launch_attention_cs(cudaStream_t st, const act_t* qkv, const float* 
   const int rows = B * (P + 1) + (with_side ? B : 0);
   if (with_side) {
     if (mask == nullptr) return cudaErrorInvalidValue;
-    return launch_cs<true>(st, qkv, mask, out, B, heads, rows);
+    return attention_rs() ? launch_cs<true, true>(st, qkv, mask, out, B, heads, rows)
+                          : launch_cs<true, false>(st, qkv, mask, out, B, heads, rows);
   }
-  return launch_cs<false>(st, qkv, nullptr, out, B, heads, rows);
+  return attention_rs() ? launch_cs<false, true>(st, qkv, nullptr, out, B, heads, rows)
+                        : launch_cs<false, false>(st, qkv, nullptr, out, B, heads, rows);
 }
 
 }  // namespace oake

@@ -17,6 +17,28 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA pipe: round x to the nearest integer n with the 1.5 * 2^23 trick, a degree-3 minimax
+// polynomial for 2^f on f = x - n in [-0.5, 0.5] (max relative error 7.5e-5, a third of the half-ulp of the fp16 the
+// result is rounded to), and n added into the exponent field.  The MUFU pipe delivers 16 ex2 per clock and SM and
+// is what bounds the softmax (tools/probes/tmem_probe.cu); every kPolyEvery-th PAIR of keys takes this path
+// instead, chosen by key index only, so a row's arithmetic does not depend on where the row sits.
+#ifndef OAKE_ATTN_POLY
+#define OAKE_ATTN_POLY 3
+#endif
+constexpr int kPolyEvery = OAKE_ATTN_POLY;  // 0: every exponential on the MUFU pipe
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.055171605f, f, 0.24261111f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// pair index j of a 32-key chunk -> which pipe
+__device__ __forceinline__ constexpr bool use_poly(int j) { return kPolyEvery > 0 && (j % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1; }
+__device__ __forceinline__ float ex2_sel(float x, bool poly) { return poly ? ex2_poly(x) : ex2(x); }
+
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -60,6 +82,39 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Warp-uniform issue forms.  A tcgen05.mma / commit is one instruction of the WARP's uniform datapath; written as
+// `if (lane == 0) tcgen05.mma` ptxas cannot prove that a single lane is active and wraps every MMA in an
+// elect / R2UR.BROADCAST / BRA.U.ANY loop over the active lanes (12 dependent instructions, ~95 cycles per MMA:
+// the 13 k-steps of P V took 1100-2000 cycles to ISSUE, profiles/r2_05_attention_trace.txt).  Called by all 32
+// lanes with warp-uniform operands and the election inside the asm, the same MMA is 4 uniform instructions.
+__device__ __forceinline__ void umma_f16_ss_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
 
