@@ -2,7 +2,7 @@
 """OAKE crops/sec benchmark (BASELINE.json metric) -- one JSON line on stdout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload oake|globals|blocks|objects] [--images I]
+                    [--workload oake|globals|blocks|objects|classifier] [--images I]
 
 A step = one pass of the OAKE hot path over one batch of I synthetic COCO-shaped images per GPU:
 `oake` runs what the north star names -- globals (1 crop/image) + blocks (pyramid grid, 17..39
@@ -279,7 +279,7 @@ def main() -> None:
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='oake', choices=['oake', 'globals', 'blocks', 'objects'])
+    ap.add_argument('--workload', default='oake', choices=['oake', 'globals', 'blocks', 'objects', 'classifier'])
     ap.add_argument('--images', type=int, default=8, help='images per step per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-library-baseline', action='store_true')
@@ -315,6 +315,29 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit('bench.py --impl ours needs a CUDA device: the OAKE hot path has no CPU fallback')
     torch.cuda.set_device(local_rank % torch.cuda.device_count())
+    if args.workload == 'classifier':
+        # BASELINE configs 4-5 in isolation (mmdet is absent): the cosine classifier at the test-time
+        # shape (N = 1000 RoIs, in = 1024, K = 66 / 1204) and the LVIS training shape (fwd + bwd, bf16 inputs), each
+        # next to PyTorch eager on the same GPU.  value = RoIs/s of the first case (OV-COCO inference, fp16 RoI features).
+        if rank != 0:
+            return
+        from oadp_b200 import build
+        build.build()
+        sys.path.insert(0, str(ROOT / 'tools'))
+        import bench_classifier
+        cases = [bench_classifier.run(*c) for c in bench_classifier.CASES]
+        head = cases[0]
+        print(json.dumps(dict(metric='cosine classifier RoIs/sec (N=1000, in=1024, K=66, inference, fused call)',
+                              value=head['n'] / (head['us'] * 1e-6), unit='RoIs/s', n_gpus=1, steps=100, warmup=10,
+                              ms_per_step=head['us'] * 1e-3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                              dtype='f16', data='synthetic', config=dict(workload='classifier', cases='BASELINE configs 4-5 '
+                                                                         'in isolation (SURVEY 8d-4/5)'),
+                              roofline=dict(bound='hbm', achieved=head['gbs'], peak=pk['hbm_gbs'], unit='GB/s',
+                                            frac=head['gbs'] / pk['hbm_gbs'], traffic=None,
+                                            note='launch / latency bound at this size: 4.45 MB of algorithmic traffic is '
+                                                 '0.7 us of HBM time (BASELINE.md section 3)'),
+                              cases=cases)))
+        return
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', torch.cuda.current_device()))
     from oadp_b200 import build, synth

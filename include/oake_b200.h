@@ -167,6 +167,22 @@ int oake_cosine_logits_bwd(const float* h, const float* text, const float* bg, c
                            int num_all, int k_pad, float alpha, int ninf_lo, int ninf_hi, float* dh, float* dbg,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* Inference fast path (no gradient): both halves in ONE call on prepared operands -- what
+ * `bbox_head.fc_cls(x)` costs at test time (oadp/dp/roi_heads.py:64-112 calls it twice per image).
+ * oake_classifier_prepare casts W [512,in] (-> w_act) and / or packs E = [text ; normalised bg ; zero padding]
+ * (-> e_act [k_pad,512]) into the tensor-core type once per weight version (either half may be NULL).
+ * oake_classifier_fwd: x [N,in] in x_dtype (OAKE_DTYPE_*; the tensor-core type passes through without a copy),
+ * writes h [N,512] fp32 (the tensor the distiller hooks read) and logits [N,k_pad] fp32: 3 launches
+ * (GEMM, row normalise, GEMM), 4 with a cast of x.  Workspace: oake_classifier_workspace_bytes. */
+#define OAKE_DTYPE_F32 0
+#define OAKE_DTYPE_F16 1
+#define OAKE_DTYPE_BF16 2
+int oake_classifier_prepare(const float* w, int in_features, const float* text, const float* bg, int num_all,
+                            int k_pad, void* w_act, void* e_act, void* stream);
+int oake_classifier_fwd(const void* x, int x_dtype, const void* w_act, const float* bias, const void* e_act, int N,
+                        int in_features, int k_pad, float alpha, float shift, int ninf_lo, int ninf_hi, float* h,
+                        float* logits, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- ViLD ensemble scoring (oadp/dp/roi_heads.py:93-112, ViLDEnsembleRoIHead._bbox_forward) ------
  * out = log( softmax(bbox_logits)^lambda * softmax(object_logits)^(1-lambda) ), last column replaced
  * by log(1 - sum of the others).  All fp32 device pointers; logits (N, K1 = num_all + 1) with row

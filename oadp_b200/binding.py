@@ -11,6 +11,7 @@ LIB_PATH = pathlib.Path(__file__).resolve().parent / 'liboake_b200.so'
 
 VARIANT_T50 = 0
 VARIANT_T197 = 1
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 
 
 class OakeError(RuntimeError):
@@ -58,6 +59,11 @@ SIGNATURES = {
     'oake_cosine_logits_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_size_t, C.c_void_p]),
+    'oake_classifier_prepare': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    'oake_classifier_fwd': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_size_t, C.c_void_p]),
     'oake_vild_ensemble': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p]),
     'oake_loss_workspace_bytes': (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),

@@ -69,6 +69,39 @@ l2norm_rows_kernel(const float* __restrict__ h_raw, float* __restrict__ h, float
   if (lane == 0) inv_norm[row] = inv;
 }
 
+// Inference form of the same: also writes the normalised row in the tensor-core type, the A operand of the
+// logits GEMM that follows (one pass over h_raw instead of l2norm + cast).
+__global__ void __launch_bounds__(256)
+l2norm_rows_act_kernel(const float* __restrict__ h_raw, float* __restrict__ h, act_t* __restrict__ h_act, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* r4 = reinterpret_cast<const float4*>(h_raw + static_cast<size_t>(row) * kDim);
+  float4 v[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[j] = r4[lane + 32 * j];
+    ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  float4* o4 = reinterpret_cast<float4*>(h + static_cast<size_t>(row) * kDim);
+  uint2* a2 = reinterpret_cast<uint2*>(h_act + static_cast<size_t>(row) * kDim);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 o = make_float4(v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
+    o4[lane + 32 * j] = o;
+    a2[lane + 32 * j] = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
+  }
+}
+
+// x in fp16 / bf16 -> act_t (a copy when the types agree is never launched: the caller passes x through)
+template <typename T>
+__global__ void cast_from_kernel(const T* __restrict__ in, act_t* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = to_act(static_cast<float>(in[i]));
+}
+
 // dh_raw = (dh - h (h . dh)) * inv_norm   -- backward of F.normalize
 __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ h, const float* __restrict__ inv_norm,
@@ -281,7 +314,9 @@ int oake_classifier_workspace_bytes(int N, int in_features, int k_pad, size_t* o
                   up(static_cast<size_t>(in_features) * 512 * 2) + 1024;
   size_t cl_fwd = up(n * kDim * 2) + up(static_cast<size_t>(k_pad) * kDim * 2);
   size_t cl_bwd = up(n * k_pad * 2) + 2 * up(static_cast<size_t>(k_pad) * kDim * 2) + 1024;
+  size_t fused = up(n * in_features * 2) + up(n * kDim * 4) + up(n * kDim * 2);
   size_t m = nl_fwd;
+  if (fused > m) m = fused;
   if (nl_bwd > m) m = nl_bwd;
   if (cl_fwd > m) m = cl_fwd;
   if (cl_bwd > m) m = cl_bwd;
@@ -309,6 +344,74 @@ int oake_normalized_linear_fwd(const float* x, const float* w, const float* b, i
   GemmEpilogue ep{b, nullptr, nullptr, nullptr, nullptr, h_raw, kDim, 0, 1, 0};
   CK(launch_gemm(st, tmA, tmW, N, kDim, in_features, ep, num_sms()));
   l2norm_rows_kernel<<<(N + 7) / 8, 256, 0, st>>>(h_raw, h, inv_norm, N);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- inference fast path: NormalizedLinear + cosine logits in ONE call, prepared operands ------------------
+int oake_classifier_prepare(const float* w, int in_features, const float* text, const float* bg, int num_all,
+                            int k_pad, void* w_act, void* e_act, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (w != nullptr) {
+    if (!w_act || in_features <= 0) return fail_msg("bad argument");
+    const long long nw = 512ll * in_features;
+    cast_kernel<<<static_cast<unsigned>((nw / 4 + 256) / 256), 256, 0, st>>>(w, static_cast<act_t*>(w_act), nw);
+  }
+  if (text != nullptr) {
+    const int K = num_all + (bg ? 1 : 0);
+    if (!e_act || k_pad % 128 != 0 || k_pad < K) return fail_msg("k_pad must be a multiple of 128 and >= %d", K);
+    pack_embeddings_kernel<<<(k_pad + 7) / 8, 256, 0, st>>>(text, bg, num_all, k_pad, static_cast<act_t*>(e_act), nullptr);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int oake_classifier_fwd(const void* x, int x_dtype, const void* w_act, const float* bias, const void* e_act, int N,
+                        int in_features, int k_pad, float alpha, float shift, int ninf_lo, int ninf_hi, float* h,
+                        float* logits, void* ws, size_t ws_bytes, void* stream) {
+  if (N == 0) return 0;
+  if (!x || !w_act || !bias || !e_act || !h || !logits || !ws) return fail_msg("NULL buffer");
+  if (in_features % 64 != 0) return fail_msg("in_features must be a multiple of 64, got %d", in_features);
+  if (k_pad % 128 != 0) return fail_msg("k_pad must be a multiple of 128");
+#ifdef OAKE_USE_BF16
+  const int act_code = OAKE_DTYPE_BF16;
+#else
+  const int act_code = OAKE_DTYPE_F16;
+#endif
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Carver c(ws, ws_bytes);
+  act_t* x_act = static_cast<act_t*>(c.take(static_cast<size_t>(N) * in_features * 2));
+  float* h_raw = static_cast<float*>(c.take(static_cast<size_t>(N) * kDim * 4));
+  act_t* h_act = static_cast<act_t*>(c.take(static_cast<size_t>(N) * kDim * 2));
+  if (!c.ok()) return fail_msg("workspace too small");
+  const long long nx = static_cast<long long>(N) * in_features;
+  const act_t* a_ptr = x_act;
+  if (x_dtype == act_code) {
+    a_ptr = static_cast<const act_t*>(x);  // already in the tensor-core type (mmcv fp16 mode): no copy at all
+  } else if (x_dtype == OAKE_DTYPE_F32) {
+    cast_kernel<<<static_cast<unsigned>((nx / 4 + 256) / 256), 256, 0, st>>>(static_cast<const float*>(x), x_act, nx);
+  } else if (x_dtype == OAKE_DTYPE_F16) {
+    cast_from_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(static_cast<const __half*>(x), x_act, nx);
+  } else if (x_dtype == OAKE_DTYPE_BF16) {
+    cast_from_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), x_act, nx);
+  } else {
+    return fail_msg("x_dtype %d: expected OAKE_DTYPE_F32 / F16 / BF16", x_dtype);
+  }
+  if ((reinterpret_cast<uintptr_t>(a_ptr) & 15) != 0) return fail_msg("x must be 16-byte aligned");
+  CUtensorMap tmA, tmW, tmH, tmE;
+  if (make_tmap_act_2d(&tmA, a_ptr, N, in_features, 128) || make_tmap_act_2d(&tmW, w_act, kDim, in_features, gemm_block_n(kDim)) ||
+      make_tmap_act_2d(&tmH, h_act, N, kDim, 128) || make_tmap_act_2d(&tmE, e_act, k_pad, kDim, gemm_block_n(k_pad)))
+    return fail_msg("cuTensorMapEncodeTiled failed");
+  const int ns = num_sms();
+  GemmEpilogue ep1{bias, nullptr, nullptr, nullptr, nullptr, h_raw, kDim, 0, 1, 0};
+  CK(launch_gemm(st, tmA, tmW, N, kDim, in_features, ep1, ns));
+  l2norm_rows_act_kernel<<<(N + 7) / 8, 256, 0, st>>>(h_raw, h, h_act, N);
+  GemmEpilogue ep2{nullptr, nullptr, nullptr, nullptr, nullptr, logits, k_pad, 0, 1, 0};
+  ep2.alpha = alpha;
+  ep2.shift = shift;
+  ep2.ninf_lo = ninf_lo;
+  ep2.ninf_hi = ninf_hi;
+  CK(launch_gemm(st, tmH, tmE, N, k_pad, kDim, ep2, ns));
   CK(cudaGetLastError());
   return 0;
 }

@@ -27,6 +27,7 @@ from .categories import Globals
 __all__ = ['BaseClassifier', 'Classifier', 'ViLDClassifier', 'NormalizedLinear']
 
 DIM = 512
+_DTYPE_CODES = {torch.float32: binding.DTYPE_F32, torch.float16: binding.DTYPE_F16, torch.bfloat16: binding.DTYPE_BF16}
 
 
 def _kpad(k: int) -> int:
@@ -186,15 +187,68 @@ class BaseClassifier(nn.Module):
     def _affine(self) -> tuple:
         return 1.0, 0.0
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        h = self._linear(x)  # through __call__: forward hooks see the normalised tensor
+    # ------------------------------------------------------------------------------ inference fast path
+    def _prepared(self, device: torch.device, k_pad: int):
+        """W and E in the tensor-core type, re-made only when a parameter changed (`_version`) or moved."""
+        lin, bg = self._linear, self._bg_embedding
+        key = (lin.weight._version, lin.weight.data_ptr(), self._embeddings.data_ptr(),
+               None if bg is None else (bg._version, bg.data_ptr()), k_pad, str(device))
+        cache = getattr(self, '_prepared_cache', None)
+        if cache is None or cache[0] != key:
+            act = torch.float16 if binding.act_dtype_name() == 'f16' else torch.bfloat16
+            w_act = torch.empty(DIM, lin.in_features, device=device, dtype=act)
+            e_act = torch.empty(k_pad, DIM, device=device, dtype=act)
+            w32 = lin.weight.detach().float().contiguous()
+            t32 = self._embeddings.detach().float().contiguous()
+            b32 = bg.detach().float().contiguous().reshape(-1) if bg is not None else None
+            binding.check(binding.load().oake_classifier_prepare(
+                w32.data_ptr(), lin.in_features, t32.data_ptr(), b32.data_ptr() if b32 is not None else None,
+                t32.shape[0], k_pad, w_act.data_ptr(), e_act.data_ptr(), _stream(w_act)))
+            cache = (key, w_act, e_act, lin.bias.detach().float().contiguous())
+            self._prepared_cache = cache
+        return cache[1], cache[2], cache[3]
+
+    def _fast_path_ok(self, x: torch.Tensor) -> bool:
+        """No gradient wanted and nobody is listening on `_linear`: the two modules may run as one call."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        lin = self._linear
+        if lin._forward_hooks or lin._forward_pre_hooks or self._forward_hooks or self._forward_pre_hooks:
+            return False
+        import torch.nn.modules.module as _m
+        if _m._global_forward_hooks or _m._global_forward_pre_hooks:
+            return False
+        return x.is_cuda and x.dim() == 2 and x.dtype in _DTYPE_CODES
+
+    def _ninf_range(self) -> tuple:
         num_all = Globals.categories.num_all
         lo = hi = 0
         if Globals.training:  # novel categories are invisible while training (classifiers.py:62-67)
             lo, hi = Globals.categories.num_bases, num_all
         if self.disable_bg_column and self._bg_embedding is not None:
             lo, hi = (lo if hi else num_all), num_all + 1  # [novels |] background: one contiguous -inf range
+        return lo, hi
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lo, hi = self._ninf_range()
         alpha, shift = self._affine()
+        if self._fast_path_ok(x):
+            # one C-ABI call: [cast x] -> GEMM -> row normalise -> GEMM (oake_classifier_fwd), prepared W / E
+            _require_cuda(x)
+            x = x.contiguous()
+            n = x.shape[0]
+            k = self._embeddings.shape[0] + (1 if self._bg_embedding is not None else 0)
+            k_pad = _kpad(k)
+            w_act, e_act, b32 = self._prepared(x.device, k_pad)
+            h = torch.empty(n, DIM, device=x.device, dtype=torch.float32)
+            logits = torch.empty(n, k_pad, device=x.device, dtype=torch.float32)
+            ws = _Workspace.get(x.device, n, self._linear.in_features, k_pad)
+            binding.check(binding.load().oake_classifier_fwd(
+                x.data_ptr(), _DTYPE_CODES[x.dtype], w_act.data_ptr(), b32.data_ptr(), e_act.data_ptr(), n,
+                self._linear.in_features, k_pad, alpha, shift, lo, hi, h.data_ptr(), logits.data_ptr(), ws.data_ptr(),
+                ws.numel(), _stream(x)))
+            return logits[:, :k]  # (a view: the padded pitch is what `vild_ensemble` takes as is)
+        h = self._linear(x)  # through __call__: forward hooks see the normalised tensor
         return _CosineLogitsFn.apply(h, self._embeddings, self._bg_embedding, alpha, shift, lo, hi)
 
 
