@@ -30,6 +30,7 @@ import collections
 import concurrent.futures
 import enum
 import itertools
+import json
 import pathlib
 import time
 from abc import ABC, abstractmethod
@@ -215,6 +216,7 @@ class BaseValidator(ABC, Generic[T]):
             raise ValueError(f"store must be 'pth' or 'packed', not {store!r}")
         self._decode, self._store = decode, store
         self._collate = bool(collate)
+        self._rows = 0  # crops encoded by this rank in this split
         self._manifest: List[Tuple[int, int, Optional[torch.Tensor]]] = []  # (image id, rows, global embedding)
         self._packed: Optional[PackedWriter] = None
         dataloader = Config(dataloader)
@@ -308,6 +310,7 @@ class BaseValidator(ABC, Generic[T]):
             batches_, ticket = entry
             for batch, result in zip(batches_, ticket.result()):
                 pending.append(self._writer.submit(self._write, result, batch))
+                self._rows += result['embeddings'].shape[0] if isinstance(result, dict) else 1
                 if self._collate:
                     rows = result['embeddings'].shape[0] if isinstance(result, dict) else 1
                     self._manifest.append((int(key_of_batch(batch)), rows, None if isinstance(result, dict) else result))
@@ -338,6 +341,12 @@ class BaseValidator(ABC, Generic[T]):
             self._writer.shutdown(wait=True)
             if self._packed is not None:
                 self._packed.close()
+        elapsed = time.perf_counter() - t0
+        rank, world = oake_dist.rank_world()
+        # one machine-readable line per rank and split (tools/bench_cli_scaling.py adds them up)
+        print('[oake-timing] ' + json.dumps(dict(name=self._name, rank=rank, world=world, images=done, crops=self._rows,
+                                                 seconds=round(elapsed, 4), decode=self._decode, store=self._store,
+                                                 output_dir=str(self._dataset._output_dir))), flush=True)
         if self._collate:
             self.collate()
         return done

@@ -106,8 +106,18 @@ def visual_params(seed: int = 0, layers: int = 12) -> Dict[str, 'np.ndarray']:
     return p
 
 
+def _write_image(job) -> None:
+    import PIL.Image
+    path, w, h, seed, fmt, i = job
+    arr = image(w, h, seed)
+    if fmt == 'jpg':
+        PIL.Image.fromarray(arr).save(path, quality=(95, 85, 75)[i % 3], subsampling=(2, 0, 1)[i % 3])
+    else:
+        PIL.Image.fromarray(arr).save(path)
+
+
 def write_coco_dataset(root, n_images: int, seed: int = 0, n_proposals: int = 40, sizes=COCO_SIZES,
-                       first_id: int = 101, fmt: str = 'png') -> dict:
+                       first_id: int = 101, fmt: str = 'png', workers: int = 0) -> dict:
     """Materialises a tiny COCO-format dataset (lossless PNG images -- or, with fmt='jpg', JPEG files
     of mixed quality / chroma sampling as COCO's are --, instances json, proposal pickle in image-id
     order) plus an OAKE config for each task.  Returns the paths."""
@@ -115,21 +125,24 @@ def write_coco_dataset(root, n_images: int, seed: int = 0, n_proposals: int = 40
     import pathlib
     import pickle
 
-    import PIL.Image
     root = pathlib.Path(root)
     (root / 'images').mkdir(parents=True, exist_ok=True)
     infos, props = [], []
+    jobs = []
     for i in range(n_images):
         w, h = sizes[i % len(sizes)]
         id_ = first_id + 7 * i
-        arr = image(w, h, seed * 100003 + i)
         name = f'{id_:012d}.{fmt}'
-        if fmt == 'jpg':
-            PIL.Image.fromarray(arr).save(root / 'images' / name, quality=(95, 85, 75)[i % 3], subsampling=(2, 0, 1)[i % 3])
-        else:
-            PIL.Image.fromarray(arr).save(root / 'images' / name)
+        jobs.append((str(root / 'images' / name), w, h, seed * 100003 + i, fmt, i))
         infos.append(dict(id=id_, file_name=name, width=w, height=h))
         props.append(proposals(w, h, n_proposals, seed=seed * 7919 + i))
+    if workers > 1:
+        import multiprocessing
+        with multiprocessing.get_context('fork').Pool(workers) as pool:
+            pool.map(_write_image, jobs, chunksize=16)
+    else:
+        for job in jobs:
+            _write_image(job)
     ann = root / 'instances.json'
     ann.write_text(json.dumps(dict(images=infos, annotations=[], categories=[])))
     pkl = root / 'proposals.pkl'
