@@ -192,6 +192,20 @@ int oake_classifier_fwd(const void* x, int x_dtype, const void* w_act, const flo
 int oake_vild_ensemble(const float* bbox_logits, const float* object_logits, const float* lambda, int N, int K1,
                        int ld_bbox, int ld_object, float* out, int ld_out, void* stream);
 
+/* ---- re-softmax + multiclass NMS (second half): mmdet `BBoxHead.get_bboxes` ->
+ * `multiclass_nms(bboxes, softmax(cls_score), score_thr, nms, max_per_img)` behind the ensemble scores, and the
+ * same call in oadp/dp/test_nni.py:55-92.  Class-agnostic boxes (`reg_class_agnostic=True` in the reference's
+ * configs): boxes (N,4) fp32 xyxy shared by all K foreground classes, 16-byte aligned, N <= 4096.
+ *   oake_softmax_rows    out[n][:K1] = softmax(in[n][:K1])                       (row pitches ld_*)
+ *   oake_multiclass_nms  keep[k][n] (uint8, K x N) = 1 iff candidate (box n, class k) has score > score_thr and
+ *                        survives greedy NMS (IoU > iou_thr suppresses, descending scores, ties by box index)
+ *                        among the candidates of class k.  scores (N, ld_scores): column k = class k (the
+ *                        background column is simply not among the first K).  ws: oake_nms_workspace_bytes(N). */
+int oake_softmax_rows(const float* in, int N, int K1, int ld_in, float* out, int ld_out, void* stream);
+int oake_nms_workspace_bytes(int N, size_t* out_bytes);
+int oake_multiclass_nms(const float* boxes_xyxy, const float* scores, int N, int K, int ld_scores, float score_thr,
+                        float iou_thr, uint8_t* keep, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- distillation-side losses: value and gradient w.r.t. the first argument in one call -
  * All fp32 device pointers.  `scale` = weight / numel for reduction='mean', weight for 'sum' (todd
  * BaseLoss.reduce; the configs' WarmupScheduler is a scalar at a given step).  loss: 1 float.  grad:

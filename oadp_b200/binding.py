@@ -66,6 +66,10 @@ SIGNATURES = {
                                       C.c_size_t, C.c_void_p]),
     'oake_vild_ensemble': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p]),
+    'oake_softmax_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    'oake_nms_workspace_bytes': (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    'oake_multiclass_nms': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
     'oake_loss_workspace_bytes': (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
     'oake_pair_loss': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
