@@ -74,6 +74,7 @@ const char* kClassNames[K_NUM] = {"frontend", "gemm_patch", "assemble_ln_pre", "
 
 struct LayerMaps {
   CUtensorMap qkv, out, fc1, fc2;
+  CUtensorMap q, kv;  // the Q rows [0, W) and the K, V rows [W, 3W) of in_proj alone (last objects block)
 };
 
 struct ProfEvent {
@@ -241,6 +242,9 @@ int oake_create(oake_handle** out, int device, const oake_weights* weights) {
       return fail("layer %d has a NULL weight pointer", l);
     }
     rc |= make_tmap_act_2d(&h->tm_layer[l].qkv, lw.qkv_w, 3 * W, W, gemm_block_n(3 * W));
+    rc |= make_tmap_act_2d(&h->tm_layer[l].q, lw.qkv_w, W, W, gemm_block_n(W));
+    rc |= make_tmap_act_2d(&h->tm_layer[l].kv, static_cast<const act_t*>(lw.qkv_w) + static_cast<size_t>(W) * W, 2 * W, W,
+                           gemm_block_n(2 * W));
     rc |= make_tmap_act_2d(&h->tm_layer[l].out, lw.out_w, W, W, gemm_block_n(W));
     rc |= make_tmap_act_2d(&h->tm_layer[l].fc1, lw.fc1_w, 4 * W, W, gemm_block_n(4 * W));
     rc |= make_tmap_act_2d(&h->tm_layer[l].fc2, lw.fc2_w, W, 4 * W, gemm_block_n(W));
@@ -331,7 +335,7 @@ int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const
   float* emb_raw = out_raw_f32 ? out_raw_f32 : reinterpret_cast<float*>(base + p.off_emb_raw);
 
   const int R = p.R, ts = p.tail_start;
-  CUtensorMap tm_patches, tm_x, tm_attn, tm_mlp, tm_x_tail, tm_attn_tail, tm_mlp_tail, tm_head;
+  CUtensorMap tm_patches, tm_x, tm_attn, tm_mlp, tm_x_tail, tm_attn_tail, tm_mlp_tail, tm_head, tm_x_side;
   int rc = 0;
   rc |= make_tmap_act_2d(&tm_patches, patches, static_cast<uint64_t>(B) * p.P, PC, 128);
   rc |= make_tmap_act_2d(&tm_x, x, R, W, 128);
@@ -341,6 +345,8 @@ int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const
   rc |= make_tmap_act_2d(&tm_attn_tail, attn + static_cast<size_t>(ts) * W, B, W, 128);
   rc |= make_tmap_act_2d(&tm_mlp_tail, mlp + static_cast<size_t>(ts) * 4 * W, B, 4 * W, 128);
   rc |= make_tmap_act_2d(&tm_head, head_in, B, W, 128);
+  tm_x_side = tm_x_tail;
+  if (side) rc |= make_tmap_act_2d(&tm_x_side, x + static_cast<size_t>(B) * p.T * W, B, W, 128);
   if (rc != 0) return fail("cuTensorMapEncodeTiled failed for an activation tensor (rc=%d)", rc);
 
   Launcher go{h, st};
@@ -374,7 +380,17 @@ int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const
     const int rn = last ? B : R;
     act_t* xr = x + static_cast<size_t>(r0) * W;
 
-    {  // q,k,v = ln_1(x) W^T + b   (LayerNorm folded, statistics from stats_b)
+    if (side && last) {
+      // Last objects block: only the side row is alive behind it (objects.py:249-258), and it needs K / V of
+      // every token but Q of itself alone: the patch / class rows skip the Q third of in_proj (K, V columns
+      // [W, 3W) for all rows), the B side rows get their Q from a GEMM of their own.
+      GemmEpilogue kv{lw.qkv_c + W, lw.qkv_s + W, stats_b, nullptr, nullptr, qkv + W, 3 * W, 0, 0, 0};
+      go.run(K_GEMM_QKV, gflops(R, 2 * W, W), [&] { return launch_gemm(st, tm_x, tm.kv, R, 2 * W, W, kv, ns); });
+      const int y0 = B * p.T;  // first side row
+      GemmEpilogue qy{lw.qkv_c, lw.qkv_s, stats_b + static_cast<size_t>(y0) * kStatSlots, nullptr, nullptr,
+                      qkv + static_cast<size_t>(y0) * 3 * W, 3 * W, 0, 0, 0};
+      go.run(K_GEMM_QKV, gflops(B, W, W), [&] { return launch_gemm(st, tm_x_side, tm.q, B, W, W, qy, ns); });
+    } else {  // q,k,v = ln_1(x) W^T + b   (LayerNorm folded, statistics from stats_b)
       GemmEpilogue ep{lw.qkv_c, lw.qkv_s, stats_b, nullptr, nullptr, qkv, 3 * W, 0, 0, 0};
       go.run(K_GEMM_QKV, gflops(R, 3 * W, W), [&] { return launch_gemm(st, tm_x, tm.qkv, R, 3 * W, W, ep, ns); });
     }

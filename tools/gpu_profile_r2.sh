@@ -1,0 +1,35 @@
+#!/bin/bash
+# Round-2 profiling pass for profiles/: launch list of one bench step, full captures of the top kernels, and the
+# NVTX-filtered capture of the dominant GEMM class that feeds roofline.traffic.
+mkdir -p gpurun_out
+export OAKE_ALLOW_RANDOM_WEIGHTS=1
+timeout 900 python -c "import torch; torch.zeros(1).cuda()"
+python -m oadp_b200.build > gpurun_out/build.log 2>&1
+echo "== bench (reference numbers for the captures below)"
+timeout 600 python bench.py --steps 10 --no-cpu-baseline --no-library-baseline > gpurun_out/bench_for_profile.json 2> gpurun_out/bench_for_profile.err
+python - <<'PY'
+import json
+d = json.loads(open('gpurun_out/bench_for_profile.json').read().strip().splitlines()[-1])
+r = d['roofline']
+print('value', round(d['value']), 'ms/step', round(d['ms_per_step'], 2), 'dominant', r['kernel'], 'flops/launch', r['flops_per_launch'])
+open('gpurun_out/dominant.txt', 'w').write(f"{r['kernel'].split('(')[1].strip(')')} {r['flops_per_launch']}\n")
+PY
+read CLS FLOPS < gpurun_out/dominant.txt
+echo "== launch list (one timed step)"
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-baseline > gpurun_out/launches_bench.log 2>&1
+python tools/launch_summary.py gpurun_out/launches.csv "bench.py --steps 1 --warmup 3 (default oake workload, 8 images)" > gpurun_out/launch_list_summary.csv; head -14 gpurun_out/launch_list_summary.csv
+echo "== ncu --set full, NVTX range $CLS (every launch of one step: warm-up skipped by launch count)"
+# warm-up 3 steps + 1 timed + e2e/roofline passes follow; the class has 12 launches per encode call (one per layer), 7 calls per step
+timeout 1500 ncu --set full --clock-control none --nvtx --nvtx-include "$CLS/" -s 252 -c 84 -f -o gpurun_out/prof_$CLS \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-baseline > gpurun_out/ncu_$CLS.log 2>&1; tail -2 gpurun_out/ncu_$CLS.log | cut -c1-200
+python tools/ncu_traffic.py gpurun_out/prof_$CLS.ncu-rep $CLS $FLOPS gpurun_out/ncu_traffic.json
+echo "== ncu --set full: the objects tower's kernels at B = 478"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_cs|gemm_tcgen05" -s 8 -c 6 -f -o gpurun_out/prof_tower \
+  python tools/quick_bench.py --variant 1 --batch 478 --iters 1 > gpurun_out/ncu_tower.log 2>&1; tail -1 gpurun_out/ncu_tower.log
+python tools/ncu_summary.py gpurun_out/prof_tower.ncu-rep > gpurun_out/ncu_tower_summary.txt; cat gpurun_out/ncu_tower_summary.txt
+echo "== ncu --set full: front end (resize, im2col) of the objects workload"
+timeout 900 ncu --set full --clock-control none -k regex:"resize_u8|im2col_u8|assemble" -s 0 -c 4 -f -o gpurun_out/prof_frontend \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-baseline --images 2 --workload objects > gpurun_out/ncu_frontend.log 2>&1
+python tools/ncu_summary.py gpurun_out/prof_frontend.ncu-rep > gpurun_out/ncu_frontend_summary.txt; cat gpurun_out/ncu_frontend_summary.txt
+echo done
