@@ -51,7 +51,14 @@ enum EpiMode {
   EPI_F32 = 0,  // fp32 out: bias, QuickGELU
   EPI_ACT = 1,  // act out: LayerNorm fold | bias, QuickGELU
   EPI_RES = 2,  // act out: bias + act residual (+ row statistics)
+  // EPI_RES for short K (out-proj, K = 768): per tile the MMAs take as long as ONE pass of the epilogue over
+  // HBM (A, residual and output are all 2 bytes per element: 404 MB per launch at B = 478, 67 us at the measured
+  // HBM rate against 98 us achieved), so the residual's latency must never be exposed.  It is fetched with
+  // cp.async straight into a ring of three staging strips per warp, TWO pieces ahead (no register staging, no
+  // LDG -> STS round trip); the ring costs one of the six operand stages.
+  EPI_RES_RING = 3,
 };
+__host__ __device__ constexpr bool is_res(int mode) { return mode == EPI_RES || mode == EPI_RES_RING; }
 
 // CTA-pair mode for the 256-wide tiles (128-wide tiles stay 1-CTA).  $OAKE_GEMM_CTA_GROUP=1|2
 // overrides the default once per process (A/B measurements); it also decides the W tensor-map box.
@@ -64,17 +71,29 @@ int cta_group() {
   return v;
 }
 
-template <int BN, int CG = 1, int EW = 8>
+// $OAKE_GEMM_RING=0 keeps the register-staged residual for short K too (A/B measurements)
+bool gemm_res_ring() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OAKE_GEMM_RING");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BN, int CG = 1, int EW = 8, bool RING = false>
 struct Cfg {
   static constexpr int kEpiWarps = EW;
   static constexpr int kThreads = 128 + 32 * EW;
-  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : (EW == 16 ? 5 : 6);
+  static constexpr int kStages = (BN == 256 && CG == 1) ? 4 : ((EW == 16 || RING) ? 5 : 6);
+  static constexpr int kRing = RING ? 3 : 1;                // staging strips per epilogue warp
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
   static constexpr int kWarpCols = BN / (EW / 4);           // columns owned by one epilogue warp
-  static constexpr int kStgBytes = 32 * 64;                 // 32 rows x 64 B, XOR-swizzled
+  static constexpr int kStripBytes = 32 * 64;               // 32 rows x 64 B, XOR-swizzled
+  static constexpr int kStgBytes = kRing * kStripBytes;
   static constexpr int kVecBytes = 2 * kWarpCols * 4;       // bias + colsum of the warp's columns (x2: double buffered)
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kBarBytes + kEpiWarps * (kStgBytes + 2 * kVecBytes) + 1024;
@@ -128,25 +147,63 @@ struct RowLn {
 //   y = [fold] rstd_m * acc + (nmr_m * s_n + c_n)   |   acc + bias_n
 //   y = QuickGELU(y)                 (c_fc)
 //   y += residual (act_t, may alias out), statistics (sum y, sum y^2)   (out_proj, c_proj)
+// Residual piece (32 rows x 32 columns of this warp) -> ring strip, asynchronously: lane (sub_r, sub_c) copies the
+// 16-byte chunk sub_c of rows 8 i + sub_r, i.e. exactly the slots the coalesced phase addresses.  One group per
+// piece (committed even when empty, so that the group arithmetic of the consumer stays uniform).
+__device__ __forceinline__ void ring_fetch(const GemmEpilogue& ep, uint32_t strip_s, int r0, int c0, int M, int lane) {
+  const int sub_r = lane >> 2, sub_c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 8 * i + sub_r;
+    if (r < M)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(stg_addr(strip_s, 8 * i + sub_r, sub_c)),
+                   "l"(ep.residual + static_cast<size_t>(r) * ep.ld_res + c0 + sub_c * 8)
+                   : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
 template <int BN, int MODE, int EW>
 __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_warp, uint8_t* stg,
                                              const float* vec, int row0, int col_base, int M, int lane,
-                                             uint4 (&res)[4], const RowLn ln, int next_row0, int next_col_base) {
+                                             uint4 (&res)[4], const RowLn ln, int next_row0, int next_col_base,
+                                             uint32_t& ring_pos) {
   constexpr int WC = Cfg<BN, 1, EW>::kWarpCols;
   constexpr int NP = WC / 32;
+  constexpr bool RING = MODE == EPI_RES_RING;
+  constexpr int kStrip = Cfg<BN, 1, EW>::kStripBytes;
   const int sub_r = lane >> 2;  // coalesced phase: 8 rows per instruction, 4 lanes x 16 B per row
   const int sub_c = lane & 3;
   const bool fold = MODE == EPI_ACT && ep.colsum != nullptr;
   const bool has_bias = ep.bias != nullptr;
   const bool gelu = MODE == EPI_ACT && ep.act == 1;
   float sum = 0.f, sumsq = 0.f;
-  const uint32_t stg_s = smem_u32(stg);
+  const uint32_t stg_base_s = smem_u32(stg);
+  uint32_t stg_s = stg_base_s;
   const uint32_t vec_s = smem_u32(vec);
   uint32_t r32[32];
   tmem_ld_32x32(t_warp, r32);
 #pragma unroll 1
   for (int pc = 0; pc < NP; ++pc) {
     const int col0 = col_base + pc * 32;
+    if (RING) {
+      // this piece lives in strip ring_pos % 3 (requested two pieces ago); request the piece two ahead -- of this
+      // tile or of the warp's next one (rows >= M when there is none: an empty group)
+      stg_s = stg_base_s + (ring_pos % 3u) * kStrip;
+      const int ahead = pc + 2;
+      const bool same = ahead < NP;
+      ring_fetch(ep, stg_base_s + ((ring_pos + 2u) % 3u) * kStrip, same ? row0 : next_row0,
+                 same ? col_base + ahead * 32 : next_col_base + (ahead - NP) * 32, M, lane);
+      // Groups complete in commit order: ..., res(p), res(p+1), [vec(next tile), committed at the top of this tile,]
+      // res(p+2).  Leave everything newer than res(p) in flight: three groups while the vector group sits among
+      // them (first two pieces of a tile), two afterwards.  This tile's own vectors are older than all of them.
+      if (pc < 2)
+        asm volatile("cp.async.wait_group 3;\n" ::: "memory");
+      else
+        asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+      __syncwarp();
+      ++ring_pos;
+    }
     if (MODE == EPI_RES) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) sts128(stg_addr(stg_s, 8 * i + sub_r, sub_c), res[i]);
@@ -198,7 +255,7 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t slot = stg_addr(stg_s, lane, j);
-      if (MODE == EPI_RES) {
+      if (is_res(MODE)) {
         const uint4 rv = lds128(slot);
         const float2 r0 = unpack2(rv.x), r1 = unpack2(rv.y), r2 = unpack2(rv.z), r3 = unpack2(rv.w);
         v[8 * j + 0] += r0.x;
@@ -236,7 +293,7 @@ __device__ __forceinline__ void epilogue_act(const GemmEpilogue& ep, uint32_t t_
   }
   // One slot per 128-column block, summed in a fixed order by the consumer: deterministic, no
   // atomics.  (Statistics of the fp32 values before the final rounding to act_t.)
-  if (MODE == EPI_RES && ep.out_stats != nullptr && row0 + lane < M)
+  if (is_res(MODE) && ep.out_stats != nullptr && row0 + lane < M)
     ep.out_stats[static_cast<size_t>(row0 + lane) * kStatSlots + col_base / 128] = make_float2(sum, sumsq);
 }
 
@@ -288,7 +345,7 @@ template <int BN, int MODE, int CG, int EW>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     int M, int N, int K, GemmEpilogue ep) {
-  using C = Cfg<BN, CG, EW>;
+  using C = Cfg<BN, CG, EW, MODE == EPI_RES_RING>;
   constexpr int kEpiWarps = EW;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment.
@@ -467,11 +524,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
     int row0 = M, col_base = 0;
+    uint32_t ring_pos = 0;  // EPI_RES_RING: pieces consumed so far (strip = ring_pos % 3)
     if (first_tile < num_tiles) {
       coords(first_tile, row0, col_base);
       request_vec(vec2, col_base);
       request_stats(row0);
       request_res(row0, col_base);
+      if (MODE == EPI_RES_RING) {  // the first two pieces of the first tile
+        ring_fetch(ep, smem_u32(stg), row0, col_base, M, lane);
+        ring_fetch(ep, smem_u32(stg) + C::kStripBytes, row0, col_base + 32, M, lane);
+      }
     }
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       float* vec = vec2 + buf * (2 * C::kWarpCols);
@@ -500,14 +562,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // this tile's vectors (all but the newest group)
+      // this tile's vectors: every group but the newest (the next tile's vectors).  (EPI_RES_RING waits inside the
+      // piece loop instead, where it can leave the residual pieces that are still ahead in flight.)
+      if (MODE != EPI_RES_RING) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
       __syncwarp();
       const uint32_t t_warp = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                               static_cast<uint32_t>(acc * BN + ch * C::kWarpCols);
       if (MODE == EPI_F32)
         epilogue_f32<BN, EW>(ep, t_warp, stg, vec, row0, col_base, M, lane);
       else
-        epilogue_act<BN, MODE, EW>(ep, t_warp, stg, vec, row0, col_base, M, lane, res, ln, next_row0, next_col_base);
+        epilogue_act<BN, MODE, EW>(ep, t_warp, stg, vec, row0, col_base, M, lane, res, ln, next_row0, next_col_base, ring_pos);
       tc_fence_before();
       __syncwarp();  // every lane is done with TMEM and with `vec` before they are handed back
       if (lane == 0) {
@@ -588,7 +652,7 @@ PFN_encodeTiled get_encode_fn() {
 template <int BN, int MODE, int CG, int EW>
 cudaError_t launch_gemm_inst(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N,
                              int K, const GemmEpilogue& ep, int num_sms) {
-  using C = Cfg<BN, CG, EW>;
+  using C = Cfg<BN, CG, EW, MODE == EPI_RES_RING>;
   if (cudaError_t e = ensure_dynamic_smem<gemm_tcgen05_kernel<BN, MODE, CG, EW>>(C::kSmemBytes); e != cudaSuccess)
     return e;
   const int tiles = ((M + BM * CG - 1) / (BM * CG)) * (N / BN);
@@ -613,7 +677,11 @@ template <int BN, int CG>
 cudaError_t launch_gemm_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N, int K,
                            const GemmEpilogue& ep, int num_sms) {
   if (ep.out_f32) return launch_gemm_inst<BN, EPI_F32, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
-  if (ep.residual != nullptr) return launch_gemm_inst<BN, EPI_RES, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
+  if (ep.residual != nullptr) {
+    // short K (out-proj): the epilogue, not the MMA, sets the pace -> residual through the cp.async ring
+    if (BN == 256 && CG == 2 && K <= 1024 && gemm_res_ring()) return launch_gemm_inst<256, EPI_RES_RING, 2, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
+    return launch_gemm_inst<BN, EPI_RES, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
+  }
   return launch_gemm_inst<BN, EPI_ACT, CG, 8>(st, tmA, tmW, M, N, K, ep, num_sms);
 }
 

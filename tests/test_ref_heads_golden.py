@@ -93,3 +93,21 @@ def test_block_loss_oracle_is_pinned(fixture, tmp_path, monkeypatch):
     assert abs(float(loss) - float(fixture['block_loss'])) < 1e-4 * abs(float(fixture['block_loss']))
     recall = MultilabelTopKRecall(k=2)(logits[:, :-1], targets)
     assert abs(float(recall) - float(fixture['block_recall'])) < 1e-4
+
+
+def test_expand_mode_constant_is_pinned(fixture):
+    """`ExpandMode.CONSTANT` (objects.py:92-93): the reference's `_expand` / `_preprocess` run with that mode
+    (same fixture file) pin the product's host geometry and the oracle front end bit-exactly."""
+    import numpy as np
+    import PIL.Image
+    from oadp_b200 import frontend
+    from oracle import frontend as ofe
+    images, proposals = mrg.ref_inputs()
+    for arr, prop, want in zip(images[:2], proposals[:2], fixture['expand_constant']):
+        plan = frontend.objects_plan(prop, (arr.shape[1], arr.shape[0]), expand_mode='CONSTANT')
+        assert np.array_equal(plan.expanded, want['expanded'].numpy()) and np.array_equal(plan.bboxes, want['bboxes'].numpy())
+        side = plan.expanded[:, 2:] - plan.expanded[:, :2]
+        assert np.allclose(side, 224.0, atol=1e-3)
+        o = ofe.objects_preprocess(PIL.Image.fromarray(arr), torch.from_numpy(prop), expand_mode='CONSTANT')
+        assert torch.equal(o.expanded, want['expanded']) and torch.equal(o.masks.to(torch.uint8), want['masks'])
+        assert torch.equal(mrg.checksums(o.objects), want['pixels'])

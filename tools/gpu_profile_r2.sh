@@ -32,4 +32,5 @@ echo "== ncu --set full: front end (resize, im2col) of the objects workload"
 timeout 900 ncu --set full --clock-control none -k regex:"resize_u8|im2col_u8|assemble" -s 0 -c 4 -f -o gpurun_out/prof_frontend \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-library-baseline --images 2 --workload objects > gpurun_out/ncu_frontend.log 2>&1
 python tools/ncu_summary.py gpurun_out/prof_frontend.ncu-rep > gpurun_out/ncu_frontend_summary.txt; cat gpurun_out/ncu_frontend_summary.txt
+rm -f gpurun_out/prof_*.ncu-rep  # the reports exceed the 64 MiB transfer limit: only the summaries above travel back
 echo done
