@@ -368,7 +368,13 @@ int oake_test_attention_main(const void* qkv, void* out_act, int B, int P, void*
  * side rows (side_only = 1, last block).  qkv act [B*(P+2),2304], mask fp32 [B,P]. */
 int oake_test_attention_side(const void* qkv, const float* mask, void* out_act, int B, int P, int side_only,
                              void* stream);
+/* Front-end matrix from fp32 NCHW crops: variant T50 -> im2col act [B*49, 3072]; variant T197 -> the block matrix
+ * act [B*225, 768] (15 x 15 blocks of 16 x 16 pixels of the crop zero-padded by 15, column order (c, ky, kx)). */
 int oake_test_im2col(const float* pixels, void* patches_act, int B, int variant, void* stream);
+/* Patch embedding alone: out fp32 [B*49, 768] (T50) or [B*225, 768] (T197; patch (gy, gx) = row gy*15+gx of a crop).
+ * conv1_w_act: act [768, 3072], the checkpoint layout (oadp/oake/objects.py:299-301 changes stride / padding only). */
+int oake_test_patch_embed(const float* pixels, const void* conv1_w_act, float* out_f32, int B, int variant,
+                          void* stream);
 
 #ifdef __cplusplus
 }

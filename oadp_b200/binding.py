@@ -105,6 +105,7 @@ SIGNATURES = {
     'oake_test_attention_side': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p]),
     'oake_test_im2col': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'oake_test_patch_embed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lib = None

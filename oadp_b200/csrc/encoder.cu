@@ -88,6 +88,7 @@ size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
   int B, P, T, R, tail_start;
+  int PB;  // rows per crop of the patch-embedding GEMM: P, or the 15 x 15 block grid of the objects tower
   size_t off_patches, off_patch_out, off_x, off_stats_a, off_stats_b, off_qkv, off_attn, off_mlp,
       off_head_in, off_emb_raw, total;
 };
@@ -100,6 +101,8 @@ struct oake_handle {
   oake_weights w;
   std::vector<oake_layer_weights> layers;
   CUtensorMap tm_conv1, tm_proj;
+  act_t* conv1_blk;  // conv1 weight regrouped to [O, (dy, dx), c, 16, 16] for the objects tower's block-matrix GEMM
+  CUtensorMap tm_conv1_blk;
   std::vector<LayerMaps> tm_layer;
   act_t* pixel_lut;  // [3*256] ToTensor + Normalize of every byte value, rounded to act_t
   long long launches;
@@ -121,15 +124,17 @@ Plan make_plan(const oake_handle* h, int B, int variant) {
   p.T = p.P + 1;
   p.R = B * p.T + (variant == OAKE_VARIANT_T197 ? B : 0);
   p.tail_start = variant == OAKE_VARIANT_T197 ? B * p.T : B * p.P;
-  const size_t patch_cols = 3 * h->w.patch * h->w.patch;
+  const bool blk = variant == OAKE_VARIANT_T197;
+  p.PB = blk ? kBlockGrid * kBlockGrid : p.P;
+  const size_t patch_cols = blk ? 3 * 16 * 16 : 3 * h->w.patch * h->w.patch;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off += align_up(bytes);
     return o;
   };
-  p.off_patches = take(static_cast<size_t>(B) * p.P * patch_cols * sizeof(act_t));
-  p.off_patch_out = take(static_cast<size_t>(B) * p.P * W * sizeof(float));
+  p.off_patches = take(static_cast<size_t>(B) * p.PB * patch_cols * sizeof(act_t));
+  p.off_patch_out = take(static_cast<size_t>(B) * p.PB * W * sizeof(float));
   p.off_x = take(static_cast<size_t>(p.R) * W * sizeof(act_t));
   p.off_stats_a = take(static_cast<size_t>(p.R) * kStatSlots * sizeof(float2));
   p.off_stats_b = take(static_cast<size_t>(p.R) * kStatSlots * sizeof(float2));
@@ -224,6 +229,7 @@ int oake_create(oake_handle** out, int device, const oake_weights* weights) {
   h->layers.assign(weights->layer, weights->layer + weights->layers);
   h->w.layer = h->layers.data();
   h->pixel_lut = nullptr;
+  h->conv1_blk = nullptr;
   h->launches = 0;
   h->profiling = false;
   memset(h->acc_ms, 0, sizeof(h->acc_ms));
@@ -249,7 +255,20 @@ int oake_create(oake_handle** out, int device, const oake_weights* weights) {
     rc |= make_tmap_act_2d(&h->tm_layer[l].fc1, lw.fc1_w, 4 * W, W, gemm_block_n(4 * W));
     rc |= make_tmap_act_2d(&h->tm_layer[l].fc2, lw.fc2_w, W, 4 * W, gemm_block_n(W));
   }
+  if (rc == 0 && h->w.pos_t197) {  // objects tower: conv1 regrouped for the shifted-A GEMM over the block matrix
+    const size_t n = static_cast<size_t>(W) * 3 * 32 * 32;
+    e = cudaMalloc(&h->conv1_blk, n * sizeof(act_t));
+    if (e == cudaSuccess) e = launch_conv1_regroup(nullptr, static_cast<const act_t*>(h->w.conv1_w), h->conv1_blk, W);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) {
+      if (h->conv1_blk) cudaFree(h->conv1_blk);
+      delete h;
+      return fail("conv1 regroup: %s", cudaGetErrorString(e));
+    }
+    rc |= make_tmap_act_2d(&h->tm_conv1_blk, h->conv1_blk, W, 3 * 32 * 32, gemm_block_n(W));
+  }
   if (rc != 0) {
+    if (h->conv1_blk) cudaFree(h->conv1_blk);
     delete h;
     return fail("cuTensorMapEncodeTiled failed for a weight tensor (rc=%d)", rc);
   }
@@ -272,6 +291,7 @@ int oake_create(oake_handle** out, int device, const oake_weights* weights) {
     e = cudaMalloc(&h->pixel_lut, 768 * sizeof(act_t));
     if (e == cudaSuccess) e = cudaMemcpy(h->pixel_lut, lut.data(), 768 * sizeof(act_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
+      if (h->conv1_blk) cudaFree(h->conv1_blk);
       delete h;
       return fail("pixel table upload: %s", cudaGetErrorString(e));
     }
@@ -288,6 +308,7 @@ void oake_destroy(oake_handle* h) {
   }
   for (auto e : h->pool) cudaEventDestroy(e);
   if (h->pixel_lut) cudaFree(h->pixel_lut);
+  if (h->conv1_blk) cudaFree(h->conv1_blk);
   delete h;
 }
 
@@ -337,7 +358,7 @@ int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const
   const int R = p.R, ts = p.tail_start;
   CUtensorMap tm_patches, tm_x, tm_attn, tm_mlp, tm_x_tail, tm_attn_tail, tm_mlp_tail, tm_head, tm_x_side;
   int rc = 0;
-  rc |= make_tmap_act_2d(&tm_patches, patches, static_cast<uint64_t>(B) * p.P, PC, 128);
+  rc |= make_tmap_act_2d(&tm_patches, patches, static_cast<uint64_t>(B) * p.PB, side ? 768 : PC, 128);
   rc |= make_tmap_act_2d(&tm_x, x, R, W, 128);
   rc |= make_tmap_act_2d(&tm_attn, attn, R, W, 128);
   rc |= make_tmap_act_2d(&tm_mlp, mlp, R, 4 * W, 128);
@@ -356,19 +377,30 @@ int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const
   auto gflops = [](double m, double n, double k) { return 2.0 * m * n * k; };
 
   // K0/K1: crops -> conv1 patch matrix -> patch embedding -> tokens + ln_pre (+ row statistics)
+  // (objects tower: the 15 x 15 block matrix instead of im2col, read at four row shifts by the GEMM -- frontend.cu)
   go.run(K_FRONTEND, 0, [&] {
-    if (pixels) return launch_im2col_pixels(st, pixels, patches, B, side ? 16 : 32, side ? 15 : 0, side ? 14 : 7);
-    return launch_im2col_u8(st, arena, crops, h->pixel_lut, patches, B, side ? 16 : 32, side ? 15 : 0,
-                            side ? 14 : 7);
+    if (side) return pixels ? launch_blockcol_pixels(st, pixels, patches, B) : launch_blockcol_u8(st, arena, crops, h->pixel_lut, patches, B);
+    if (pixels) return launch_im2col_pixels(st, pixels, patches, B, 32, 0, 7);
+    return launch_im2col_u8(st, arena, crops, h->pixel_lut, patches, B, 32, 0, 7);
   });
   {
     GemmEpilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, patch_out, W, 0, 1, 0};
-    const int M = B * p.P;
-    go.run(K_GEMM_PATCH, gflops(M, W, PC), [&] { return launch_gemm(st, tm_patches, h->tm_conv1, M, W, PC, ep, ns); });
+    const int M = B * p.PB;
+    if (side) {
+      ep.a_seg_kb = 768 / 64;
+      ep.a_shift[0] = 0;
+      ep.a_shift[1] = 1;
+      ep.a_shift[2] = kBlockGrid;
+      ep.a_shift[3] = kBlockGrid + 1;
+    }
+    // (credited with the algorithmic work: P patches per crop, not the block grid's junk rows)
+    go.run(K_GEMM_PATCH, gflops(static_cast<double>(B) * p.P, W, PC),
+           [&] { return launch_gemm(st, tm_patches, side ? h->tm_conv1_blk : h->tm_conv1, M, W, PC, ep, ns); });
   }
   go.run(K_ASSEMBLE, 0, [&] {
     return launch_assemble_ln_pre(st, patch_out, h->w.class_emb, side ? h->w.pos_t197 : h->w.pos_t50,
-                                  h->w.ln_pre_w, h->w.ln_pre_b, x, stats_b, B, p.P, W, side ? 1 : 0);
+                                  h->w.ln_pre_w, h->w.ln_pre_b, x, stats_b, B, p.P, W, side ? 1 : 0,
+                                  side ? kBlockGrid : 0);
   });
 
   for (int l = 0; l < L; ++l) {
@@ -566,9 +598,52 @@ int oake_test_attention_side(const void* qkv, const float* mask, void* out_act, 
 
 int oake_test_im2col(const float* pixels, void* patches_act, int B, int variant, void* stream) {
   const bool side = variant == OAKE_VARIANT_T197;
-  cudaError_t e = launch_im2col_pixels(static_cast<cudaStream_t>(stream), pixels, static_cast<act_t*>(patches_act),
-                                       B, side ? 16 : 32, side ? 15 : 0, side ? 14 : 7);
+  cudaError_t e = side ? launch_blockcol_pixels(static_cast<cudaStream_t>(stream), pixels, static_cast<act_t*>(patches_act), B)
+                       : launch_im2col_pixels(static_cast<cudaStream_t>(stream), pixels, static_cast<act_t*>(patches_act), B, 32, 0, 7);
   if (e != cudaSuccess) return fail("im2col launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Patch embedding alone (front-end matrix + conv1 GEMM) from fp32 NCHW crops: out fp32 [B * PB, 768], PB = 49 rows
+// per crop (T50) or the 15 x 15 block grid (T197: patch (gy, gx) is row gy * 15 + gx, the rest is scratch).
+int oake_test_patch_embed(const float* pixels, const void* conv1_w_act, float* out_f32, int B, int variant,
+                          void* stream) {
+  if (!pixels || !conv1_w_act || !out_f32 || B <= 0) return fail("bad argument");
+  const bool side = variant == OAKE_VARIANT_T197;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int W = 768, PC = 3072;
+  const int PB = side ? kBlockGrid * kBlockGrid : 49;
+  const size_t a_elems = static_cast<size_t>(B) * PB * (side ? 768 : PC);
+  act_t *a = nullptr, *wb = nullptr;
+  int dev = 0, ns = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&ns, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = cudaMalloc(&a, a_elems * sizeof(act_t));
+  if (e == cudaSuccess && side) e = cudaMalloc(&wb, static_cast<size_t>(W) * PC * sizeof(act_t));
+  if (e == cudaSuccess && side) e = launch_conv1_regroup(st, static_cast<const act_t*>(conv1_w_act), wb, W);
+  if (e == cudaSuccess)
+    e = side ? launch_blockcol_pixels(st, pixels, a, B) : launch_im2col_pixels(st, pixels, a, B, 32, 0, 7);
+  int rc = 0;
+  if (e == cudaSuccess) {
+    CUtensorMap tmA, tmW;
+    rc = make_tmap_act_2d(&tmA, a, static_cast<uint64_t>(B) * PB, side ? 768 : PC, 128) ||
+         make_tmap_act_2d(&tmW, side ? wb : conv1_w_act, W, PC, gemm_block_n(W));
+    if (rc == 0) {
+      GemmEpilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, out_f32, W, 0, 1, 0};
+      if (side) {
+        ep.a_seg_kb = 768 / 64;
+        ep.a_shift[1] = 1;
+        ep.a_shift[2] = kBlockGrid;
+        ep.a_shift[3] = kBlockGrid + 1;
+      }
+      e = launch_gemm(st, tmA, tmW, B * PB, W, PC, ep, ns);
+    }
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (a) cudaFree(a);
+  if (wb) cudaFree(wb);
+  if (rc != 0) return fail("cuTensorMapEncodeTiled failed");
+  if (e != cudaSuccess) return fail("patch embedding: %s", cudaGetErrorString(e));
   return 0;
 }
 

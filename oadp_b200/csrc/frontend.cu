@@ -123,6 +123,113 @@ im2col_u8_kernel(const uint8_t* __restrict__ arena, const oake_crop_src* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Objects tower (stride 16, pad 15, 32 x 32 kernel; objects.py:299-301): block matrix instead of im2col.
+// The padded 254 x 254 crop is cut into 15 x 15 NON-overlapping 16 x 16 blocks (rows 0..239: the last 14 padded
+// rows / columns are never touched by a patch); row (b, by, bx) of the block matrix holds one block, column
+// order (c, ky, kx), 768 wide.  A 32 x 32 patch at (gy, gx) is the four blocks (gy + dy, gx + dx), i.e. rows
+// r, r + 1, r + 15, r + 16 of the matrix, so the patch embedding is ONE GEMM whose A operand is read at four row
+// shifts (GemmEpilogue::a_seg_kb) against conv1's weight regrouped by (dy, dx) -- 0.35 MB per crop written and
+// re-read (from L2) instead of the 1.2 MB of an explicit im2col in which every pixel appears four times.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlk = 16;                       // block edge
+constexpr int kBlkGrid = 15;                   // blocks per crop edge
+constexpr int kBlkCols = 3 * kBlk * kBlk;      // 768
+constexpr int kBlkPad = 15;
+
+// One thread = 8 consecutive kx of one (crop, block, ky), three channels: 24 contiguous source bytes, three
+// 16-byte chunks out; a warp writes one whole block (3 x 512 contiguous bytes).
+__global__ void __launch_bounds__(256)
+blockcol_u8_kernel(const uint8_t* __restrict__ arena, const oake_crop_src* __restrict__ crops,
+                   const act_t* __restrict__ lut, act_t* __restrict__ blocks, long long total) {
+  __shared__ act_t s_lut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int sub = static_cast<int>(idx & 31);
+  const long long brow = idx >> 5;  // b * 225 + by * 15 + bx
+  const int b = static_cast<int>(brow / (kBlkGrid * kBlkGrid));
+  const int g = static_cast<int>(brow - static_cast<long long>(b) * (kBlkGrid * kBlkGrid));
+  const int by = g / kBlkGrid, bx = g - by * kBlkGrid;
+  const int ky = sub >> 1, kx0 = (sub & 1) * 8;
+  const int y = by * kBlk + ky - kBlkPad;
+  const int x0 = bx * kBlk + kx0 - kBlkPad;
+  uint32_t out[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[c][j] = 0u;
+  if (y >= 0 && y < kImg) {
+    const oake_crop_src cs = crops[b];
+    const uint8_t* src = arena + cs.off + (static_cast<long long>(y) * cs.pitch_px + x0) * 3;
+    unsigned short h[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int x = x0 + j;
+      const bool ok = x >= 0 && x < kImg;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        act_t val = to_act(0.f);
+        if (ok) val = s_lut[c * 256 + src[j * 3 + c]];
+        h[c][j] = *reinterpret_cast<unsigned short*>(&val);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        out[c][j] = static_cast<uint32_t>(h[c][2 * j]) | (static_cast<uint32_t>(h[c][2 * j + 1]) << 16);
+  }
+  act_t* dst = blocks + brow * kBlkCols + ky * kBlk + kx0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    *reinterpret_cast<uint4*>(dst + c * kBlk * kBlk) = make_uint4(out[c][0], out[c][1], out[c][2], out[c][3]);
+}
+
+// The same block matrix from fp32 NCHW crops; one thread = one 16-byte output chunk.
+__global__ void __launch_bounds__(256)
+blockcol_pixels_kernel(const float* __restrict__ pixels, act_t* __restrict__ blocks, long long total) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunk = static_cast<int>(idx % (kBlkCols / 8));  // (c, ky, kx0)
+  const long long brow = idx / (kBlkCols / 8);
+  const int b = static_cast<int>(brow / (kBlkGrid * kBlkGrid));
+  const int g = static_cast<int>(brow - static_cast<long long>(b) * (kBlkGrid * kBlkGrid));
+  const int by = g / kBlkGrid, bx = g - by * kBlkGrid;
+  const int c = chunk >> 5, ky = (chunk >> 1) & 15, kx0 = (chunk & 1) * 8;
+  const int y = by * kBlk + ky - kBlkPad;
+  const int x0 = bx * kBlk + kx0 - kBlkPad;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (y >= 0 && y < kImg) {
+    const float* src = pixels + (static_cast<size_t>(b) * 3 + c) * kImg * kImg + static_cast<size_t>(y) * kImg;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int x = x0 + j;
+      if (x >= 0 && x < kImg) v[j] = __ldg(src + x);
+    }
+  }
+  uint4 u;
+  u.x = pack2(v[0], v[1]);
+  u.y = pack2(v[2], v[3]);
+  u.z = pack2(v[4], v[5]);
+  u.w = pack2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(blocks + brow * kBlkCols + chunk * 8) = u;
+}
+
+// conv1 weight [O, 3, 32, 32] -> [O, (dy, dx), 3, 16, 16]: the K order the shifted-A patch GEMM walks.
+__global__ void conv1_regroup_kernel(const act_t* __restrict__ w, act_t* __restrict__ out, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int o = idx / kCols, k = idx - o * kCols;
+  const int s = k / kBlkCols, r = k - s * kBlkCols;
+  const int c = r >> 8, ky = (r >> 4) & 15, kx = r & 15;
+  const int dy = s >> 1, dx = s & 1;
+  out[idx] = w[static_cast<size_t>(o) * kCols + c * kPatch * kPatch + (dy * kBlk + ky) * kPatch + dx * kBlk + kx];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pillow-exact antialiased bicubic resize of a crop rectangle, uint8 HWC
 // ------------------------------------------------------------------------------------------------
 constexpr int kTile = 32;       // output tile (pixels)
@@ -367,6 +474,27 @@ cudaError_t launch_im2col_u8(cudaStream_t st, const uint8_t* arena, const oake_c
   const long long blocks = (total + 255) / 256;
   im2col_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(arena, crops, lut, patches, total, stride, pad,
                                                                   grid);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_blockcol_pixels(cudaStream_t st, const float* pixels, act_t* blocks, int B) {
+  if (B <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(B) * kBlkGrid * kBlkGrid * (kBlkCols / 8);
+  blockcol_pixels_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(pixels, blocks, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_blockcol_u8(cudaStream_t st, const uint8_t* arena, const oake_crop_src* crops, const act_t* lut,
+                               act_t* blocks, int B) {
+  if (B <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(B) * kBlkGrid * kBlkGrid * 32;
+  blockcol_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(arena, crops, lut, blocks, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv1_regroup(cudaStream_t st, const act_t* w, act_t* out, int out_ch) {
+  const int total = out_ch * kCols;
+  conv1_regroup_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, out, total);
   return cudaGetLastError();
 }
 

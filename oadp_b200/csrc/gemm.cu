@@ -408,16 +408,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n_blk = tile - m_blk * num_n;
         const int a_row = (m_blk * CG + cta_rank) * BM;                // this CTA's 128 rows of A
         const int w_row = n_blk * BN + cta_rank * (BN / CG);           // this CTA's share of the W tile
+        int seg = 0, seg_kb = 0;  // shifted-A mode: segment of K, k-block inside it
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          int a_col = kb * BK, a_r = a_row;
+          if (ep.a_seg_kb > 0) {
+            a_col = seg_kb * BK;
+            a_r = a_row + ep.a_shift[seg & 3];
+            if (++seg_kb == ep.a_seg_kb) {
+              seg_kb = 0;
+              ++seg;
+            }
+          }
           if (CG == 2) {
             // both CTAs' bytes are accounted on the leader's barrier
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes * 2);
-            tma_load_2d_2cta(sA + stage * C::kABytes, &tmA, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d_2cta(sA + stage * C::kABytes, &tmA, &full_bar[stage], a_col, a_r);
             tma_load_2d_2cta(sB + stage * C::kBBytes, &tmW, &full_bar[stage], kb * BK, w_row);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-            tma_load_2d(sA + stage * C::kABytes, &tmA, &full_bar[stage], kb * BK, a_row);
+            tma_load_2d(sA + stage * C::kABytes, &tmA, &full_bar[stage], a_col, a_r);
             tma_load_2d(sB + stage * C::kBBytes, &tmW, &full_bar[stage], kb * BK, w_row);
           }
           if (++stage == C::kStages) {

@@ -42,6 +42,11 @@ struct GemmEpilogue {
   float shift = 0.f;
   int ninf_lo = 0;
   int ninf_hi = 0;
+  // Shifted-A mode (patch embedding of the objects tower over the block matrix, frontend.cu): K is walked in
+  // segments of a_seg_kb 64-wide k-blocks; segment s reads A columns [0, 64 a_seg_kb) again, at rows + a_shift[s]
+  // (rows past the end of A read as zeros).  0 = off.
+  int a_seg_kb = 0;
+  int a_shift[4] = {0, 0, 0, 0};
 };
 
 // Encodes a 2D row-major [rows, cols] act_t tensor as a TMA map with a (box_rows x 64) box and
@@ -65,10 +70,11 @@ cudaError_t launch_layernorm(cudaStream_t st, const act_t* x, const float* w, co
                              act_t* out, int rows, int width);
 // Builds the residual stream x (act_t) and its row statistics ([rows][kStatSlots], slot 0 = sum /
 // sum of squares of the stored values, other slots zero): rows [0, B*P) = LN(patch_out + pos[1 + i % P]); rows [B*P, B*P+B) = LN(class_emb +
-// pos[0]); if with_y, rows [B*P+B, B*P+2B) = copy of the class rows.
+// pos[0]); if with_y, rows [B*P+B, B*P+2B) = copy of the class rows.  src_grid > 0: patch (gy, gx) of crop b is row
+// b * src_grid^2 + gy * src_grid + gx of patch_out (the block-matrix GEMM's output grid) instead of row b * P + i.
 cudaError_t launch_assemble_ln_pre(cudaStream_t st, const float* patch_out, const float* class_emb,
                                    const float* pos, const float* w, const float* b, act_t* x,
-                                   float2* stats, int B, int P, int width, int with_y);
+                                   float2* stats, int B, int P, int width, int with_y, int src_grid = 0);
 cudaError_t launch_l2norm_half(cudaStream_t st, const float* e, __half* out, int rows, int dim);
 
 // ----------------------------------------------------------- attention.cu
@@ -95,6 +101,13 @@ cudaError_t launch_im2col_pixels(cudaStream_t st, const float* pixels, act_t* pa
 // ToTensor+Normalize value of byte v in channel c, already rounded to act_t.
 cudaError_t launch_im2col_u8(cudaStream_t st, const uint8_t* arena, const oake_crop_src* crops,
                              const act_t* lut, act_t* patches, int B, int stride, int pad, int grid);
+// Objects tower: the 15 x 15 block matrix [B*225, 768] (16 x 16 blocks of the zero-padded crop, column order
+// (c, ky, kx)) that replaces im2col there, and conv1's weight regrouped to [O, (dy, dx), c, ky, kx] for it.
+constexpr int kBlockGrid = 15;
+cudaError_t launch_blockcol_pixels(cudaStream_t st, const float* pixels, act_t* blocks, int B);
+cudaError_t launch_blockcol_u8(cudaStream_t st, const uint8_t* arena, const oake_crop_src* crops, const act_t* lut,
+                               act_t* blocks, int B);
+cudaError_t launch_conv1_regroup(cudaStream_t st, const act_t* w, act_t* out, int out_ch);
 // Pillow-exact crop + antialiased bicubic resize, one job per (source rectangle -> output window).
 cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs,
                              int n_jobs, int max_tiles, int* err_flag);

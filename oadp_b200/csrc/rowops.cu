@@ -81,14 +81,19 @@ __global__ void __launch_bounds__(256)
 assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restrict__ class_emb,
                        const float* __restrict__ pos, const float* __restrict__ w,
                        const float* __restrict__ b, act_t* __restrict__ x, float2* __restrict__ stats,
-                       int B, int P, int with_y) {
+                       int B, int P, int with_y, int src_grid, int pgrid) {
   const int rows = B * P + B;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const bool is_cls = row >= B * P;
-  const float4* src = reinterpret_cast<const float4*>(
-      is_cls ? class_emb : patch_out + static_cast<size_t>(row) * kWidth);
+  size_t src_row = row;
+  if (src_grid > 0 && !is_cls) {
+    const int b = row / P, i = row - b * P;
+    const int gy = i / pgrid, gx = i - gy * pgrid;
+    src_row = static_cast<size_t>(b) * src_grid * src_grid + gy * src_grid + gx;
+  }
+  const float4* src = reinterpret_cast<const float4*>(is_cls ? class_emb : patch_out + src_row * kWidth);
   const int tok = is_cls ? 0 : 1 + row % P;
   const float4* p4 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(tok) * kWidth);
   float4 v[6];
@@ -133,12 +138,14 @@ cudaError_t launch_layernorm(cudaStream_t st, const act_t* x, const float* w, co
 
 cudaError_t launch_assemble_ln_pre(cudaStream_t st, const float* patch_out, const float* class_emb,
                                    const float* pos, const float* w, const float* b, act_t* x,
-                                   float2* stats, int B, int P, int width, int with_y) {
+                                   float2* stats, int B, int P, int width, int with_y, int src_grid) {
   if (width != kWidth) return cudaErrorInvalidValue;
   if (B <= 0) return cudaSuccess;
   const int rows = B * P + B;
+  int pgrid = 1;
+  while (pgrid * pgrid < P) ++pgrid;
   assemble_ln_pre_kernel<<<(rows + 7) / 8, 256, 0, st>>>(patch_out, class_emb, pos, w, b, x, stats, B,
-                                                         P, with_y);
+                                                         P, with_y, src_grid, pgrid);
   return cudaGetLastError();
 }
 

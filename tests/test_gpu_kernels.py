@@ -211,12 +211,38 @@ def test_attention_side(lib, side_only, B):
 
 @pytest.mark.parametrize('variant', [0, 1])
 def test_im2col(lib, variant):
+    """T50: conv1's im2col.  T197 (stride 16, pad 15; objects.py:299-301): the 15 x 15 matrix of 16 x 16 blocks of
+    the zero-padded crop, which the patch GEMM reads at four row shifts."""
     B = 3
     g = torch.Generator(device=DEV).manual_seed(12)
     px = torch.randn(B, 3, 224, 224, device=DEV, generator=g)
-    stride, pad, grid = ((32, 0, 7), (16, 15, 14))[variant]
-    out = torch.empty(B * grid * grid, 3072, device=DEV, dtype=act_dtype())
+    if variant == 0:
+        out = torch.empty(B * 49, 3072, device=DEV, dtype=act_dtype())
+        ref = F.unfold(px, 32, stride=32).transpose(1, 2).reshape(B * 49, 3072)
+    else:
+        out = torch.empty(B * 225, 768, device=DEV, dtype=act_dtype())
+        ref = F.unfold(F.pad(px, (15, 1, 15, 1)), 16, stride=16).transpose(1, 2).reshape(B * 225, 768)
     binding.check(lib.oake_test_im2col(px.data_ptr(), out.data_ptr(), B, variant, stream()))
     torch.cuda.synchronize()
-    ref = F.unfold(px, 32, padding=pad, stride=stride).transpose(1, 2).reshape(B * grid * grid, 3072)
     assert torch.equal(out, ref.to(act_dtype()))  # pure data movement + one rounding: bit-exact
+
+
+@pytest.mark.parametrize('variant,B', [(0, 3), (1, 1), (1, 5), (1, 37)])
+def test_patch_embed_matches_conv2d(lib, variant, B):
+    """Front-end matrix + conv1 GEMM against F.conv2d on the same rounded operands (objects.py:299-301 for T197:
+    the shifted-A GEMM over the block matrix must equal the stride-16 / pad-15 convolution)."""
+    g = torch.Generator(device=DEV).manual_seed(13 + B)
+    px = torch.randn(B, 3, 224, 224, device=DEV, generator=g)
+    w = (torch.randn(768, 3, 32, 32, device=DEV, generator=g) * 0.02).to(act_dtype())
+    stride, pad, grid, pb = ((32, 0, 7, 49), (16, 15, 14, 225))[variant]
+    out = torch.full((B * pb, 768), float('nan'), device=DEV)
+    binding.check(lib.oake_test_patch_embed(px.data_ptr(), w.data_ptr(), out.data_ptr(), B, variant, stream()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(px.to(act_dtype()).double(), w.double(), stride=stride, padding=pad)  # [B, 768, grid, grid]
+    ref = ref.permute(0, 2, 3, 1)
+    if variant == 0:
+        got = out.view(B, 7, 7, 768)
+    else:
+        got = out.view(B, 15, 15, 768)[:, :14, :14]
+    assert torch.isfinite(got).all()
+    assert (got.double() - ref).abs().max() < 2e-3  # fp32 accumulation over K = 3072 of O(1) x O(0.02) products
