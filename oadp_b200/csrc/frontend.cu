@@ -13,6 +13,8 @@
 //  * im2col_pixels: the same patch matrix from (B,3,224,224) fp32 crops that were preprocessed on
 //    the host, i.e. the tensor the reference hands to `encode_image` / `visual`.
 //  * object_masks: the 14x14 foreground masks of objects.py:129-155.
+#include <mutex>
+
 #include "../../include/oake_b200.h"
 #include "kernels.cuh"
 
@@ -301,54 +303,274 @@ __device__ __forceinline__ uint8_t pil_clip8(int ss) {
   return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-struct ResizeSmem {
-  int kh[kTile][kMaxTaps];
-  int kv[kTile][kMaxTaps];
-  int h_first[kTile], h_count[kTile], v_first[kTile], v_count[kTile];
-  int r_lo, r_hi;
-  double ww[2 * kTile];
-  union {
-    double w[2 * kTile][kMaxTaps];    // raw filter weights (coefficient phase): [0,32) horizontal, [32,64) vertical
-    uint8_t tmp[kMaxRows][kTile][3];  // horizontally resampled rows (pixel phase)
-  };
+// ---- Coefficients once per JOB, pixels per tile.
+// A tile used to regenerate its 64 rows of filter coefficients itself: in fp64, behind five barriers, as many
+// instructions as the pixel work of an upsampled crop (and 40-tap rows for the 5x downscales that the expanded
+// boxes of large proposals need, objects.py:76-99).  resize_prepare_kernel now computes the tables of both axes once
+// per job (libImaging precompute_coeffs + normalize_coeffs_8bpc, the same device functions as before: same bits)
+// into a stream-ordered scratch, and sorts the jobs into two classes:
+//   FAST  at most kFastTaps taps per axis (scale factors up to 3.5): resize_fast_kernel, one CTA per tile, pure
+//         integer pixel work in 17 KB of shared memory -- eight CTAs = 64 warps per SM instead of four (the kernel
+//         is bound by the latency of its byte loads, profiles/r2_07);
+//   BIG   everything else: a persistent grid (56 KB per CTA) walks the (job, tile) list the prepare kernel collected.
+//         Jobs whose tables found no room in the scratch fall back to per-tile generation there.
+// Both kernels compute only the part of a tile's source footprint that lies inside the image: PIL `crop` pads with
+// zeros, a zero row / column of the intermediate image adds exactly 0 to every sum, and a tile that misses the
+// image altogether is written as zeros at once.
+constexpr int kFastTaps = 16;
+constexpr int kFastRows = 128;             // 31 * 3.5 + 2 * 7 + 2 source rows under one 32-row tile
+constexpr int kJobTabInts = 12288;         // scratch budget per job (48 KB); a 224 x 224 FAST window needs 8064 ints
+constexpr int kTabSlackInts = 1 << 20;     // + 4 MB per pass: a few whole-image pyramid levels (640 + 480 samples each)
+
+struct ResizeState {  // header of the scratch of one oake_resize_u8 pass
+  int n_big;          // jobs on the BIG work list
+  int big_tiles;      // sum of their tile counts
+  int next;           // work counter of the persistent kernel
+  int tab_used;       // ints handed out of the table arena
+};
+struct ResizeJobInfo {
+  int cls;      // 0 = FAST, 1 = BIG
+  int tab_off;  // first int of the job's tables in the arena (horizontal entries, then vertical), -1 = none
+  int entry;    // ints per table entry: first, count, taps
+  int pad;
 };
 
+__device__ __forceinline__ int pil_ksize(int in_size, int out_size) {
+  const PilAxis a = pil_axis(in_size, out_size);
+  return static_cast<int>(ceil(a.support)) * 2 + 1;  // libImaging precompute_coeffs
+}
+
+// grid = jobs.  Classifies the job, reserves and fills its tables, appends BIG jobs to the work list.
 __global__ void __launch_bounds__(256)
-resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ dst_arena,
-                 const oake_resize_job* __restrict__ jobs, int* __restrict__ err) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  ResizeSmem& sm = *reinterpret_cast<ResizeSmem*>(smem_raw);
+resize_prepare_kernel(const oake_resize_job* __restrict__ jobs, int n_jobs, ResizeState* __restrict__ state,
+                      ResizeJobInfo* __restrict__ info, int4* __restrict__ big_list, int* __restrict__ tab) {
+  __shared__ ResizeJobInfo s_info;
+  const int jb = blockIdx.x;
+  const oake_resize_job job = jobs[jb];
+  const int samples = job.win_w + job.win_h;
+  if (threadIdx.x == 0) {
+    const int kmax = max(pil_ksize(job.box_w, job.out_w), pil_ksize(job.box_h, job.out_h));
+    ResizeJobInfo ji;
+    ji.entry = 2 + (kmax <= kFastTaps ? kFastTaps : kMaxTaps);
+    ji.pad = 0;
+    ji.tab_off = -1;
+    if (kmax <= kMaxTaps) {
+      const long long need = static_cast<long long>(samples) * ji.entry;
+      const long long cap = static_cast<long long>(n_jobs) * kJobTabInts + kTabSlackInts;
+      if (need <= cap) {
+        const int off = atomicAdd(&state->tab_used, static_cast<int>(need));
+        if (off + need <= cap) ji.tab_off = off;
+      }
+    }
+    ji.cls = (kmax <= kFastTaps && ji.tab_off >= 0) ? 0 : 1;
+    if (ji.cls == 1) {
+      const int tiles = ((job.win_w + kTile - 1) / kTile) * ((job.win_h + kTile - 1) / kTile);
+      const int slot = atomicAdd(&state->n_big, 1);
+      const int start = atomicAdd(&state->big_tiles, tiles);
+      big_list[slot] = make_int4(jb, start, tiles, 0);
+    }
+    s_info = ji;
+    info[jb] = ji;
+  }
+  __syncthreads();
+  const ResizeJobInfo ji = s_info;
+  if (ji.tab_off < 0) return;
+  const PilAxis ax_h = pil_axis(job.box_w, job.out_w);
+  const PilAxis ax_v = pil_axis(job.box_h, job.out_h);
+  const int taps = ji.entry - 2;
+  for (int sidx = threadIdx.x; sidx < samples; sidx += blockDim.x) {
+    const bool is_h = sidx < job.win_w;
+    const PilAxis& ax = is_h ? ax_h : ax_v;
+    const int in_size = is_h ? job.box_w : job.box_h;
+    const int xx = is_h ? job.win_x + sidx : job.win_y + sidx - job.win_w;
+    int first, count;
+    pil_bounds(ax, in_size, xx, &first, &count);
+    count = min(count, taps);  // (count <= ksize <= taps already)
+    double w[kMaxTaps];
+    for (int x = 0; x < count; ++x) w[x] = pil_weight(ax, xx, first, x);
+    const double ww = pil_weight_sum(w, count);
+    int* e = tab + ji.tab_off + static_cast<size_t>(sidx) * ji.entry;
+    e[0] = first;
+    e[1] = count;
+    for (int x = 0; x < count; ++x) e[2 + x] = pil_fixed(w[x], ww);
+  }
+}
+
+template <int TAPS, int ROWS, bool GEN>
+struct TileSmem {
+  int kh[kTile][TAPS + 1];  // (+1: odd row pitch, thread = column reads are conflict-free)
+  int kv[kTile][TAPS + 1];
+  int h_first[kTile], h_count[kTile], v_first[kTile], v_count[kTile];
+  int work_job, work_tile;
+  double ww[GEN ? 2 * kTile : 1];
+  union {
+    double w[GEN ? 2 * kTile : 1][GEN ? kMaxTaps : 1];  // raw filter weights (per-tile generation: BIG jobs without a table)
+    uint8_t tmp[ROWS][kTile][3];    // horizontally resampled rows (pixel phase)
+  };
+};
+using FastSmem = TileSmem<kFastTaps, kFastRows, false>;
+using BigSmem = TileSmem<kMaxTaps, kMaxRows, true>;
+
+// The tile's 32 + 32 table entries -> shared memory.  (ox0, oy0): tile origin relative to the window.
+template <class SM>
+__device__ __forceinline__ void tile_load_tables(SM& sm, const int* __restrict__ tj, int entry, int win_w, int ox0,
+                                                 int oy0, int tw, int th) {
+  const int* eh = tj + static_cast<size_t>(ox0) * entry;
+  const int* ev = tj + static_cast<size_t>(win_w + oy0) * entry;
+  const int per_axis = kTile * entry;
+  for (int idx = threadIdx.x; idx < 2 * per_axis; idx += blockDim.x) {
+    const bool is_h = idx < per_axis;
+    const int k = is_h ? idx : idx - per_axis;
+    const int e = k / entry, f = k - e * entry;
+    if (e >= (is_h ? tw : th)) continue;
+    const int v = __ldg((is_h ? eh : ev) + k);
+    if (f == 0) (is_h ? sm.h_first : sm.v_first)[e] = v;
+    else if (f == 1) (is_h ? sm.h_count : sm.v_count)[e] = v;
+    else (is_h ? sm.kh : sm.kv)[e][f - 2] = v;
+  }
+}
+
+// Source footprint of the tile (valid after the tile's bounds are in shared memory and a barrier):
+// tmp row r holds source row y_lo + r; rows [rv0, rv1) lie inside the image.  Returns false for a tile that
+// misses the image altogether.  Bounds are monotonic in the sample index (libImaging: xmin, xmax from a centre
+// that grows with the sample).
+struct Footprint {
+  int r_lo, nr, y_lo, rv0, rv1;
+};
+template <class SM>
+__device__ __forceinline__ bool tile_footprint(const SM& sm, const oake_resize_job& job, int tw, int th, int max_rows,
+                                               int* __restrict__ err, Footprint* fp) {
+  fp->r_lo = sm.v_first[0];
+  fp->nr = sm.v_first[th - 1] + sm.v_count[th - 1] - fp->r_lo;
+  if (fp->nr > max_rows) {
+    if (threadIdx.x == 0) atomicExch(err, 1);
+    fp->nr = max_rows;
+  }
+  fp->y_lo = job.box_y0 + fp->r_lo;
+  fp->rv0 = max(0, -fp->y_lo);
+  fp->rv1 = min(fp->nr, job.src_h - fp->y_lo);
+  const int x_lo = job.box_x0 + sm.h_first[0], x_hi = job.box_x0 + sm.h_first[tw - 1] + sm.h_count[tw - 1];
+  return fp->rv0 < fp->rv1 && x_hi > 0 && x_lo < job.src_w;
+}
+
+template <class SM>
+__device__ __forceinline__ void tile_zero(const oake_resize_job& job, uint8_t* __restrict__ dst_arena, int ox0, int oy0,
+                                          int tw, int th) {
+  uint8_t* dst = dst_arena + job.dst_off;
+  const int j = threadIdx.x & (kTile - 1);
+  for (int r = threadIdx.x / kTile; r < th && j < tw; r += blockDim.x / kTile) {
+    uint8_t* o = dst + (static_cast<long long>(oy0 + r) * job.dst_pitch_px + ox0 + j) * 3;
+    o[0] = 0;
+    o[1] = 0;
+    o[2] = 0;
+  }
+}
+
+// Horizontal pass (crop rows y_lo + [rv0, rv1) -> tmp, uint8 like Pillow's intermediate image), barrier, vertical
+// pass.  One thread per (row, output column): the three channels share the tap loop, and the taps that fall outside
+// the source image are cut off once, outside the loop.
+template <class SM>
+__device__ __forceinline__ void tile_pixels(SM& sm, const oake_resize_job& job, const uint8_t* __restrict__ src_arena,
+                                            uint8_t* __restrict__ dst_arena, int ox0, int oy0, int tw, int th,
+                                            const Footprint& fp) {
+  const uint8_t* src = src_arena + job.src_off;
+  uint8_t* dst = dst_arena + job.dst_off;
+  const int tid = threadIdx.x;
+  const int j = tid & (kTile - 1);  // output column of the tile; rows go tid / 32, + 8, + 16, ...
+  if (j < tw) {
+    const int first = job.box_x0 + sm.h_first[j];
+    const int t0 = max(0, -first);
+    const int t1 = min(sm.h_count[j], job.src_w - first);
+    const int* k = sm.kh[j];
+    for (int r = fp.rv0 + tid / kTile; r < fp.rv1; r += blockDim.x / kTile) {
+      int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
+      const uint8_t* px = src + (static_cast<long long>(fp.y_lo + r) * job.src_pitch_px + first + t0) * 3;
+#pragma unroll 4
+      for (int t = t0; t < t1; ++t, px += 3) {
+        const int kk = k[t];
+        s0 += static_cast<int>(px[0]) * kk;
+        s1 += static_cast<int>(px[1]) * kk;
+        s2 += static_cast<int>(px[2]) * kk;
+      }
+      uint8_t* o = sm.tmp[r][j];
+      o[0] = pil_clip8(s0);
+      o[1] = pil_clip8(s1);
+      o[2] = pil_clip8(s2);
+    }
+  }
+  __syncthreads();
+  for (int r = tid / kTile; r < th && j < tw; r += blockDim.x / kTile) {
+    const int first = sm.v_first[r] - fp.r_lo;
+    const int t0 = max(0, fp.rv0 - first);
+    const int t1 = min(sm.v_count[r], fp.rv1 - first);
+    const int* k = sm.kv[r];
+    const uint8_t* px = sm.tmp[first + t0][j];
+    int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
+#pragma unroll 4
+    for (int t = t0; t < t1; ++t, px += kTile * 3) {
+      const int kk = k[t];
+      s0 += static_cast<int>(px[0]) * kk;
+      s1 += static_cast<int>(px[1]) * kk;
+      s2 += static_cast<int>(px[2]) * kk;
+    }
+    uint8_t* o = dst + (static_cast<long long>(oy0 + r) * job.dst_pitch_px + ox0 + j) * 3;
+    o[0] = pil_clip8(s0);
+    o[1] = pil_clip8(s1);
+    o[2] = pil_clip8(s2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+resize_fast_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ dst_arena,
+                   const oake_resize_job* __restrict__ jobs, const ResizeJobInfo* __restrict__ info,
+                   const int* __restrict__ tab, int* __restrict__ err) {
+  __shared__ FastSmem sm;
+  const ResizeJobInfo ji = info[blockIdx.y];
+  if (ji.cls != 0) return;
   const oake_resize_job job = jobs[blockIdx.y];
   const int tiles_x = (job.win_w + kTile - 1) / kTile;
   const int tiles_y = (job.win_h + kTile - 1) / kTile;
   if (static_cast<int>(blockIdx.x) >= tiles_x * tiles_y) return;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int ox0 = job.win_x + tx * kTile, oy0 = job.win_y + ty * kTile;
-  const int tw = min(kTile, job.win_x + job.win_w - ox0);
-  const int th = min(kTile, job.win_y + job.win_h - oy0);
-  const int tid = threadIdx.x;
+  const int ox0 = tx * kTile, oy0 = ty * kTile;  // relative to the window
+  const int tw = min(kTile, job.win_w - ox0);
+  const int th = min(kTile, job.win_h - oy0);
+  tile_load_tables(sm, tab + ji.tab_off, ji.entry, job.win_w, ox0, oy0, tw, th);
+  __syncthreads();
+  Footprint fp;
+  if (!tile_footprint(sm, job, tw, th, kFastRows, err, &fp)) {
+    tile_zero<FastSmem>(job, dst_arena, ox0, oy0, tw, th);
+    return;
+  }
+  tile_pixels(sm, job, src_arena, dst_arena, ox0, oy0, tw, th, fp);
+}
 
+// Per-tile coefficient generation (BIG jobs without a table): the CTA shares the work -- pil_bounds one thread per
+// output sample, pil_weight one thread per tap, pil_weight_sum one thread per sample (libImaging's order), the
+// divide / fixed-point rounding of every tap independent again.
+__device__ __forceinline__ void tile_generate(BigSmem& sm, const oake_resize_job& job, int ox0, int oy0, int tw, int th) {
+  const int tid = threadIdx.x;
   const PilAxis ax_h = pil_axis(job.box_w, job.out_w);
   const PilAxis ax_v = pil_axis(job.box_h, job.out_h);
+  const int gx0 = job.win_x + ox0, gy0 = job.win_y + oy0;
   if (tid < kTile) {
-    if (tid < tw) pil_bounds(ax_h, job.box_w, ox0 + tid, &sm.h_first[tid], &sm.h_count[tid]);
+    if (tid < tw) pil_bounds(ax_h, job.box_w, gx0 + tid, &sm.h_first[tid], &sm.h_count[tid]);
   } else if (tid < 2 * kTile) {
     const int r = tid - kTile;
-    if (r < th) pil_bounds(ax_v, job.box_h, oy0 + r, &sm.v_first[r], &sm.v_count[r]);
+    if (r < th) pil_bounds(ax_v, job.box_h, gy0 + r, &sm.v_first[r], &sm.v_count[r]);
   }
   __syncthreads();
-  // One filter tap per thread: thread = (sample sidx = tid % 64, tap x = tid / 64, + 4, + 8, ...), so a
-  // warp holds 32 samples at the same tap and the loop stops at the widest tap window of the tile
-  // (typically 5..9 of the 48 slots).
+  // thread = (sample sidx = tid % 64, tap x = tid / 64, + 4, + 8, ...): a warp holds 32 samples at the same tap and
+  // the loop stops at the widest tap window of the tile
   const int sidx = tid & (2 * kTile - 1);
   const bool s_h = sidx < kTile;
   const int s_r = sidx - kTile;
   const bool s_live = s_h ? sidx < tw : s_r < th;
   const int s_count = !s_live ? 0 : (s_h ? sm.h_count[sidx] : sm.v_count[s_r]);
   const int s_first = !s_live ? 0 : (s_h ? sm.h_first[sidx] : sm.v_first[s_r]);
-  const int max_count = __reduce_max_sync(0xffffffffu, s_count);  // widest window among this warp's 32 samples
+  const int max_count = __reduce_max_sync(0xffffffffu, s_count);
   for (int x = tid / (2 * kTile); x < max_count; x += blockDim.x / (2 * kTile))
-    if (x < s_count) sm.w[sidx][x] = pil_weight(s_h ? ax_h : ax_v, s_h ? ox0 + sidx : oy0 + s_r, s_first, x);
+    if (x < s_count) sm.w[sidx][x] = pil_weight(s_h ? ax_h : ax_v, s_h ? gx0 + sidx : gy0 + s_r, s_first, x);
   __syncthreads();
   if (tid < kTile) {
     if (tid < tw) sm.ww[tid] = pil_weight_sum(sm.w[tid], sm.h_count[tid]);
@@ -359,67 +581,53 @@ resize_u8_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ ds
   __syncthreads();
   for (int x = tid / (2 * kTile); x < max_count; x += blockDim.x / (2 * kTile))
     if (x < s_count) (s_h ? sm.kh[sidx] : sm.kv[s_r])[x] = pil_fixed(sm.w[sidx][x], sm.ww[sidx]);
-  __syncthreads();
-  if (tid == 0) {
-    int lo = sm.v_first[0], hi = 0;
-    for (int r = 0; r < th; ++r) hi = max(hi, sm.v_first[r] + sm.v_count[r]);
-    sm.r_lo = lo;
-    sm.r_hi = hi;
-    if (hi - lo > kMaxRows) atomicExch(err, 1);
-  }
-  __syncthreads();
-  const int r_lo = sm.r_lo;
-  const int nr = min(sm.r_hi - r_lo, kMaxRows);
-  const uint8_t* src = src_arena + job.src_off;
+  __syncthreads();  // (the weights' storage is the pixel phase's tmp)
+}
 
-  // horizontal pass: crop rows [r_lo, r_lo + nr) -> tmp (uint8, like Pillow's intermediate image).
-  // One thread per (row, output column): the three channels share the tap loop, and the taps that
-  // fall outside the source image (zero padding of PIL `crop`) are cut off once, outside the loop.
-  const int j = tid & (kTile - 1);  // output column of the tile; rows go tid / 32, + 8, + 16, ...
-  for (int r = tid / kTile; r < nr && j < tw; r += blockDim.x / kTile) {
-    const int y = job.box_y0 + r_lo + r;
-    int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
-    if (y >= 0 && y < job.src_h) {
-      const int first = job.box_x0 + sm.h_first[j];
-      const int t0 = max(0, -first);
-      const int t1 = min(sm.h_count[j], job.src_w - first);
-      const uint8_t* px = src + (static_cast<long long>(y) * job.src_pitch_px + first + t0) * 3;
-      const int* k = sm.kh[j];
-#pragma unroll 4
-      for (int t = t0; t < t1; ++t, px += 3) {
-        const int kk = k[t];
-        s0 += static_cast<int>(px[0]) * kk;
-        s1 += static_cast<int>(px[1]) * kk;
-        s2 += static_cast<int>(px[2]) * kk;
+// Persistent grid over the (job, tile) pairs of the BIG jobs; nothing to do (and gone at once) when there are none.
+__global__ void __launch_bounds__(256)
+resize_big_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ dst_arena,
+                  const oake_resize_job* __restrict__ jobs, ResizeState* __restrict__ state,
+                  const ResizeJobInfo* __restrict__ info, const int4* __restrict__ big_list,
+                  const int* __restrict__ tab, int* __restrict__ err) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  BigSmem& sm = *reinterpret_cast<BigSmem*>(smem_raw);
+  const int total = state->big_tiles, n_big = state->n_big;
+  for (;;) {
+    __syncthreads();  // the previous tile's shared memory is free
+    if (threadIdx.x == 0) sm.work_tile = atomicAdd(&state->next, 1);
+    __syncthreads();
+    const int w = sm.work_tile;
+    if (w >= total) return;
+    __syncthreads();  // everyone has read the work index before the search overwrites it
+    for (int e = threadIdx.x; e < n_big; e += blockDim.x) {
+      const int4 it = big_list[e];
+      if (w >= it.y && w < it.y + it.z) {
+        sm.work_job = it.x;
+        sm.work_tile = w - it.y;
       }
     }
-    uint8_t* o = sm.tmp[r][j];
-    o[0] = pil_clip8(s0);
-    o[1] = pil_clip8(s1);
-    o[2] = pil_clip8(s2);
-  }
-  __syncthreads();
-
-  // vertical pass
-  uint8_t* dst = dst_arena + job.dst_off;
-  for (int r = tid / kTile; r < th && j < tw; r += blockDim.x / kTile) {
-    const int first = sm.v_first[r] - r_lo;
-    const int t1 = min(sm.v_count[r], nr - first);
-    const int* k = sm.kv[r];
-    const uint8_t* px = sm.tmp[first][j];
-    int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
-#pragma unroll 4
-    for (int t = 0; t < t1; ++t, px += kTile * 3) {
-      const int kk = k[t];
-      s0 += static_cast<int>(px[0]) * kk;
-      s1 += static_cast<int>(px[1]) * kk;
-      s2 += static_cast<int>(px[2]) * kk;
+    __syncthreads();
+    const int jb = sm.work_job, tile = sm.work_tile;
+    const oake_resize_job job = jobs[jb];
+    const ResizeJobInfo ji = info[jb];
+    const int tiles_x = (job.win_w + kTile - 1) / kTile;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int ox0 = tx * kTile, oy0 = ty * kTile;
+    const int tw = min(kTile, job.win_w - ox0);
+    const int th = min(kTile, job.win_h - oy0);
+    if (ji.tab_off >= 0) {
+      tile_load_tables(sm, tab + ji.tab_off, ji.entry, job.win_w, ox0, oy0, tw, th);
+      __syncthreads();
+    } else {
+      tile_generate(sm, job, ox0, oy0, tw, th);
     }
-    const int oy = oy0 - job.win_y + r, ox = ox0 - job.win_x + j;
-    uint8_t* o = dst + (static_cast<long long>(oy) * job.dst_pitch_px + ox) * 3;
-    o[0] = pil_clip8(s0);
-    o[1] = pil_clip8(s1);
-    o[2] = pil_clip8(s2);
+    Footprint fp;
+    if (!tile_footprint(sm, job, tw, th, kMaxRows, err, &fp)) {
+      tile_zero<BigSmem>(job, dst_arena, ox0, oy0, tw, th);
+      continue;
+    }
+    tile_pixels(sm, job, src_arena, dst_arena, ox0, oy0, tw, th, fp);
   }
 }
 
@@ -498,14 +706,68 @@ cudaError_t launch_conv1_regroup(cudaStream_t st, const act_t* w, act_t* out, in
   return cudaGetLastError();
 }
 
+namespace {
+// Stream-ordered scratch of the resize calls: a pool of its own per device that keeps what it has been given
+// (the default pool hands memory back at every synchronisation).
+cudaError_t resize_pool(cudaMemPool_t* out) {
+  static cudaMemPool_t pools[64] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (pools[dev] == nullptr) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    if (cudaError_t e = cudaMemPoolCreate(&pool, &props); e != cudaSuccess) return e;
+    unsigned long long keep = ~0ull;
+    if (cudaError_t e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); e != cudaSuccess) return e;
+    pools[dev] = pool;
+  }
+  *out = pools[dev];
+  return cudaSuccess;
+}
+constexpr int kResizeSlice = 8192;  // jobs per pass: bounds the table scratch at 8192 x 48 KB = 403 MB
+}  // namespace
+
 cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs,
                              int n_jobs, int max_tiles, int* err_flag) {
   if (n_jobs <= 0 || max_tiles <= 0) return cudaSuccess;
-  if (cudaError_t e = ensure_dynamic_smem<resize_u8_kernel>(static_cast<int>(sizeof(ResizeSmem))); e != cudaSuccess)
+  if (cudaError_t e = ensure_dynamic_smem<resize_big_kernel>(static_cast<int>(sizeof(BigSmem))); e != cudaSuccess)
     return e;
-  dim3 grid(max_tiles, n_jobs);
-  resize_u8_kernel<<<grid, 256, sizeof(ResizeSmem), st>>>(src, dst, jobs, err_flag);
-  return cudaGetLastError();
+  int dev = 0, num_sms = 0;
+  if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+  if (cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); e != cudaSuccess) return e;
+  cudaMemPool_t pool;
+  if (cudaError_t e = resize_pool(&pool); e != cudaSuccess) return e;
+  const int slice = n_jobs < kResizeSlice ? n_jobs : kResizeSlice;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t off_info = 256;
+  const size_t off_list = off_info + up(static_cast<size_t>(slice) * sizeof(ResizeJobInfo));
+  const size_t off_tab = off_list + up(static_cast<size_t>(slice) * sizeof(int4));
+  const size_t bytes = off_tab + (static_cast<size_t>(slice) * kJobTabInts + kTabSlackInts) * sizeof(int);
+  uint8_t* scratch = nullptr;
+  if (cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), bytes, pool, st); e != cudaSuccess) return e;
+  ResizeState* state = reinterpret_cast<ResizeState*>(scratch);
+  ResizeJobInfo* info = reinterpret_cast<ResizeJobInfo*>(scratch + off_info);
+  int4* big_list = reinterpret_cast<int4*>(scratch + off_list);
+  int* tab = reinterpret_cast<int*>(scratch + off_tab);
+  cudaError_t err = cudaSuccess;
+  for (int j0 = 0; j0 < n_jobs && err == cudaSuccess; j0 += slice) {
+    const int n = n_jobs - j0 < slice ? n_jobs - j0 : slice;
+    err = cudaMemsetAsync(state, 0, sizeof(ResizeState), st);
+    if (err != cudaSuccess) break;
+    resize_prepare_kernel<<<n, 256, 0, st>>>(jobs + j0, n, state, info, big_list, tab);
+    resize_fast_kernel<<<dim3(max_tiles, n), 256, 0, st>>>(src, dst, jobs + j0, info, tab, err_flag);
+    resize_big_kernel<<<4 * num_sms, 256, sizeof(BigSmem), st>>>(src, dst, jobs + j0, state, info, big_list, tab, err_flag);
+    err = cudaGetLastError();
+  }
+  const cudaError_t e2 = cudaFreeAsync(scratch, st);
+  return err != cudaSuccess ? err : e2;
 }
 
 cudaError_t launch_object_masks(cudaStream_t st, const float* fg, const float* box, float* masks, int B,
