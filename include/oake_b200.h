@@ -124,6 +124,18 @@ typedef struct {
 int oake_resize_u8(const uint8_t* src_arena, uint8_t* dst_arena, const oake_resize_job* jobs, int n_jobs,
                    int max_tiles, int* err_flag, void* stream);
 
+/* The same crop-and-resize with the pixels written straight into the tower's front-end matrix inside `ws`
+ * (ToTensor + Normalize through the exact fp32 table, rounded once to the tensor-core type): job i becomes crop i of
+ * a following oake_encode_patches(h, n_jobs, variant, ...) on the same workspace and stream.  Every job's window must
+ * be the whole 224 x 224 crop (win_x = win_y = 0 of a 224 x 224 resize, or the CenterCrop window); dst_off and
+ * dst_pitch_px are ignored.  This is the reference's transform + `encode_image` / `visual` call without the uint8
+ * crop in between (oadp/oake/globals.py:32,57; objects.py:116-127,330). */
+int oake_resize_to_patches(oake_handle* h, const uint8_t* src_arena, const oake_resize_job* jobs, int n_jobs,
+                           int variant, void* ws, size_t ws_bytes, int* err_flag, void* stream);
+/* The tower on the front-end matrix that oake_resize_to_patches left in `ws` (same B = n_jobs, same variant). */
+int oake_encode_patches(oake_handle* h, int B, int variant, const float* masks, void* out_f16, float* out_raw_f32,
+                        void* ws, size_t ws_bytes, void* stream);
+
 /* Where a 224x224 uint8 HWC crop lives: arena + off, rows pitch_px pixels apart.  Block crops of
  * oadp/oake/blocks.py:79-81 need no copy at all: they are windows into the pyramid level. */
 typedef struct {

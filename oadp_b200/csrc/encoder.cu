@@ -324,15 +324,16 @@ int oake_workspace_bytes(const oake_handle* h, int max_crops, int variant, size_
 
 namespace {
 
-// The tower.  Exactly one of `pixels` (fp32 NCHW crops) or (`arena`, `crops`) (uint8 crops) is given.
+// The tower.  Exactly one of `pixels` (fp32 NCHW crops) or (`arena`, `crops`) (uint8 crops) is given -- or neither
+// with `prepared`: the workspace's front-end matrix has been filled by oake_resize_to_patches.
 int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const oake_crop_src* crops, int B,
                 int variant, const float* masks, void* out_f16, float* out_raw_f32, void* ws, size_t ws_bytes,
-                void* stream) {
+                void* stream, bool prepared = false) {
   if (!h) return fail("handle is NULL");
   if (variant != OAKE_VARIANT_T50 && variant != OAKE_VARIANT_T197) return fail("bad variant %d", variant);
   if (B < 0) return fail("B < 0");
   if (B == 0) return 0;
-  if ((!pixels && !(arena && crops)) || !out_f16 || !ws) return fail("NULL buffer");
+  if ((!prepared && !pixels && !(arena && crops)) || !out_f16 || !ws) return fail("NULL buffer");
   const bool side = variant == OAKE_VARIANT_T197;
   if (side && !masks) return fail("variant T197 needs masks");
   if (side && !h->w.pos_t197) return fail("handle was created without pos_t197");
@@ -378,7 +379,7 @@ int encode_impl(oake_handle* h, const float* pixels, const uint8_t* arena, const
 
   // K0/K1: crops -> conv1 patch matrix -> patch embedding -> tokens + ln_pre (+ row statistics)
   // (objects tower: the 15 x 15 block matrix instead of im2col, read at four row shifts by the GEMM -- frontend.cu)
-  go.run(K_FRONTEND, 0, [&] {
+  if (!prepared) go.run(K_FRONTEND, 0, [&] {
     if (side) return pixels ? launch_blockcol_pixels(st, pixels, patches, B) : launch_blockcol_u8(st, arena, crops, h->pixel_lut, patches, B);
     if (pixels) return launch_im2col_pixels(st, pixels, patches, B, 32, 0, 7);
     return launch_im2col_u8(st, arena, crops, h->pixel_lut, patches, B, 32, 0, 7);
@@ -479,6 +480,32 @@ int oake_encode_crops_u8(oake_handle* h, const uint8_t* arena, const oake_crop_s
                          void* stream) {
   if (B > 0 && (!arena || !crops)) return fail("arena / crops is NULL");
   return encode_impl(h, nullptr, arena, crops, B, variant, masks, out_f16, out_raw_f32, ws, ws_bytes, stream);
+}
+
+int oake_resize_to_patches(oake_handle* h, const uint8_t* src_arena, const oake_resize_job* jobs, int n_jobs, int variant,
+                           void* ws, size_t ws_bytes, int* err_flag, void* stream) {
+  if (!h) return fail("handle is NULL");
+  if (variant != OAKE_VARIANT_T50 && variant != OAKE_VARIANT_T197) return fail("bad variant %d", variant);
+  if (n_jobs < 0) return fail("negative count");
+  if (n_jobs == 0) return 0;
+  if (!src_arena || !jobs || !ws || !err_flag) return fail("NULL buffer");
+  const Plan p = make_plan(h, n_jobs, variant);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + kAlign - 1) / kAlign * kAlign);
+  if (static_cast<size_t>(base - static_cast<uint8_t*>(ws)) + p.total > ws_bytes)
+    return fail("workspace too small: need %zu bytes, got %zu", p.total + kAlign, ws_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  nvtxRangePushA("frontend_resize_to_patches");
+  cudaError_t e = launch_resize_to_matrix(st, src_arena, jobs, n_jobs, err_flag, h->pixel_lut,
+                                          reinterpret_cast<act_t*>(base + p.off_patches), variant == OAKE_VARIANT_T197 ? 1 : 0);
+  nvtxRangePop();
+  h->launches += 3;
+  if (e != cudaSuccess) return fail("resize_to_patches launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int oake_encode_patches(oake_handle* h, int B, int variant, const float* masks, void* out_f16, float* out_raw_f32,
+                        void* ws, size_t ws_bytes, void* stream) {
+  return encode_impl(h, nullptr, nullptr, nullptr, B, variant, masks, out_f16, out_raw_f32, ws, ws_bytes, stream, true);
 }
 
 int oake_resize_u8(const uint8_t* src_arena, uint8_t* dst_arena, const oake_resize_job* jobs, int n_jobs,

@@ -330,11 +330,26 @@ struct ResizeState {  // header of the scratch of one oake_resize_u8 pass
 };
 struct ResizeJobInfo {
   int cls;      // 0 = FAST, 1 = BIG
-  int tab_off;  // first int of the job's tables in the arena (horizontal entries, then vertical), -1 = none
-  int entry;    // ints per table entry: first, count, taps
+  int tab_off;  // first int of the job's tables in the arena, -1 = none.  Per axis (horizontal, then vertical), with
+                // n = the window size rounded up to whole tiles: first[n], count[n], taps[n][pitch]
+  int pitch;    // ints per row of taps: kFastTaps + 1 or kMaxTaps + 1
   int pad;
 };
 
+// Where the resized pixels go.  mode 0: uint8 HWC at the job's dst_off (the C ABI's oake_resize_u8).  mode 1: straight
+// into the tower's front-end matrix as act_t through the ToTensor + Normalize table -- job i of the launch is crop
+// crop0 + i, its window is the whole 224 x 224 crop, and pixel (y, x, c) lands at
+//   row (crop * grid + (y + pad) >> shift) * grid + ((x + pad) >> shift),  column (c << 2 shift) + ky << shift + kx
+// (T50: 32 x 32 patches = conv1's im2col, shift 5, pad 0, grid 7; T197: the 16 x 16 block matrix, shift 4, pad 15,
+// grid 15).  Every pixel has exactly one place in either matrix, so the uint8 crop and the kernel that re-read it
+// disappear.
+struct ResizeOut {
+  int mode;
+  act_t* matrix;
+  const act_t* lut;
+  int shift, pad, grid;
+  int crop0;
+};
 __device__ __forceinline__ int pil_ksize(int in_size, int out_size) {
   const PilAxis a = pil_axis(in_size, out_size);
   return static_cast<int>(ceil(a.support)) * 2 + 1;  // libImaging precompute_coeffs
@@ -343,19 +358,27 @@ __device__ __forceinline__ int pil_ksize(int in_size, int out_size) {
 // grid = jobs.  Classifies the job, reserves and fills its tables, appends BIG jobs to the work list.
 __global__ void __launch_bounds__(256)
 resize_prepare_kernel(const oake_resize_job* __restrict__ jobs, int n_jobs, ResizeState* __restrict__ state,
-                      ResizeJobInfo* __restrict__ info, int4* __restrict__ big_list, int* __restrict__ tab) {
+                      ResizeJobInfo* __restrict__ info, int4* __restrict__ big_list, int* __restrict__ tab,
+                      int* __restrict__ err, ResizeOut out) {
   __shared__ ResizeJobInfo s_info;
   const int jb = blockIdx.x;
   const oake_resize_job job = jobs[jb];
-  const int samples = job.win_w + job.win_h;
+  if (out.mode == 1 && (job.win_w != kImg || job.win_h != kImg)) {  // the matrix holds whole crops only
+    if (threadIdx.x == 0) {
+      atomicExch(err, 1);
+      info[jb] = ResizeJobInfo{0, -1, 0, 1};  // (pad = 1: skipped by both tile kernels)
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     const int kmax = max(pil_ksize(job.box_w, job.out_w), pil_ksize(job.box_h, job.out_h));
     ResizeJobInfo ji;
-    ji.entry = 2 + (kmax <= kFastTaps ? kFastTaps : kMaxTaps);
+    ji.pitch = 1 + (kmax <= kFastTaps ? kFastTaps : kMaxTaps);
     ji.pad = 0;
     ji.tab_off = -1;
     if (kmax <= kMaxTaps) {
-      const long long need = static_cast<long long>(samples) * ji.entry;
+      const int n_h = (job.win_w + kTile - 1) / kTile * kTile, n_v = (job.win_h + kTile - 1) / kTile * kTile;
+      const long long need = static_cast<long long>(n_h + n_v) * (2 + ji.pitch);
       const long long cap = static_cast<long long>(n_jobs) * kJobTabInts + kTabSlackInts;
       if (need <= cap) {
         const int off = atomicAdd(&state->tab_used, static_cast<int>(need));
@@ -373,35 +396,60 @@ resize_prepare_kernel(const oake_resize_job* __restrict__ jobs, int n_jobs, Resi
     info[jb] = ji;
   }
   __syncthreads();
+  if (out.mode == 1 && out.pad > 0) {
+    // the zero border of the padded crop: every (block, channel, ky) row of the matrix that holds a padding element
+    // is cleared here; the tile kernels (later in the stream) then write the pixels that share those rows
+    const int crop = out.crop0 + jb, g = out.grid, bs = 1 << out.shift;  // (one row = bs elements = 32 bytes at bs = 16)
+    const int last = 224 + out.pad - 1;                                  // last padded coordinate that holds a pixel
+    act_t* base = out.matrix + static_cast<size_t>(crop) * g * g * 3 * bs * bs;
+    for (int row = threadIdx.x; row < g * g * 3 * bs; row += blockDim.x) {
+      const int ky = row & (bs - 1), blk = row / (3 * bs);
+      const int by = blk / g, bx = blk - by * g;
+      const int py = by * bs + ky;
+      const bool padded = py < out.pad || py > last || bx * bs < out.pad || bx * bs + bs - 1 > last;
+      if (padded) {
+        uint4* o = reinterpret_cast<uint4*>(base + static_cast<size_t>(row) * bs);
+        for (int i = 0; i < bs / 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
   const ResizeJobInfo ji = s_info;
   if (ji.tab_off < 0) return;
   const PilAxis ax_h = pil_axis(job.box_w, job.out_w);
   const PilAxis ax_v = pil_axis(job.box_h, job.out_h);
-  const int taps = ji.entry - 2;
-  for (int sidx = threadIdx.x; sidx < samples; sidx += blockDim.x) {
-    const bool is_h = sidx < job.win_w;
-    const PilAxis& ax = is_h ? ax_h : ax_v;
-    const int in_size = is_h ? job.box_w : job.box_h;
-    const int xx = is_h ? job.win_x + sidx : job.win_y + sidx - job.win_w;
-    int first, count;
-    pil_bounds(ax, in_size, xx, &first, &count);
-    count = min(count, taps);  // (count <= ksize <= taps already)
-    double w[kMaxTaps];
-    for (int x = 0; x < count; ++x) w[x] = pil_weight(ax, xx, first, x);
-    const double ww = pil_weight_sum(w, count);
-    int* e = tab + ji.tab_off + static_cast<size_t>(sidx) * ji.entry;
-    e[0] = first;
-    e[1] = count;
-    for (int x = 0; x < count; ++x) e[2 + x] = pil_fixed(w[x], ww);
+  const int n_h = (job.win_w + kTile - 1) / kTile * kTile, n_v = (job.win_h + kTile - 1) / kTile * kTile;
+  for (int sidx = threadIdx.x; sidx < n_h + n_v; sidx += blockDim.x) {
+    const bool is_h = sidx < n_h;
+    const int i = is_h ? sidx : sidx - n_h, n = is_h ? n_h : n_v;
+    int* axis = tab + ji.tab_off + (is_h ? 0 : n_h * (2 + ji.pitch));
+    int first = 0, count = 0;
+    if (i < (is_h ? job.win_w : job.win_h)) {
+      const PilAxis& ax = is_h ? ax_h : ax_v;
+      const int xx = (is_h ? job.win_x : job.win_y) + i;
+      pil_bounds(ax, is_h ? job.box_w : job.box_h, xx, &first, &count);
+      count = min(count, ji.pitch - 1);  // (count <= ksize <= taps already)
+      double w[kMaxTaps];
+      for (int x = 0; x < count; ++x) w[x] = pil_weight(ax, xx, first, x);
+      const double ww = pil_weight_sum(w, count);
+      int* k = axis + 2 * n + static_cast<size_t>(i) * ji.pitch;
+      for (int x = 0; x < count; ++x) k[x] = pil_fixed(w[x], ww);
+    }
+    axis[i] = first;  // (samples beyond the window: empty entries, so that tiles copy whole rows)
+    axis[n + i] = count;
   }
 }
 
 template <int TAPS, int ROWS, bool GEN>
 struct TileSmem {
-  int kh[kTile][TAPS + 1];  // (+1: odd row pitch, thread = column reads are conflict-free)
-  int kv[kTile][TAPS + 1];
-  int h_first[kTile], h_count[kTile], v_first[kTile], v_count[kTile];
+  static constexpr int kPitch = TAPS + 1;  // odd row pitch: thread = column reads are conflict-free
+  alignas(16) int kh[kTile][TAPS + 1];
+  alignas(16) int kv[kTile][TAPS + 1];
+  alignas(16) int h_first[kTile];
+  alignas(16) int h_count[kTile];
+  alignas(16) int v_first[kTile];
+  alignas(16) int v_count[kTile];
   int work_job, work_tile;
+  alignas(16) act_t lut[768];  // ToTensor + Normalize table (matrix output only)
   double ww[GEN ? 2 * kTile : 1];
   union {
     double w[GEN ? 2 * kTile : 1][GEN ? kMaxTaps : 1];  // raw filter weights (per-tile generation: BIG jobs without a table)
@@ -411,22 +459,28 @@ struct TileSmem {
 using FastSmem = TileSmem<kFastTaps, kFastRows, false>;
 using BigSmem = TileSmem<kMaxTaps, kMaxRows, true>;
 
-// The tile's 32 + 32 table entries -> shared memory.  (ox0, oy0): tile origin relative to the window.
+// The tile's 32 + 32 table rows -> shared memory, as 16-byte copies (the table has the shared arrays' layout).
+// (tx, ty): tile coordinates inside the window.
 template <class SM>
-__device__ __forceinline__ void tile_load_tables(SM& sm, const int* __restrict__ tj, int entry, int win_w, int ox0,
-                                                 int oy0, int tw, int th) {
-  const int* eh = tj + static_cast<size_t>(ox0) * entry;
-  const int* ev = tj + static_cast<size_t>(win_w + oy0) * entry;
-  const int per_axis = kTile * entry;
-  for (int idx = threadIdx.x; idx < 2 * per_axis; idx += blockDim.x) {
-    const bool is_h = idx < per_axis;
-    const int k = is_h ? idx : idx - per_axis;
-    const int e = k / entry, f = k - e * entry;
-    if (e >= (is_h ? tw : th)) continue;
-    const int v = __ldg((is_h ? eh : ev) + k);
-    if (f == 0) (is_h ? sm.h_first : sm.v_first)[e] = v;
-    else if (f == 1) (is_h ? sm.h_count : sm.v_count)[e] = v;
-    else (is_h ? sm.kh : sm.kv)[e][f - 2] = v;
+__device__ __forceinline__ void tile_load_tables(SM& sm, const int* __restrict__ tj, int win_w, int win_h, int tx, int ty) {
+  constexpr int P = SM::kPitch;
+  constexpr int kK4 = kTile * P / 4;  // 16-byte pieces of one axis' taps
+  const int n_h = (win_w + kTile - 1) / kTile * kTile, n_v = (win_h + kTile - 1) / kTile * kTile;
+  const int* ah = tj;
+  const int* av = tj + n_h * (2 + P);
+  const int4* k_h = reinterpret_cast<const int4*>(ah + 2 * n_h + tx * kTile * P);
+  const int4* k_v = reinterpret_cast<const int4*>(av + 2 * n_v + ty * kTile * P);
+  int4* s_kh = reinterpret_cast<int4*>(&sm.kh[0][0]);
+  int4* s_kv = reinterpret_cast<int4*>(&sm.kv[0][0]);
+  for (int i = threadIdx.x; i < kK4; i += blockDim.x) {
+    s_kh[i] = __ldg(k_h + i);
+    s_kv[i] = __ldg(k_v + i);
+  }
+  if (threadIdx.x < 4 * (kTile / 4)) {  // first / count of both axes: four rows of 32 ints
+    const int a = threadIdx.x / (kTile / 4), o = threadIdx.x % (kTile / 4);
+    const int* g = a == 0 ? ah + tx * kTile : a == 1 ? ah + n_h + tx * kTile : a == 2 ? av + ty * kTile : av + n_v + ty * kTile;
+    int* d = a == 0 ? sm.h_first : a == 1 ? sm.h_count : a == 2 ? sm.v_first : sm.v_count;
+    reinterpret_cast<int4*>(d)[o] = __ldg(reinterpret_cast<const int4*>(g) + o);
   }
 }
 
@@ -453,28 +507,82 @@ __device__ __forceinline__ bool tile_footprint(const SM& sm, const oake_resize_j
   return fp->rv0 < fp->rv1 && x_hi > 0 && x_lo < job.src_w;
 }
 
-template <class SM>
-__device__ __forceinline__ void tile_zero(const oake_resize_job& job, uint8_t* __restrict__ dst_arena, int ox0, int oy0,
-                                          int tw, int th) {
-  uint8_t* dst = dst_arena + job.dst_off;
+// Output of one thread's column `ox` of the window.  MODE 0: uint8 HWC at the job's dst_off.  MODE 1 / 2: the T50 /
+// T197 front-end matrix (ResizeOut): the column part of the address is fixed per thread, a row adds a 32-bit offset,
+// and the ToTensor + Normalize table sits in shared memory.
+template <int MODE>
+struct PixelSink {
+  static constexpr int kShift = MODE == 2 ? 4 : 5, kPad = MODE == 2 ? kBlkPad : 0, kGrid = MODE == 2 ? kBlkGrid : 7;
+  static constexpr int kCs = 1 << (2 * kShift);  // channel stride inside a matrix row
+  uint8_t* u8;
+  long long pitch3;
+  act_t* col;
+  const act_t* lut;
+  __device__ __forceinline__ PixelSink(const oake_resize_job& job, uint8_t* __restrict__ dst_arena, const ResizeOut& out, int jb,
+                                       int ox, const act_t* s_lut) {
+    if (MODE == 0) {
+      u8 = dst_arena + job.dst_off + static_cast<long long>(ox) * 3;
+      pitch3 = static_cast<long long>(job.dst_pitch_px) * 3;
+    } else {
+      const int px = ox + kPad;
+      col = out.matrix + (static_cast<size_t>(out.crop0 + jb) * kGrid * kGrid + (px >> kShift)) * 3 * kCs + (px & ((1 << kShift) - 1));
+      lut = s_lut;
+    }
+  }
+  __device__ __forceinline__ void put(int oy, int v0, int v1, int v2) const {
+    if (MODE == 0) {
+      uint8_t* o = u8 + oy * pitch3;
+      o[0] = static_cast<uint8_t>(v0);
+      o[1] = static_cast<uint8_t>(v1);
+      o[2] = static_cast<uint8_t>(v2);
+    } else {
+      const int py = oy + kPad;
+      act_t* o = col + ((py >> kShift) * (kGrid * 3 * kCs) + ((py & ((1 << kShift) - 1)) << kShift));
+      o[0] = lut[v0];
+      o[kCs] = lut[256 + v1];
+      o[2 * kCs] = lut[512 + v2];
+    }
+  }
+};
+
+// (matrix output) the table -> shared memory; the caller's next barrier publishes it
+template <int MODE, class SM>
+__device__ __forceinline__ void tile_load_lut(SM& sm, const ResizeOut& out) {
+  if (MODE != 0 && threadIdx.x < 768 / 8)
+    reinterpret_cast<uint4*>(sm.lut)[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(out.lut) + threadIdx.x);
+}
+
+template <int MODE, class SM>
+__device__ __forceinline__ void tile_zero(const SM& sm, const oake_resize_job& job, uint8_t* __restrict__ dst_arena,
+                                          const ResizeOut& out, int jb, int ox0, int oy0, int tw, int th) {
   const int j = threadIdx.x & (kTile - 1);
-  for (int r = threadIdx.x / kTile; r < th && j < tw; r += blockDim.x / kTile) {
-    uint8_t* o = dst + (static_cast<long long>(oy0 + r) * job.dst_pitch_px + ox0 + j) * 3;
-    o[0] = 0;
-    o[1] = 0;
-    o[2] = 0;
+  if (MODE != 0) __syncthreads();  // the table (block-uniform path: every thread of the CTA is here)
+  if (j >= tw) return;
+  const PixelSink<MODE> sink(job, dst_arena, out, jb, ox0 + j, sm.lut);
+  for (int r = threadIdx.x / kTile; r < th; r += blockDim.x / kTile) sink.put(oy0 + r, 0, 0, 0);
+}
+
+// N taps of one output sample, three channels: `px` advances by `step` bytes per tap.
+template <int N>
+__device__ __forceinline__ void taps_fixed(const int* __restrict__ k, const uint8_t* __restrict__ px, int step, int& s0, int& s1,
+                                           int& s2) {
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    const int kk = k[t];
+    s0 += static_cast<int>(px[t * step + 0]) * kk;
+    s1 += static_cast<int>(px[t * step + 1]) * kk;
+    s2 += static_cast<int>(px[t * step + 2]) * kk;
   }
 }
 
 // Horizontal pass (crop rows y_lo + [rv0, rv1) -> tmp, uint8 like Pillow's intermediate image), barrier, vertical
 // pass.  One thread per (row, output column): the three channels share the tap loop, and the taps that fall outside
 // the source image are cut off once, outside the loop.
-template <class SM>
+template <int MODE, class SM>
 __device__ __forceinline__ void tile_pixels(SM& sm, const oake_resize_job& job, const uint8_t* __restrict__ src_arena,
-                                            uint8_t* __restrict__ dst_arena, int ox0, int oy0, int tw, int th,
-                                            const Footprint& fp) {
+                                            uint8_t* __restrict__ dst_arena, const ResizeOut& out, int jb, int ox0, int oy0,
+                                            int tw, int th, const Footprint& fp) {
   const uint8_t* src = src_arena + job.src_off;
-  uint8_t* dst = dst_arena + job.dst_off;
   const int tid = threadIdx.x;
   const int j = tid & (kTile - 1);  // output column of the tile; rows go tid / 32, + 8, + 16, ...
   if (j < tw) {
@@ -482,9 +590,11 @@ __device__ __forceinline__ void tile_pixels(SM& sm, const oake_resize_job& job, 
     const int t0 = max(0, -first);
     const int t1 = min(sm.h_count[j], job.src_w - first);
     const int* k = sm.kh[j];
-    for (int r = fp.rv0 + tid / kTile; r < fp.rv1; r += blockDim.x / kTile) {
+    const long long row_bytes = static_cast<long long>(job.src_pitch_px) * 3;
+    const uint8_t* px_row = src + static_cast<long long>(fp.y_lo + fp.rv0 + tid / kTile) * row_bytes + (first + t0) * 3;
+    for (int r = fp.rv0 + tid / kTile; r < fp.rv1; r += 256 / kTile, px_row += (256 / kTile) * row_bytes) {
       int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
-      const uint8_t* px = src + (static_cast<long long>(fp.y_lo + r) * job.src_pitch_px + first + t0) * 3;
+      const uint8_t* px = px_row;
 #pragma unroll 4
       for (int t = t0; t < t1; ++t, px += 3) {
         const int kk = k[t];
@@ -499,35 +609,46 @@ __device__ __forceinline__ void tile_pixels(SM& sm, const oake_resize_job& job, 
     }
   }
   __syncthreads();
-  for (int r = tid / kTile; r < th && j < tw; r += blockDim.x / kTile) {
+  if (j >= tw) return;
+  const PixelSink<MODE> sink(job, dst_arena, out, jb, ox0 + j, sm.lut);
+  for (int r = tid / kTile; r < th; r += 256 / kTile) {
     const int first = sm.v_first[r] - fp.r_lo;
     const int t0 = max(0, fp.rv0 - first);
     const int t1 = min(sm.v_count[r], fp.rv1 - first);
-    const int* k = sm.kv[r];
+    const int* k = sm.kv[r] + t0;
     const uint8_t* px = sm.tmp[first + t0][j];
     int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
+    // a warp shares its row, hence the tap count: the common counts run without loop or remainder code
+    switch (t1 - t0) {
+      case 4: taps_fixed<4>(k, px, kTile * 3, s0, s1, s2); break;
+      case 5: taps_fixed<5>(k, px, kTile * 3, s0, s1, s2); break;
+      case 6: taps_fixed<6>(k, px, kTile * 3, s0, s1, s2); break;
+      case 7: taps_fixed<7>(k, px, kTile * 3, s0, s1, s2); break;
+      case 8: taps_fixed<8>(k, px, kTile * 3, s0, s1, s2); break;
+      case 9: taps_fixed<9>(k, px, kTile * 3, s0, s1, s2); break;
+      default:
 #pragma unroll 4
-    for (int t = t0; t < t1; ++t, px += kTile * 3) {
-      const int kk = k[t];
-      s0 += static_cast<int>(px[0]) * kk;
-      s1 += static_cast<int>(px[1]) * kk;
-      s2 += static_cast<int>(px[2]) * kk;
+        for (int t = t0; t < t1; ++t, px += kTile * 3, ++k) {
+          const int kk = k[0];
+          s0 += static_cast<int>(px[0]) * kk;
+          s1 += static_cast<int>(px[1]) * kk;
+          s2 += static_cast<int>(px[2]) * kk;
+        }
     }
-    uint8_t* o = dst + (static_cast<long long>(oy0 + r) * job.dst_pitch_px + ox0 + j) * 3;
-    o[0] = pil_clip8(s0);
-    o[1] = pil_clip8(s1);
-    o[2] = pil_clip8(s2);
+    sink.put(oy0 + r, pil_clip8(s0), pil_clip8(s1), pil_clip8(s2));
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(256)
 resize_fast_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ dst_arena,
                    const oake_resize_job* __restrict__ jobs, const ResizeJobInfo* __restrict__ info,
-                   const int* __restrict__ tab, int* __restrict__ err) {
+                   const int* __restrict__ tab, int* __restrict__ err, ResizeOut out) {
   __shared__ FastSmem sm;
-  const ResizeJobInfo ji = info[blockIdx.y];
-  if (ji.cls != 0) return;
-  const oake_resize_job job = jobs[blockIdx.y];
+  const int jb = blockIdx.y;
+  const ResizeJobInfo ji = info[jb];
+  if (ji.cls != 0 || ji.pad != 0) return;
+  const oake_resize_job job = jobs[jb];
   const int tiles_x = (job.win_w + kTile - 1) / kTile;
   const int tiles_y = (job.win_h + kTile - 1) / kTile;
   if (static_cast<int>(blockIdx.x) >= tiles_x * tiles_y) return;
@@ -535,14 +656,15 @@ resize_fast_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ 
   const int ox0 = tx * kTile, oy0 = ty * kTile;  // relative to the window
   const int tw = min(kTile, job.win_w - ox0);
   const int th = min(kTile, job.win_h - oy0);
-  tile_load_tables(sm, tab + ji.tab_off, ji.entry, job.win_w, ox0, oy0, tw, th);
+  tile_load_tables(sm, tab + ji.tab_off, job.win_w, job.win_h, tx, ty);
+  tile_load_lut<MODE>(sm, out);
   __syncthreads();
   Footprint fp;
   if (!tile_footprint(sm, job, tw, th, kFastRows, err, &fp)) {
-    tile_zero<FastSmem>(job, dst_arena, ox0, oy0, tw, th);
+    tile_zero<MODE>(sm, job, dst_arena, out, jb, ox0, oy0, tw, th);
     return;
   }
-  tile_pixels(sm, job, src_arena, dst_arena, ox0, oy0, tw, th, fp);
+  tile_pixels<MODE>(sm, job, src_arena, dst_arena, out, jb, ox0, oy0, tw, th, fp);
 }
 
 // Per-tile coefficient generation (BIG jobs without a table): the CTA shares the work -- pil_bounds one thread per
@@ -585,14 +707,16 @@ __device__ __forceinline__ void tile_generate(BigSmem& sm, const oake_resize_job
 }
 
 // Persistent grid over the (job, tile) pairs of the BIG jobs; nothing to do (and gone at once) when there are none.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 resize_big_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ dst_arena,
                   const oake_resize_job* __restrict__ jobs, ResizeState* __restrict__ state,
                   const ResizeJobInfo* __restrict__ info, const int4* __restrict__ big_list,
-                  const int* __restrict__ tab, int* __restrict__ err) {
+                  const int* __restrict__ tab, int* __restrict__ err, ResizeOut out) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BigSmem& sm = *reinterpret_cast<BigSmem*>(smem_raw);
   const int total = state->big_tiles, n_big = state->n_big;
+  tile_load_lut<MODE>(sm, out);  // (published by the loop's barriers)
   for (;;) {
     __syncthreads();  // the previous tile's shared memory is free
     if (threadIdx.x == 0) sm.work_tile = atomicAdd(&state->next, 1);
@@ -616,18 +740,18 @@ resize_big_kernel(const uint8_t* __restrict__ src_arena, uint8_t* __restrict__ d
     const int ox0 = tx * kTile, oy0 = ty * kTile;
     const int tw = min(kTile, job.win_w - ox0);
     const int th = min(kTile, job.win_h - oy0);
-    if (ji.tab_off >= 0) {
-      tile_load_tables(sm, tab + ji.tab_off, ji.entry, job.win_w, ox0, oy0, tw, th);
+    if (ji.tab_off >= 0 && ji.pitch == BigSmem::kPitch) {
+      tile_load_tables(sm, tab + ji.tab_off, job.win_w, job.win_h, tx, ty);
       __syncthreads();
-    } else {
+    } else {  // the scratch had no room for this job's tables
       tile_generate(sm, job, ox0, oy0, tw, th);
     }
     Footprint fp;
     if (!tile_footprint(sm, job, tw, th, kMaxRows, err, &fp)) {
-      tile_zero<BigSmem>(job, dst_arena, ox0, oy0, tw, th);
+      tile_zero<MODE>(sm, job, dst_arena, out, jb, ox0, oy0, tw, th);
       continue;
     }
-    tile_pixels(sm, job, src_arena, dst_arena, ox0, oy0, tw, th, fp);
+    tile_pixels<MODE>(sm, job, src_arena, dst_arena, out, jb, ox0, oy0, tw, th, fp);
   }
 }
 
@@ -734,11 +858,17 @@ cudaError_t resize_pool(cudaMemPool_t* out) {
 constexpr int kResizeSlice = 8192;  // jobs per pass: bounds the table scratch at 8192 x 48 KB = 403 MB
 }  // namespace
 
-cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs,
-                             int n_jobs, int max_tiles, int* err_flag) {
+namespace {
+cudaError_t launch_resize(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs, int n_jobs,
+                          int max_tiles, int* err_flag, ResizeOut out) {
   if (n_jobs <= 0 || max_tiles <= 0) return cudaSuccess;
-  if (cudaError_t e = ensure_dynamic_smem<resize_big_kernel>(static_cast<int>(sizeof(BigSmem))); e != cudaSuccess)
-    return e;
+  const int mode = out.mode == 0 ? 0 : (out.shift == 5 ? 1 : 2);
+  {
+    cudaError_t e = mode == 0   ? ensure_dynamic_smem<resize_big_kernel<0>>(static_cast<int>(sizeof(BigSmem)))
+                    : mode == 1 ? ensure_dynamic_smem<resize_big_kernel<1>>(static_cast<int>(sizeof(BigSmem)))
+                                : ensure_dynamic_smem<resize_big_kernel<2>>(static_cast<int>(sizeof(BigSmem)));
+    if (e != cudaSuccess) return e;
+  }
   int dev = 0, num_sms = 0;
   if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
   if (cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); e != cudaSuccess) return e;
@@ -761,13 +891,39 @@ cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, 
     const int n = n_jobs - j0 < slice ? n_jobs - j0 : slice;
     err = cudaMemsetAsync(state, 0, sizeof(ResizeState), st);
     if (err != cudaSuccess) break;
-    resize_prepare_kernel<<<n, 256, 0, st>>>(jobs + j0, n, state, info, big_list, tab);
-    resize_fast_kernel<<<dim3(max_tiles, n), 256, 0, st>>>(src, dst, jobs + j0, info, tab, err_flag);
-    resize_big_kernel<<<4 * num_sms, 256, sizeof(BigSmem), st>>>(src, dst, jobs + j0, state, info, big_list, tab, err_flag);
+    ResizeOut o = out;
+    o.crop0 = out.crop0 + j0;
+    resize_prepare_kernel<<<n, 256, 0, st>>>(jobs + j0, n, state, info, big_list, tab, err_flag, o);
+    const dim3 fg(max_tiles, n);
+    const int bg = 4 * num_sms;
+    const size_t bs = sizeof(BigSmem);
+    if (mode == 0) {
+      resize_fast_kernel<0><<<fg, 256, 0, st>>>(src, dst, jobs + j0, info, tab, err_flag, o);
+      resize_big_kernel<0><<<bg, 256, bs, st>>>(src, dst, jobs + j0, state, info, big_list, tab, err_flag, o);
+    } else if (mode == 1) {
+      resize_fast_kernel<1><<<fg, 256, 0, st>>>(src, dst, jobs + j0, info, tab, err_flag, o);
+      resize_big_kernel<1><<<bg, 256, bs, st>>>(src, dst, jobs + j0, state, info, big_list, tab, err_flag, o);
+    } else {
+      resize_fast_kernel<2><<<fg, 256, 0, st>>>(src, dst, jobs + j0, info, tab, err_flag, o);
+      resize_big_kernel<2><<<bg, 256, bs, st>>>(src, dst, jobs + j0, state, info, big_list, tab, err_flag, o);
+    }
     err = cudaGetLastError();
   }
   const cudaError_t e2 = cudaFreeAsync(scratch, st);
   return err != cudaSuccess ? err : e2;
+}
+}  // namespace
+
+cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs,
+                             int n_jobs, int max_tiles, int* err_flag) {
+  return launch_resize(st, src, dst, jobs, n_jobs, max_tiles, err_flag, ResizeOut{0, nullptr, nullptr, 0, 0, 0, 0});
+}
+
+cudaError_t launch_resize_to_matrix(cudaStream_t st, const uint8_t* src, const oake_resize_job* jobs, int n_jobs,
+                                    int* err_flag, const act_t* lut, act_t* matrix, int blocks16) {
+  // every job's window must be the whole 224 x 224 crop (checked by the prepare kernel: err_flag)
+  return launch_resize(st, src, nullptr, jobs, n_jobs, 49, err_flag,
+                       blocks16 ? ResizeOut{1, matrix, lut, 4, kBlkPad, kBlkGrid, 0} : ResizeOut{1, matrix, lut, 5, 0, 7, 0});
 }
 
 cudaError_t launch_object_masks(cudaStream_t st, const float* fg, const float* box, float* masks, int B,

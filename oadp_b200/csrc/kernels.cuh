@@ -111,6 +111,11 @@ cudaError_t launch_conv1_regroup(cudaStream_t st, const act_t* w, act_t* out, in
 // Pillow-exact crop + antialiased bicubic resize, one job per (source rectangle -> output window).
 cudaError_t launch_resize_u8(cudaStream_t st, const uint8_t* src, uint8_t* dst, const oake_resize_job* jobs,
                              int n_jobs, int max_tiles, int* err_flag);
+// The same resize with the pixels written straight into the tower's front-end matrix (act_t, through the
+// ToTensor + Normalize table): job i = crop i, windows must be whole 224 x 224 crops.  blocks16 = 0: conv1's im2col
+// [n*49, 3072] (T50); 1: the block matrix [n*225, 768] of the objects tower, zero border included.
+cudaError_t launch_resize_to_matrix(cudaStream_t st, const uint8_t* src, const oake_resize_job* jobs, int n_jobs,
+                                    int* err_flag, const act_t* lut, act_t* matrix, int blocks16);
 cudaError_t launch_object_masks(cudaStream_t st, const float* fg, const float* box, float* masks, int B,
                                 int grid);
 int resize_max_taps();

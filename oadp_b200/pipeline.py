@@ -15,6 +15,8 @@ Results per image have exactly the reference's layouts:
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import functools
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -35,6 +37,8 @@ def _align(v: int, a: int = 256) -> int:
 
 _STAGE_POOL = None
 _STAGE_WORKERS = 8
+# OAKE_FUSED_FRONTEND=0: resize into uint8 crops + a separate matrix kernel, as before (A/B measurements)
+_FUSED_FRONTEND = os.environ.get('OAKE_FUSED_FRONTEND', '1') != '0'
 
 
 def _stage_pool():
@@ -302,7 +306,12 @@ class OakePipeline:
             copy_range(0)
         jpeg_job = self._stage_jpeg(compressed, fresh) if compressed else None
         self._slot.jpeg_count = len(compressed)
-        return dict(n=n, variant=variant, img_bytes=img_bytes, meta_host_bytes=meta_host_bytes, jpeg=jpeg_job,
+        # crops that are exactly the outputs of one resize stage (globals, objects) never exist as uint8: the resize
+        # kernel writes the tower's front-end matrix itself, chunk by chunk (oake_resize_to_patches)
+        fused = (_FUSED_FRONTEND and len(stages) == 1 and n > 0 and stages[0].size == n
+                 and bool((stages[0]['win_w'] == frontend.SIZE).all() and (stages[0]['win_h'] == frontend.SIZE).all())
+                 and np.array_equal(stages[0]['dst_off'], crops['off']))
+        return dict(n=n, variant=variant, img_bytes=img_bytes, meta_host_bytes=meta_host_bytes, jpeg=jpeg_job, fused=fused,
                     raw_images=len(images) - len(compressed), raw_ranges=raw_ranges if compressed else None,
                     stages=[(j.size, frontend.max_tiles(j), o) for j, o in zip(stages, stage_offs)],
                     crops_off=crops_off, fg_off=fg_off, box_off=box_off, masks_off=masks_off)
@@ -401,8 +410,9 @@ class OakePipeline:
             b.record()
             self.frontend_events.append((name, a, b))
 
+        fused = job.get('fused', False)
         for count, tiles, o in job['stages']:
-            if count:
+            if count and not fused:
                 timed('resize_u8', lambda: binding.check(self.lib.oake_resize_u8(
                     arena_ptr, arena_ptr, meta_ptr + o, count, tiles, self._err.data_ptr(), st)))
                 self.frontend_launches += 1
@@ -418,6 +428,16 @@ class OakePipeline:
             ws = self.engine._workspace(min(n, step), variant)
             for s in range(0, n, step):
                 b = min(step, n - s)
+                if fused:
+                    jobs_ptr = meta_ptr + job['stages'][0][2] + s * frontend.RESIZE_JOB.itemsize
+                    timed('resize_u8', lambda: binding.check(self.lib.oake_resize_to_patches(
+                        self.engine._handle, arena_ptr, jobs_ptr, b, variant, ws.data_ptr(), ws.numel(),
+                        self._err.data_ptr(), st)))
+                    self.frontend_launches += 3
+                    binding.check(self.lib.oake_encode_patches(
+                        self.engine._handle, b, variant, (masks_ptr + s * 196 * 4) if masks_ptr else None,
+                        out[s:].data_ptr(), None, ws.data_ptr(), ws.numel(), st))
+                    continue
                 binding.check(self.lib.oake_encode_crops_u8(
                     self.engine._handle, arena_ptr, meta_ptr + job['crops_off'] + s * frontend.CROP_SRC.itemsize, b,
                     variant, (masks_ptr + s * 196 * 4) if masks_ptr else None, out[s:].data_ptr(), None,

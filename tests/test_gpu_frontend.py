@@ -134,3 +134,21 @@ def test_pipeline_objects(pipe):
     dry = pipe.encode_objects(imgs, props, dry_run=True)
     assert all(d['embeddings'].shape[0] <= 5 for d in dry)
     assert torch.equal(dry[0]['embeddings'], got[0]['embeddings'][:dry[0]['embeddings'].shape[0]])
+
+
+def test_fused_front_end_is_the_unfused_one(pipe, monkeypatch):
+    """oake_resize_to_patches (pixels straight into the tower's front-end matrix, zero border included) must give the
+    embeddings of the two-step path (uint8 crops, then the matrix kernel) bit for bit: same table, same rounding."""
+    from oadp_b200 import pipeline as pl
+    imgs = synth.images(3, seed=4)
+    props = [synth.proposals(im.shape[1], im.shape[0], 150, seed=40 + i) for i, im in enumerate(imgs)]
+    props[0][1] = [0.0, 0.0, 640.0, 480.0, 0.9]  # expanded far beyond the image: BIG class, tiles outside the image
+    got = {}
+    for fused in (True, False):
+        monkeypatch.setattr(pl, '_FUSED_FRONTEND', fused)
+        objs = pipe.encode_objects(imgs, props)
+        glob = pipe.encode_globals(imgs)
+        got[fused] = (torch.cat([o['embeddings'] for o in objs]), torch.stack(glob))
+    assert got[True][0].shape[0] > 400
+    assert torch.equal(got[True][0], got[False][0])
+    assert torch.equal(got[True][1], got[False][1])
