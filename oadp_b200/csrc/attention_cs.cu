@@ -52,6 +52,22 @@ __device__ long long g_attn_trace[8 * 32 * 4];
   } while (0)
 #endif
 
+// Two measured-and-rejected variants of the softmax, kept behind build flags (A/B on one box, ms per 11 launches at
+// B = 478: default 2.88-2.90; SUMMMA 2.87-3.03; MAXPIPE 3.07-3.14; both 3.19-3.25 -- tools/gpu_attn_ab.sh):
+// -DOAKE_ATTN_SUMMMA=1: the row sum as one more product of P -- against a 16 x 16 tile of ones, into 16 spare TMEM
+//   columns of the tile, issued behind P V; the drain warp reads it next to O.  Removes one FADD per key from the
+//   softmax warps: no gain, i.e. the exponential phase is not bound by its instruction count.
+// -DOAKE_ATTN_MAXPIPE=1: two score chunks in flight in the row-maximum pass and three-input maxima: slower (the 64
+//   registers of scores in flight push a few values into local memory, which lives in L2 next to 195 KB of shared memory).
+#ifndef OAKE_ATTN_SUMMMA
+#define OAKE_ATTN_SUMMMA 0
+#endif
+#ifndef OAKE_ATTN_MAXPIPE
+#define OAKE_ATTN_MAXPIPE 0
+#endif
+constexpr bool kSumMma = OAKE_ATTN_SUMMMA != 0;
+constexpr bool kMaxPipe = OAKE_ATTN_MAXPIPE != 0;
+
 template <bool SIDE>
 struct CCfg {
   static constexpr int P = 196;
@@ -68,13 +84,15 @@ struct CCfg {
   static constexpr int kStage = 2 * kQTile + 2 * kKV;
   static constexpr int kPHi = kSplit;            // P columns of the upper half start here
   static constexpr int kOCol = kSplit + (NK - kSplit) / 2;  // 152
+  static constexpr int kSumCol = kOCol + 64;                // 216: row sums (P x ones), 16 columns
+  static constexpr int kOnesBytes = 2048;                   // 16 rows x 128 B of fp16 ones: any layout reads ones
   static constexpr int kBufCols = 256;           // TMEM columns per tile
   static constexpr int kMaskFloats = 208;        // staged mask row (196 used), 16-byte granules
   static constexpr int kMaskBytes = 2048;        // both stages' mask rows, padded
   static constexpr int kXchgBytes = 2 * 2 * 2 * 128 * 4;  // partial max + sum: [2][tile][half][row]
   static constexpr int kOutStage = 32 * 128;     // bytes per drain warp: 32 rows x 64 halves
   static constexpr int kNumBars = 16;
-  static constexpr int kSmemBytes = 1024 + 2 * kStage + kMaskBytes + kXchgBytes + 4 * kOutStage + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = 1024 + 2 * kStage + kMaskBytes + kXchgBytes + 4 * kOutStage + kOnesBytes + kNumBars * 8 + 16;
   static constexpr int kSoftmaxWarps = 8;
   static constexpr int kDrainWarp0 = 8;
   static constexpr int kLoaderWarp = 12;
@@ -159,6 +177,7 @@ struct HalfRow {
 
   // partial row maximum in the base-2 domain (scaled, biased)
   __device__ __forceinline__ float pass_max() const {
+    if (kMaxPipe && MODE == kPlain) return pass_max_pipelined();
     float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
@@ -189,6 +208,33 @@ struct HalfRow {
     return mx;
   }
 
+  // kPlain rows: raw maxima (the scale is positive), chunks 0 and 1 requested together, chunk 2 (and the tail)
+  // requested while chunk 1 is reduced
+  __device__ __forceinline__ float pass_max_pipelined() const {
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    auto reduce = [&](const uint32_t (&a)[32]) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], __uint_as_float(a[j]), __uint_as_float(a[j + 1]));
+    };
+    uint32_t ra[32], rb[32], rt[16];
+    tmem_ld_32x32(t_row + k0, ra);
+    tmem_ld_32x32(t_row + k0 + 32, rb);
+    tmem_ld_wait();
+    reduce(ra);
+    tmem_ld_32x32(t_row + k0 + 64, ra);
+    reduce(rb);
+    if (HI) tmem_ld_32x16(t_row + kTail, rt);  // (after chunk 1 is consumed: its registers are free)
+    tmem_ld_wait();
+    reduce(ra);
+    float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    if (HI) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (kTail + j < C::T) mx = fmaxf(mx, __uint_as_float(rt[j]));  // keys 192 .. 196: patches and the class key
+    }
+    return mx * scale;
+  }
+
   // p = exp2(s - max) -> packed fp16 behind the reads; partial row sum of the unrounded values
   __device__ __forceinline__ float pass_exp(float neg_mx) const {
     constexpr int pbase = HI ? C::kPHi : 0;
@@ -212,7 +258,7 @@ struct HalfRow {
             p[e] = ex2_sel(fmaf(__uint_as_float(ra[jj]), scale, neg_mx) + patch_bias(k0 + c * 32 + jj, jj, wa), use_poly(j));
           }
         }
-        s4[j & 3] += p[0] + p[1];
+        if (!kSumMma) s4[j & 3] += p[0] + p[1];
         pa[j] = pack2(p[0], p[1]);
       }
       tmem_st_32x16(t_row + pbase + c * 16, pa);
@@ -231,7 +277,7 @@ struct HalfRow {
           const int jj = 2 * j + e;
           p[e] = kTail + jj <= C::T ? ex2(fmaf(__uint_as_float(rt[jj]), scale, neg_mx) + tail_bias(jj, wt)) : 0.f;
         }
-        s4[j & 3] += p[0] + p[1];
+        if (!kSumMma) s4[j & 3] += p[0] + p[1];
         pt[j] = pack2(p[0], p[1]);
       }
       tmem_st_32x8(t_row + pbase + 48, pt);
@@ -249,7 +295,8 @@ __device__ __forceinline__ void softmax_half(uint32_t t_row, bool is_y, uint32_t
   *xmax_mine = mine;
   pair_sync(q);
   const float mx = fmaxf(mine, *xmax_other);
-  *xsum_mine = h.pass_exp(-mx);
+  const float sum = h.pass_exp(-mx);
+  if (!kSumMma) *xsum_mine = sum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -420,7 +467,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
   float* xmax = reinterpret_cast<float*>(smem + 2 * C::kStage + C::kMaskBytes);  // [tile][half][128]
   float* xsum = xmax + 2 * 2 * 128;                                               // [tile][half][128]
   uint8_t* out_stage = smem + 2 * C::kStage + C::kMaskBytes + C::kXchgBytes;      // [4 drain warps][kOutStage]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + 4 * C::kOutStage);
+  uint8_t* ones = out_stage + 4 * C::kOutStage;  // [kOnesBytes] fp16 1.0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + C::kOnesBytes);
   uint64_t* qk_full = bars + 0;   // [stage]  loader -> MMA
   uint64_t* qk_free = bars + 2;   // [stage]  MMA (S of both tiles retired) -> loader
   uint64_t* v_full = bars + 4;    // [stage]  loader -> MMA, side-row warps (mask row)
@@ -455,6 +503,10 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_ptr);
+  if (kSumMma) {
+    for (int i = threadIdx.x; i < C::kOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3C003C00u;
+    fence_proxy_async();  // generic-proxy writes -> tensor core reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -536,6 +588,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
                          make_smem_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
       umma_commit_warp(&s_full[t]);
     };
+    constexpr uint32_t idesc_sum = make_idesc_f16(128, 16);
+    const uint64_t ones_desc = make_smem_desc_k_sw128(smem_u32(ones));
     auto issue_pv = [&](int n, int t) {
       const uint32_t v_addr = smem_base + (n & 1) * C::kStage + 2 * C::kQTile + C::kKV;
       const uint32_t buf = tmem_u + t * C::kBufCols;
@@ -543,6 +597,13 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
       for (int k = 0; k < C::kUnits; ++k) {
         const uint32_t p_col = k * 16 < C::kSplit ? k * 8 : C::kPHi + (k - C::kSplit / 16) * 8;
         umma_f16_ts_warp(buf + C::kOCol, buf + p_col, make_smem_desc_mn_sw128(v_addr + k * 2048), idesc_o, k != 0 ? 1u : 0u);
+      }
+      if (kSumMma) {  // row sums = P x ones (every k-step reads the same tile of ones)
+#pragma unroll
+        for (int k = 0; k < C::kUnits; ++k) {
+          const uint32_t p_col = k * 16 < C::kSplit ? k * 8 : C::kPHi + (k - C::kSplit / 16) * 8;
+          umma_f16_ts_warp(buf + C::kSumCol, buf + p_col, ones_desc, idesc_sum, k != 0 ? 1u : 0u);
+        }
       }
       umma_commit_warp(&o_full[t]);
     };
@@ -722,15 +783,20 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
           if (lane == 0) mbar_arrive(&p_ready[t]);
         } else {
           if (warp_live) {
-            mbar_wait(&p_ready[t], n & 1);  // all eight softmax warps done: the row sums are in place
-            const float sum = xs[0] + xs[128];
+            float sum = 0.f;
+            if (!kSumMma) {
+              mbar_wait(&p_ready[t], n & 1);  // all eight softmax warps done: the row sums are in place
+              sum = xs[0] + xs[128];
+            }
             mbar_wait(&o_full[t], n & 1);
             OAKE_TRACE(warp == 8 ? 2 : 7, 2 * n + t, 0);  // drain: o_full seen
             tc_fence_after();
-            uint32_t o0[32], o1[32];
+            uint32_t o0[32], o1[32], osum = 0u;
             tmem_ld_32x32(t_row + C::kOCol, o0);
             tmem_ld_32x32(t_row + C::kOCol + 32, o1);
+            if (kSumMma) tmem_ld_32x1(t_row + C::kSumCol, osum);
             tmem_ld_wait();
+            if (kSumMma) sum = __uint_as_float(osum);
             // the accumulator is in registers: the tile's TMEM goes back to the tensor core before
             // the scaling and the global stores
             tc_fence_before();

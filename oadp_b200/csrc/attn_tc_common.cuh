@@ -33,7 +33,8 @@ __device__ __forceinline__ float ex2_poly(float x) {
   float p = fmaf(0.055171605f, f, 0.24261111f);
   p = fmaf(p, f, 0.69326097f);
   p = fmaf(p, f, 0.99992806f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+  // n into the exponent field: p_bits + (t_bits << 23) as one integer multiply-add (the low 23 bits of t hold n)
+  return __int_as_float(__float_as_int(t) * 0x800000 + __float_as_int(p));
 }
 // pair index j of a 32-key chunk -> which pipe
 __device__ __forceinline__ constexpr bool use_poly(int j) { return kPolyEvery > 0 && (j % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1; }
@@ -71,6 +72,9 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
