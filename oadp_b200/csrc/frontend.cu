@@ -317,6 +317,9 @@ __device__ __forceinline__ uint8_t pil_clip8(int ss) {
 // Both kernels compute only the part of a tile's source footprint that lies inside the image: PIL `crop` pads with
 // zeros, a zero row / column of the intermediate image adds exactly 0 to every sum, and a tile that misses the
 // image altogether is written as zeros at once.
+#ifndef OAKE_RESIZE_HFIXED
+#define OAKE_RESIZE_HFIXED 1  // 0: the horizontal pass always takes the general tap loop (A/B builds)
+#endif
 constexpr int kFastTaps = 16;
 constexpr int kFastRows = 128;             // 31 * 3.5 + 2 * 7 + 2 source rows under one 32-row tile
 constexpr int kJobTabInts = 12288;         // scratch budget per job (48 KB); a 224 x 224 FAST window needs 8064 ints
@@ -585,27 +588,57 @@ __device__ __forceinline__ void tile_pixels(SM& sm, const oake_resize_job& job, 
   const uint8_t* src = src_arena + job.src_off;
   const int tid = threadIdx.x;
   const int j = tid & (kTile - 1);  // output column of the tile; rows go tid / 32, + 8, + 16, ...
-  if (j < tw) {
-    const int first = job.box_x0 + sm.h_first[j];
-    const int t0 = max(0, -first);
-    const int t1 = min(sm.h_count[j], job.src_w - first);
-    const int* k = sm.kh[j];
+  {
+    const bool live = j < tw;
+    const int first = live ? job.box_x0 + sm.h_first[j] : 0;
+    const int t0 = live ? max(0, -first) : 0;
+    const int t1 = live ? min(sm.h_count[j], job.src_w - first) : 0;
+    const int* k = sm.kh[live ? j : 0];
     const long long row_bytes = static_cast<long long>(job.src_pitch_px) * 3;
     const uint8_t* px_row = src + static_cast<long long>(fp.y_lo + fp.rv0 + tid / kTile) * row_bytes + (first + t0) * 3;
-    for (int r = fp.rv0 + tid / kTile; r < fp.rv1; r += 256 / kTile, px_row += (256 / kTile) * row_bytes) {
-      int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
-      const uint8_t* px = px_row;
-#pragma unroll 4
-      for (int t = t0; t < t1; ++t, px += 3) {
-        const int kk = k[t];
-        s0 += static_cast<int>(px[0]) * kk;
-        s1 += static_cast<int>(px[1]) * kk;
-        s2 += static_cast<int>(px[2]) * kk;
+    // A warp = the 32 columns of one row.  When no column of the tile is clipped by the image's left / right edge, every
+    // lane runs the warp's widest tap count N with its coefficients in registers (zero weights beyond its own count;
+    // first + N stays inside the source row): no loop, no remainder, no shared-memory reads per row.
+    const int nmax = __reduce_max_sync(0xffffffffu, t1 - t0);
+    const bool fixed = OAKE_RESIZE_HFIXED && __all_sync(0xffffffffu, !live || (t0 == 0 && t1 == sm.h_count[j] && first + nmax <= job.src_w)) &&
+                       nmax >= 4 && nmax <= 9;
+    if (fixed) {
+      int kr[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) kr[t] = t < t1 ? k[t] : 0;  // (t0 == 0: the lane's own taps, zero weights beyond)
+      if (live) {
+        for (int r = fp.rv0 + tid / kTile; r < fp.rv1; r += 256 / kTile, px_row += (256 / kTile) * row_bytes) {
+          int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
+          switch (nmax) {
+            case 4: taps_fixed<4>(kr, px_row, 3, s0, s1, s2); break;
+            case 5: taps_fixed<5>(kr, px_row, 3, s0, s1, s2); break;
+            case 6: taps_fixed<6>(kr, px_row, 3, s0, s1, s2); break;
+            case 7: taps_fixed<7>(kr, px_row, 3, s0, s1, s2); break;
+            case 8: taps_fixed<8>(kr, px_row, 3, s0, s1, s2); break;
+            default: taps_fixed<9>(kr, px_row, 3, s0, s1, s2); break;
+          }
+          uint8_t* o = sm.tmp[r][j];
+          o[0] = pil_clip8(s0);
+          o[1] = pil_clip8(s1);
+          o[2] = pil_clip8(s2);
+        }
       }
-      uint8_t* o = sm.tmp[r][j];
-      o[0] = pil_clip8(s0);
-      o[1] = pil_clip8(s1);
-      o[2] = pil_clip8(s2);
+    } else if (live) {
+      for (int r = fp.rv0 + tid / kTile; r < fp.rv1; r += 256 / kTile, px_row += (256 / kTile) * row_bytes) {
+        int s0 = 1 << (kPrecBits - 1), s1 = s0, s2 = s0;
+        const uint8_t* px = px_row;
+#pragma unroll 4
+        for (int t = t0; t < t1; ++t, px += 3) {
+          const int kk = k[t];
+          s0 += static_cast<int>(px[0]) * kk;
+          s1 += static_cast<int>(px[1]) * kk;
+          s2 += static_cast<int>(px[2]) * kk;
+        }
+        uint8_t* o = sm.tmp[r][j];
+        o[0] = pil_clip8(s0);
+        o[1] = pil_clip8(s1);
+        o[2] = pil_clip8(s2);
+      }
     }
   }
   __syncthreads();
