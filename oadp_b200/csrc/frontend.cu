@@ -13,6 +13,9 @@
 //  * im2col_pixels: the same patch matrix from (B,3,224,224) fp32 crops that were preprocessed on
 //    the host, i.e. the tensor the reference hands to `encode_image` / `visual`.
 //  * object_masks: the 14x14 foreground masks of objects.py:129-155.
+#include <stdlib.h>
+
+#include <algorithm>
 #include <mutex>
 
 #include "../../include/oake_b200.h"
@@ -382,7 +385,7 @@ resize_prepare_kernel(const oake_resize_job* __restrict__ jobs, int n_jobs, Resi
     if (kmax <= kMaxTaps) {
       const int n_h = (job.win_w + kTile - 1) / kTile * kTile, n_v = (job.win_h + kTile - 1) / kTile * kTile;
       const long long need = static_cast<long long>(n_h + n_v) * (2 + ji.pitch);
-      const long long cap = static_cast<long long>(n_jobs) * kJobTabInts + kTabSlackInts;
+      const long long cap = n_jobs > 0 ? static_cast<long long>(n_jobs) * kJobTabInts + kTabSlackInts : 0;  // (0: test hook)
       if (need <= cap) {
         const int off = atomicAdd(&state->tab_used, static_cast<int>(need));
         if (off + need <= cap) ji.tab_off = off;
@@ -889,6 +892,12 @@ cudaError_t resize_pool(cudaMemPool_t* out) {
   return cudaSuccess;
 }
 constexpr int kResizeSlice = 8192;  // jobs per pass: bounds the table scratch at 8192 x 48 KB = 403 MB
+// Test hooks (tests/test_gpu_frontend.py): $OAKE_RESIZE_SLICE = jobs per pass, $OAKE_RESIZE_NO_TABLES=1 = no room for
+// any table, i.e. every job takes the per-tile coefficient generation of the BIG kernel.
+int env_int(const char* name, int fallback) {
+  const char* e = getenv(name);
+  return (e != nullptr && e[0] != 0) ? atoi(e) : fallback;
+}
 }  // namespace
 
 namespace {
@@ -907,7 +916,9 @@ cudaError_t launch_resize(cudaStream_t st, const uint8_t* src, uint8_t* dst, con
   if (cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); e != cudaSuccess) return e;
   cudaMemPool_t pool;
   if (cudaError_t e = resize_pool(&pool); e != cudaSuccess) return e;
-  const int slice = n_jobs < kResizeSlice ? n_jobs : kResizeSlice;
+  const int max_slice = std::max(1, env_int("OAKE_RESIZE_SLICE", kResizeSlice));
+  const bool no_tables = env_int("OAKE_RESIZE_NO_TABLES", 0) != 0;
+  const int slice = n_jobs < max_slice ? n_jobs : max_slice;
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t off_info = 256;
   const size_t off_list = off_info + up(static_cast<size_t>(slice) * sizeof(ResizeJobInfo));
@@ -926,7 +937,7 @@ cudaError_t launch_resize(cudaStream_t st, const uint8_t* src, uint8_t* dst, con
     if (err != cudaSuccess) break;
     ResizeOut o = out;
     o.crop0 = out.crop0 + j0;
-    resize_prepare_kernel<<<n, 256, 0, st>>>(jobs + j0, n, state, info, big_list, tab, err_flag, o);
+    resize_prepare_kernel<<<n, 256, 0, st>>>(jobs + j0, no_tables ? 0 : n, state, info, big_list, tab, err_flag, o);
     const dim3 fg(max_tiles, n);
     const int bg = 4 * num_sms;
     const size_t bs = sizeof(BigSmem);

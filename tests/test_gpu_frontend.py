@@ -152,3 +152,21 @@ def test_fused_front_end_is_the_unfused_one(pipe, monkeypatch):
     assert got[True][0].shape[0] > 400
     assert torch.equal(got[True][0], got[False][0])
     assert torch.equal(got[True][1], got[False][1])
+
+
+def test_resize_paths_agree(pipe, monkeypatch):
+    """The three ways a crop can travel through oake_resize_u8 give the same bytes: per-job coefficient tables (FAST and
+    BIG classes), per-tile generation when the scratch has no room for tables, and passes of a few jobs at a time."""
+    w, h = 640, 480
+    arr = synth.image(w, h, 33)
+    props = synth.proposals(w, h, 90, seed=8)
+    props[1] = [0.0, 0.0, 640.0, 480.0, 0.9]   # BIG class (scale ~7), mostly outside the image
+    props[2] = [100.0, 50.0, 600.0, 470.0, 0.9]  # BIG class, mostly inside
+    plan = frontend.objects_plan(props, (w, h))
+    jobs = frontend.crop_jobs(0, w, h, plan.boxes_int, 1 << 21)
+    ref = pipe.debug_crops_u8([arr], jobs)
+    monkeypatch.setenv('OAKE_RESIZE_NO_TABLES', '1')
+    assert np.array_equal(pipe.debug_crops_u8([arr], jobs), ref)
+    monkeypatch.delenv('OAKE_RESIZE_NO_TABLES')
+    monkeypatch.setenv('OAKE_RESIZE_SLICE', '7')
+    assert np.array_equal(pipe.debug_crops_u8([arr], jobs), ref)
