@@ -323,6 +323,9 @@ __device__ __forceinline__ uint8_t pil_clip8(int ss) {
 #ifndef OAKE_RESIZE_HFIXED
 #define OAKE_RESIZE_HFIXED 1  // 0: the horizontal pass always takes the general tap loop (A/B builds)
 #endif
+// (Measured and rejected on one box, ms per 2350 crops, tools/bench_resize.py: FAST up to 24 taps / 200 rows 2.16 vs
+// 2.09 -- heavy tiles in a plain grid; the BIG kernel on a side stream next to the FAST one, two CTAs per SM, 2.19
+// vs 2.08.)
 constexpr int kFastTaps = 16;
 constexpr int kFastRows = 128;             // 31 * 3.5 + 2 * 7 + 2 source rows under one 32-row tile
 constexpr int kJobTabInts = 12288;         // scratch budget per job (48 KB); a 224 x 224 FAST window needs 8064 ints
