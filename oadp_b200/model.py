@@ -15,6 +15,8 @@ fused `F.normalize(...).half()` result the validators store is available from `e
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from typing import Dict, Optional, Tuple
@@ -137,7 +139,9 @@ class OakeEngine:
     """One liboake_b200 handle bound to (device, current stream) + a growable workspace."""
 
     # chunk sizes chosen so that ceil(rows / 128) lands on a multiple of the 148 SMs (no ragged last wave)
-    MAX_CROPS = {binding.VARIANT_T50: 1894, binding.VARIANT_T197: 478}
+    # ($OAKE_CHUNK_T197 / $OAKE_CHUNK_T50 override them: A/B measurements)
+    MAX_CROPS = {binding.VARIANT_T50: int(os.environ.get('OAKE_CHUNK_T50', 1894)),
+                 binding.VARIANT_T197: int(os.environ.get('OAKE_CHUNK_T197', 478))}
 
     def __init__(self, params: Params, device: torch.device | str = 'cuda', pos_mode: str = 'bilinear') -> None:
         self.lib = binding.load()
