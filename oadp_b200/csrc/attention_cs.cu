@@ -19,8 +19,22 @@
 //                1 / sum, swizzled smem strip, whole 128-byte rows to global memory.
 //   warp  12     loader (TMA boxes + cp.async rows, two-stage ring, non-blocking)
 //   warp  13     MMA issue (one thread), order PV(n,0) S(n+1,0) PV(n,1) S(n+1,1)
+//   warp  15     (objects) the side token's query row, see below
 //
 // so that PV(n,t), its drain and S(n+1,t) run underneath the softmax of the other tile.
+//
+// The objects side token (objects.py:224-247: one more query that sees the patches through the additive mask
+// bias -100 * mask, itself, and not the class token) is row 197 of the item = row 69 of tile 1.  Its biased softmax
+// used to be a special path of the two softmax warps that held it -- 1.5x their instructions for ONE live row, and a
+// tile waits for its slowest warp: 171 us per launch against 135 us without the side row (B = 478,
+// tools/bench_attn_side.py).  Now two SIDE warps (14 and 15: lane quarters 2 and 3, where that row lands on even /
+// odd items) take it off the critical path: as soon as S of tile 1 is complete -- the softmax warps are still busy
+// with tile 0 -- the side warp of the item's parity reads its quarter of S from TMEM, the one lane that holds the row
+// spreads the 208 scores over shared memory, all 32 lanes do bias, maximum, exponentials and sum, and the packed
+// probabilities wait in shared memory.  The eight softmax warps run ONE plain path for all rows; the thread that owns
+// the side row swaps in the prepared probabilities (a few 16-byte loads) before the P store.  (A first attempt
+// computed the row with mma.sync from the K / V tiles in a warp of its own: correct, but the legacy HMMA pipe
+// issues about one m16n8k16 per 66 cycles and sub-partition here -- 291 us per launch.)  Any fp32 mask values are honoured.
 //
 // TMEM columns of a tile (256 per tile, 512 per CTA):
 //   S   [0, 208)  fp32 scores, keys in order (196 patches, class, side, 10 x padding)
@@ -71,8 +85,8 @@ constexpr bool kMaxPipe = OAKE_ATTN_MAXPIPE != 0;
 template <bool SIDE>
 struct CCfg {
   static constexpr int P = 196;
-  static constexpr int T = P + 1;
-  static constexpr int TQ = T + (SIDE ? 1 : 0);
+  static constexpr int T = P + 1;                // keys every row may see: patches + class
+  static constexpr int TQ = T + (SIDE ? 1 : 0);  // rows / keys of an item: + the side token (row 197, seen only by itself)
   static constexpr int NK = 208;                 // keys, padded to the MMA K granule (16)
   static constexpr int kUnits = NK / 16;         // 13
   static constexpr int kSplit = 96;              // first key of the upper half
@@ -86,18 +100,22 @@ struct CCfg {
   static constexpr int kOCol = kSplit + (NK - kSplit) / 2;  // 152
   static constexpr int kSumCol = kOCol + 64;                // 216: row sums (P x ones), 16 columns
   static constexpr int kOnesBytes = 2048;                   // 16 rows x 128 B of fp16 ones: any layout reads ones
+  // side warps' scratch, one set per item parity: 208 fp32 scores, 104 words of packed probabilities, 2 partial sums
+  static constexpr int kSideX = 0, kSideP = 2 * 208 * 4, kSideSum = kSideP + 2 * 104 * 4;
+  static constexpr int kSideBytes = SIDE ? kSideSum + 64 : 0;
   static constexpr int kBufCols = 256;           // TMEM columns per tile
   static constexpr int kMaskFloats = 208;        // staged mask row (196 used), 16-byte granules
   static constexpr int kMaskBytes = 2048;        // both stages' mask rows, padded
   static constexpr int kXchgBytes = 2 * 2 * 2 * 128 * 4;  // partial max + sum: [2][tile][half][row]
   static constexpr int kOutStage = 32 * 128;     // bytes per drain warp: 32 rows x 64 halves
-  static constexpr int kNumBars = 16;
-  static constexpr int kSmemBytes = 1024 + 2 * kStage + kMaskBytes + kXchgBytes + 4 * kOutStage + kOnesBytes + kNumBars * 8 + 16;
+  static constexpr int kNumBars = 18;
+  static constexpr int kSmemBytes = 1024 + 2 * kStage + kMaskBytes + kXchgBytes + 4 * kOutStage + kOnesBytes + kSideBytes + kNumBars * 8 + 16;
   static constexpr int kSoftmaxWarps = 8;
   static constexpr int kDrainWarp0 = 8;
   static constexpr int kLoaderWarp = 12;
   static constexpr int kMmaWarp = 13;
-  static constexpr int kThreads = 32 * 14;
+  static constexpr int kSideWarp0 = 14;          // (objects) warps 14 / 15 = lane quarters 2 / 3 = side row of even / odd items
+  static constexpr int kThreads = SIDE ? 32 * 16 : 32 * 14;
   // Register-resident form (RS): 16 warps = four warpgroups, the unit `setmaxnreg` works on.  At launch every
   // thread owns 128 registers (64 K / 512); the two softmax warpgroups then grow to kRegsSoftmax (a half row of
   // S, 96 / 112 scores, lives in registers from one TMEM read to the exponentials), paid for by the drain
@@ -116,15 +134,6 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
-// How a softmax warp biases its scores.
-//   kPlain: main-stream rows only.  Keys 0..196 (patches, class) valid, no bias.
-//   kBits / kLoad: the warps that hold the side row (warp-uniform code, per-lane select).  The side
-//           row adds -100 log2e mask[key] on patches, -inf on the class key, 0 on its own key
-//           (objects.py:204-247); main-stream rows add 0 / -inf by key validity.  kBits takes the mask
-//           from 7 words of bits (the reference's masks are 0 / 1 by construction, objects.py:147-153);
-//           kLoad reads the fp32 mask row for any other mask values.
-enum BiasMode { kPlain = 0, kBits = 1, kLoad = 2 };
-
 // Named barrier of the two softmax warps of lane quarter q (ids 1..4, 64 threads; id 0 is
 // __syncthreads).  Immediate ids: ptxas then reserves five barriers instead of all sixteen.
 // __noinline__: both halves' instantiations then arrive from the same instruction, which is what
@@ -142,74 +151,42 @@ __device__ __noinline__ void pair_sync(int q) {
 // move them around the callee-saved set); the id is a register operand.
 __device__ __forceinline__ void pair_sync_inline(int q) { asm volatile("bar.sync %0, 64;\n" ::"r"(q + 1) : "memory"); }
 
-// One half (HI = 0: keys 0..95, HI = 1: keys 96..207) of one query row.  The arithmetic of a
-// main-stream row is the same in every mode (bias added after the fma), so a row gets bit-identical
-// results whichever warp pair it lands in: batch composition stays invisible.
-template <bool SIDE, int MODE, int HI>
+// One half (HI = 0: keys 0..95, HI = 1: keys 96..207) of one query row of the tile.  Keys 0..196 (patches, class)
+// are valid for every row; key 197 (the objects side token's own key) and the padding are not.
+template <bool SIDE, int HI>
 struct HalfRow {
   using C = CCfg<SIDE>;
   static constexpr float scale = 0.125f * kLog2e;
-  static constexpr float kNegB = -100.0f * kLog2e;
   static constexpr int k0 = HI ? C::kSplit : 0;   // first key
-  static constexpr int kTail = 192;               // keys 192..207: patches 192..195, class, side, padding
+  static constexpr int kTail = 192;               // keys 192..207: patches 192..195, class, (side), padding
 
   uint32_t t_row;
-  bool is_y;
-  uint32_t ymask_addr, ybits;
 
-  __device__ __forceinline__ float patch_bias(int col, int j, uint32_t w) const {
-    if (MODE == kBits) return (w >> j) & 1u ? kNegB : 0.f;
-    return is_y ? kNegB * lds_f32(ymask_addr + col * 4) : 0.f;
-  }
-  __device__ __forceinline__ uint32_t group_bits(int g) const {  // lane g < 7 holds keys 32g..32g+31
-    if (MODE != kBits) return 0u;
-    const uint32_t w = __shfl_sync(0xffffffffu, ybits, g);
-    return is_y ? w : 0u;
-  }
-  __device__ __forceinline__ float tail_bias(int j, uint32_t w) const {
-    const int col = kTail + j;
-    if (col < C::P) return MODE == kPlain ? 0.f : patch_bias(col, j, w);
-    const float main_b = col < C::T ? 0.f : -INFINITY;  // class key valid, side key / padding not
-    if (MODE == kPlain) return main_b;
-    const float y_b = col == C::T ? 0.f : -INFINITY;     // the side token sees itself, not the class key
-    return is_y ? y_b : main_b;
-  }
-
-  // partial row maximum in the base-2 domain (scaled, biased)
+  // partial row maximum in the base-2 domain (scaled)
   __device__ __forceinline__ float pass_max() const {
-    if (kMaxPipe && MODE == kPlain) return pass_max_pipelined();
+    if (kMaxPipe) return pass_max_pipelined();
     float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       uint32_t ra[32];
       tmem_ld_32x32(t_row + k0 + c * 32, ra);
-      const uint32_t wa = group_bits(k0 / 32 + c);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (MODE == kPlain) {
-          m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(ra[j]));
-        } else {
-          m4[j & 3] = fmaxf(m4[j & 3], fmaf(__uint_as_float(ra[j]), scale, patch_bias(k0 + c * 32 + j, j, wa)));
-        }
-      }
+      for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(ra[j]));
     }
     float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-    if (MODE == kPlain) mx *= scale;  // the scale is positive: max(s) * scale == max(s * scale)
     if (HI) {
       uint32_t rt[16];
       tmem_ld_32x16(t_row + kTail, rt);
-      const uint32_t wt = group_bits(6);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (kTail + j <= C::T) mx = fmaxf(mx, fmaf(__uint_as_float(rt[j]), scale, tail_bias(j, wt)));
+        if (kTail + j < C::T) mx = fmaxf(mx, __uint_as_float(rt[j]));
     }
-    return mx;
+    return mx * scale;  // the scale is positive: max(s) * scale == max(s * scale)
   }
 
-  // kPlain rows: raw maxima (the scale is positive), chunks 0 and 1 requested together, chunk 2 (and the tail)
-  // requested while chunk 1 is reduced
+  // chunks 0 and 1 requested together, chunk 2 (and the tail) requested while chunk 1 is reduced (-DOAKE_ATTN_MAXPIPE=1)
   __device__ __forceinline__ float pass_max_pipelined() const {
     float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     auto reduce = [&](const uint32_t (&a)[32]) {
@@ -235,38 +212,40 @@ struct HalfRow {
     return mx * scale;
   }
 
-  // p = exp2(s - max) -> packed fp16 behind the reads; partial row sum of the unrounded values
-  __device__ __forceinline__ float pass_exp(float neg_mx) const {
+  // p = exp2(s - max) -> packed fp16 behind the reads; partial row sum of the unrounded values.
+  // `y_words` != 0 (the one thread that owns the objects side row): the row's packed probabilities, prepared by a
+  // side warp (shared-window address of word 0 = keys 0, 1), replace what the plain path computed for it.
+  __device__ __forceinline__ float pass_exp(float neg_mx, uint32_t y_words) const {
     constexpr int pbase = HI ? C::kPHi : 0;
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       uint32_t ra[32];
       tmem_ld_32x32(t_row + k0 + c * 32, ra);
-      const uint32_t wa = group_bits(k0 / 32 + c);
       tmem_ld_wait();
       uint32_t pa[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float p[2];
+        const float p0 = ex2_sel(fmaf(__uint_as_float(ra[2 * j]), scale, neg_mx), use_poly(j));
+        const float p1 = ex2_sel(fmaf(__uint_as_float(ra[2 * j + 1]), scale, neg_mx), use_poly(j));
+        if (!kSumMma) s4[j & 3] += p0 + p1;
+        pa[j] = pack2(p0, p1);
+      }
+      if (SIDE && y_words != 0u) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int jj = 2 * j + e;
-          if (MODE == kPlain) {
-            p[e] = ex2_sel(fmaf(__uint_as_float(ra[jj]), scale, neg_mx), use_poly(j));
-          } else {  // bias added after the fma: same bits as kPlain for a main-stream row (bias 0)
-            p[e] = ex2_sel(fmaf(__uint_as_float(ra[jj]), scale, neg_mx) + patch_bias(k0 + c * 32 + jj, jj, wa), use_poly(j));
-          }
+        for (int j = 0; j < 4; ++j) {
+          const uint4 w = lds128(y_words + (k0 / 2 + c * 16 + 4 * j) * 4);
+          pa[4 * j + 0] = w.x;
+          pa[4 * j + 1] = w.y;
+          pa[4 * j + 2] = w.z;
+          pa[4 * j + 3] = w.w;
         }
-        if (!kSumMma) s4[j & 3] += p[0] + p[1];
-        pa[j] = pack2(p[0], p[1]);
       }
       tmem_st_32x16(t_row + pbase + c * 16, pa);
     }
     if (HI) {
       uint32_t rt[16];
       tmem_ld_32x16(t_row + kTail, rt);
-      const uint32_t wt = group_bits(6);
       tmem_ld_wait();
       uint32_t pt[8];
 #pragma unroll
@@ -275,10 +254,20 @@ struct HalfRow {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int jj = 2 * j + e;
-          p[e] = kTail + jj <= C::T ? ex2(fmaf(__uint_as_float(rt[jj]), scale, neg_mx) + tail_bias(jj, wt)) : 0.f;
+          p[e] = kTail + jj < C::T ? ex2(fmaf(__uint_as_float(rt[jj]), scale, neg_mx)) : 0.f;
         }
         if (!kSumMma) s4[j & 3] += p[0] + p[1];
         pt[j] = pack2(p[0], p[1]);
+      }
+      if (SIDE && y_words != 0u) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 w = lds128(y_words + (kTail / 2 + 4 * j) * 4);
+          pt[4 * j + 0] = w.x;
+          pt[4 * j + 1] = w.y;
+          pt[4 * j + 2] = w.z;
+          pt[4 * j + 3] = w.w;
+        }
       }
       tmem_st_32x8(t_row + pbase + 48, pt);
     }
@@ -287,16 +276,20 @@ struct HalfRow {
 };
 
 // pass_max -> exchange with the other half's warp -> pass_exp; leaves the partial sum in `xsum`.
-template <bool SIDE, int MODE, int HI>
-__device__ __forceinline__ void softmax_half(uint32_t t_row, bool is_y, uint32_t ymask_addr, uint32_t ybits, int q,
-                                             float* xmax_mine, const float* xmax_other, float* xsum_mine) {
-  HalfRow<SIDE, MODE, HI> h{t_row, is_y, ymask_addr, ybits};
+// warp_y: this warp's rows include the objects side row (is_y: this thread's row is it) -- its probabilities and its
+// sum come from the side warp (`y_ready`, `y_words`, `y_sum`), everything else is the one plain path.
+template <bool SIDE, int HI>
+__device__ __forceinline__ void softmax_half(uint32_t t_row, int q, float* xmax_mine, const float* xmax_other,
+                                             float* xsum_mine, bool warp_y, bool is_y, uint64_t* y_ready,
+                                             uint32_t y_parity, uint32_t y_words, const float* y_sum) {
+  HalfRow<SIDE, HI> h{t_row};
   const float mine = h.pass_max();
   *xmax_mine = mine;
   pair_sync(q);
   const float mx = fmaxf(mine, *xmax_other);
-  const float sum = h.pass_exp(-mx);
-  if (!kSumMma) *xsum_mine = sum;
+  if (SIDE && warp_y) mbar_wait(y_ready, y_parity);  // (long complete: the side warp ran under the softmax of tile 0)
+  const float sum = h.pass_exp(-mx, (SIDE && is_y) ? y_words : 0u);
+  if (!kSumMma) *xsum_mine = (SIDE && is_y) ? y_sum[HI] : sum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,7 +461,8 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
   float* xsum = xmax + 2 * 2 * 128;                                               // [tile][half][128]
   uint8_t* out_stage = smem + 2 * C::kStage + C::kMaskBytes + C::kXchgBytes;      // [4 drain warps][kOutStage]
   uint8_t* ones = out_stage + 4 * C::kOutStage;  // [kOnesBytes] fp16 1.0
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + C::kOnesBytes);
+  uint8_t* side = ones + C::kOnesBytes;  // (objects) side warps' scratch: [parity] scores, packed probabilities, sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + C::kOnesBytes + C::kSideBytes);
   uint64_t* qk_full = bars + 0;   // [stage]  loader -> MMA
   uint64_t* qk_free = bars + 2;   // [stage]  MMA (S of both tiles retired) -> loader
   uint64_t* v_full = bars + 4;    // [stage]  loader -> MMA, side-row warps (mask row)
@@ -477,6 +471,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
   uint64_t* p_ready = bars + 10;  // [tile]   8 softmax warps -> MMA, drain warps (row sums)
   uint64_t* o_full = bars + 12;   // [tile]   MMA -> drain warps
   uint64_t* o_free = bars + 14;   // [tile]   4 drain warps (O in registers) -> MMA
+  uint64_t* y_ready = bars + 16;  // [parity] side warp (the side row's probabilities are in shared memory) -> its softmax warps
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + C::kNumBars);
 
   const int warp = threadIdx.x >> 5;
@@ -495,6 +490,7 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
       mbar_init(&qk_free[i], 1);
       mbar_init(&v_full[i], 33);
       mbar_init(&v_free[i], 1);
+      mbar_init(&y_ready[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], C::kSoftmaxWarps);
       mbar_init(&o_full[i], 1);
@@ -641,7 +637,87 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
         }
       }
     }
-   }  // (RS: warps 14 and 15 only complete the fourth warpgroup)
+   } else if (SIDE && !RS && warp >= C::kSideWarp0) {
+    // ================================================================== the objects side row's softmax
+    // Row 197 = row 69 of tile 1: TMEM lane 69 on even items (quarter 2: warp 14), lane 56 + 69 = 125 on odd items
+    // (quarter 3: warp 15).  Every side warp follows s_full[1] item by item (it can never fall two phases behind: the
+    // next S of tile 1 needs this item's P, which needs its side row) and works on the items of its parity.
+    constexpr float scale = 0.125f * kLog2e;
+    constexpr float kNegB = -100.0f * kLog2e;
+    const int par = warp - C::kSideWarp0;            // item parity served = scratch set
+    const int q = warp & 3;                           // == 2 + par
+    const int ylane = (par ? C::kShift : 0) + C::kRows1 - 1 - q * 32;  // 5 / 29
+    float* sx = reinterpret_cast<float*>(side + C::kSideX) + par * C::NK;
+    uint32_t* sp = reinterpret_cast<uint32_t*>(side + C::kSideP) + par * (C::NK / 2);
+    float* ssum = reinterpret_cast<float*>(side + C::kSideSum) + par * 2;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 1 * C::kBufCols;
+    for (int n = 0; n < N; ++n) {
+      const int s = n & 1, u = n >> 1;
+      mbar_wait(&s_full[1], n & 1);
+      if (s != par) continue;
+      tc_fence_after();
+      // the row's 208 scores: TMEM -> the registers of lane `ylane` -> shared memory
+#pragma unroll 1
+      for (int c = 0; c < C::NK / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (lane == ylane) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(sx + c * 32 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+      }
+      {
+        uint32_t r[16];
+        tmem_ld_32x16(t_row + 192, r);
+        tmem_ld_wait();
+        if (lane == ylane) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(sx + 192 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_wait(&v_full[s], u & 1);  // the crop's mask row lands with the V stage
+      __syncwarp();
+      // bias (-100 mask on the patches, the class key and the padding out, its own key 197 in), maximum, exponentials
+      const float* ym = ymask + s * C::kMaskFloats;
+      float x[7];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const int j = lane + 32 * i;
+        float v = -INFINITY;
+        if (j < P) v = fmaf(sx[j], scale, kNegB * ym[j]);
+        else if (j == C::T) v = sx[j] * scale;
+        x[i] = v;
+        mx = fmaxf(mx, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        x[i] = ex2(x[i] - mx);
+        sum += x[i];
+      }
+      sum = warp_sum(sum);
+      // packed pairs (keys 2 w, 2 w + 1): even lanes pack their value with their right neighbour's
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const float nb = __shfl_down_sync(0xffffffffu, x[i], 1);
+        const int j = lane + 32 * i;
+        if ((lane & 1) == 0 && j < C::NK) sp[j >> 1] = pack2(x[i], nb);
+      }
+      if (lane == 0) {
+        ssum[0] = sum;
+        ssum[1] = 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&y_ready[par]);  // (release: the scratch is visible to the softmax warps that wait)
+    }
+   }  // (warp 14, and 15 without a side token, only complete the fourth warpgroup)
   } else if (RS && warp < C::kDrainWarp0) {
     // ================================================================== softmax warps, register-resident form
     setmaxnreg_inc<C::kRegsSoftmax>();
@@ -751,31 +827,12 @@ attention_cs_kernel(const __grid_constant__ CUtensorMap tmQ0,  // qkv [R, 3W], b
 
         if (!drain) {
           if (warp_live) {
-            uint32_t ymask_addr = 0u, ybits = 0u;
-            int mode = kPlain;
-            if (warp_y) {
-              mbar_wait(&v_full[s], u & 1);  // the crop's mask row lands with the V stage
-              ymask_addr = smem_u32(ymask + s * C::kMaskFloats);
-              uint32_t other = 0u;  // lane g keeps the bits of keys 32g .. 32g+31
-#pragma unroll
-              for (int g = 0; g < 7; ++g) {
-                const int col = g * 32 + lane;
-                const float m = col < P ? lds_f32(ymask_addr + col * 4) : 0.f;
-                const uint32_t w = __ballot_sync(0xffffffffu, m != 0.f);
-                other |= __ballot_sync(0xffffffffu, m != 0.f && m != 1.f);
-                if (lane == g) ybits = w;
-              }
-              mode = other == 0u ? kBits : kLoad;
-            }
-            if (hi == 0) {
-              if (mode == kPlain) softmax_half<SIDE, kPlain, 0>(t_row, false, 0u, 0u, q, xm, xm + 128, xs);
-              else if (mode == kBits) softmax_half<SIDE, kBits, 0>(t_row, is_y, ymask_addr, ybits, q, xm, xm + 128, xs);
-              else softmax_half<SIDE, kLoad, 0>(t_row, is_y, ymask_addr, 0u, q, xm, xm + 128, xs);
-            } else {
-              if (mode == kPlain) softmax_half<SIDE, kPlain, 1>(t_row, false, 0u, 0u, q, xm + 128, xm, xs + 128);
-              else if (mode == kBits) softmax_half<SIDE, kBits, 1>(t_row, is_y, ymask_addr, ybits, q, xm + 128, xm, xs + 128);
-              else softmax_half<SIDE, kLoad, 1>(t_row, is_y, ymask_addr, 0u, q, xm + 128, xm, xs + 128);
-            }
+            // (objects) the side row's probabilities wait in the scratch set of the item's parity
+            uint64_t* yr = &y_ready[s];
+            const uint32_t yw = smem_u32(side + C::kSideP) + s * (C::NK / 2) * 4;
+            const float* ys = reinterpret_cast<const float*>(side + C::kSideSum) + s * 2;
+            if (hi == 0) softmax_half<SIDE, 0>(t_row, q, xm, xm + 128, xs, warp_y, is_y, yr, u & 1, yw, ys);
+            else softmax_half<SIDE, 1>(t_row, q, xm + 128, xm, xs + 128, warp_y, is_y, yr, u & 1, yw, ys);
             tmem_st_wait();
           }
           tc_fence_before();
@@ -907,8 +964,7 @@ cudaError_t launch_attention_cs(cudaStream_t st, const act_t* qkv, const float* 
   const int rows = B * (P + 1) + (with_side ? B : 0);
   if (with_side) {
     if (mask == nullptr) return cudaErrorInvalidValue;
-    return attention_rs() ? launch_cs<true, true>(st, qkv, mask, out, B, heads, rows)
-                          : launch_cs<true, false>(st, qkv, mask, out, B, heads, rows);
+    return launch_cs<true, false>(st, qkv, mask, out, B, heads, rows);  // (the opt-in RS form has no side warp)
   }
   return attention_rs() ? launch_cs<false, true>(st, qkv, nullptr, out, B, heads, rows)
                         : launch_cs<false, false>(st, qkv, nullptr, out, B, heads, rows);
