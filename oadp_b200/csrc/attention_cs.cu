@@ -79,6 +79,13 @@ __device__ long long g_attn_trace[8 * 32 * 4];
 #ifndef OAKE_ATTN_MAXPIPE
 #define OAKE_ATTN_MAXPIPE 0
 #endif
+// -DOAKE_ATTN_TAILMERGE=0: the upper half loads its 16-column tail (keys 192..207) in a fourth round of its own.
+// Default: the tail is requested together with the third 32-column chunk, so both halves of a lane quarter wait for
+// three TMEM loads per pass -- a tile waits for its slowest warp, and the upper half was it.
+#ifndef OAKE_ATTN_TAILMERGE
+#define OAKE_ATTN_TAILMERGE 1
+#endif
+constexpr bool kTailMerge = OAKE_ATTN_TAILMERGE != 0;
 constexpr bool kSumMma = OAKE_ATTN_SUMMMA != 0;
 constexpr bool kMaxPipe = OAKE_ATTN_MAXPIPE != 0;
 
@@ -166,19 +173,30 @@ struct HalfRow {
   __device__ __forceinline__ float pass_max() const {
     if (kMaxPipe) return pass_max_pipelined();
     float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    uint32_t rt[16];
+    constexpr bool merge = HI && kTailMerge;
 #pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < (merge ? 2 : 3); ++c) {
       uint32_t ra[32];
       tmem_ld_32x32(t_row + k0 + c * 32, ra);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(ra[j]));
     }
-    float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-    if (HI) {
-      uint32_t rt[16];
+    if (merge) {  // third chunk and tail in one round
+      uint32_t ra[32];
+      tmem_ld_32x32(t_row + k0 + 64, ra);
       tmem_ld_32x16(t_row + kTail, rt);
       tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(ra[j]));
+    }
+    float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    if (HI) {
+      if (!merge) {
+        tmem_ld_32x16(t_row + kTail, rt);
+        tmem_ld_wait();
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (kTail + j < C::T) mx = fmaxf(mx, __uint_as_float(rt[j]));
@@ -217,12 +235,9 @@ struct HalfRow {
   // side warp (shared-window address of word 0 = keys 0, 1), replace what the plain path computed for it.
   __device__ __forceinline__ float pass_exp(float neg_mx, uint32_t y_words) const {
     constexpr int pbase = HI ? C::kPHi : 0;
+    constexpr bool merge = HI && kTailMerge;
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-      uint32_t ra[32];
-      tmem_ld_32x32(t_row + k0 + c * 32, ra);
-      tmem_ld_wait();
+    auto do_chunk = [&](int c, const uint32_t (&ra)[32]) {
       uint32_t pa[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -242,11 +257,27 @@ struct HalfRow {
         }
       }
       tmem_st_32x16(t_row + pbase + c * 16, pa);
+    };
+#pragma unroll 1
+    for (int c = 0; c < (merge ? 2 : 3); ++c) {
+      uint32_t ra[32];
+      tmem_ld_32x32(t_row + k0 + c * 32, ra);
+      tmem_ld_wait();
+      do_chunk(c, ra);
     }
-    if (HI) {
-      uint32_t rt[16];
+    uint32_t rt[16];
+    if (merge) {  // third chunk and tail in one round
+      uint32_t ra[32];
+      tmem_ld_32x32(t_row + k0 + 64, ra);
       tmem_ld_32x16(t_row + kTail, rt);
       tmem_ld_wait();
+      do_chunk(2, ra);
+    }
+    if (HI) {
+      if (!merge) {
+        tmem_ld_32x16(t_row + kTail, rt);
+        tmem_ld_wait();
+      }
       uint32_t pt[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
