@@ -86,6 +86,12 @@ __device__ long long g_attn_trace[8 * 32 * 4];
 #define OAKE_ATTN_TAILMERGE 1
 #endif
 constexpr bool kTailMerge = OAKE_ATTN_TAILMERGE != 0;
+// -DOAKE_ATTN_EXPPIPE=1: the exponential pass in 16-column pieces, the next piece's TMEM load in flight during the
+// arithmetic of the current one (two 16-register buffers).  Same arithmetic per key.
+#ifndef OAKE_ATTN_EXPPIPE
+#define OAKE_ATTN_EXPPIPE 0
+#endif
+constexpr bool kExpPipe = OAKE_ATTN_EXPPIPE != 0;
 constexpr bool kSumMma = OAKE_ATTN_SUMMMA != 0;
 constexpr bool kMaxPipe = OAKE_ATTN_MAXPIPE != 0;
 
@@ -233,7 +239,75 @@ struct HalfRow {
   // p = exp2(s - max) -> packed fp16 behind the reads; partial row sum of the unrounded values.
   // `y_words` != 0 (the one thread that owns the objects side row): the row's packed probabilities, prepared by a
   // side warp (shared-window address of word 0 = keys 0, 1), replace what the plain path computed for it.
+  // 16-column pieces, double buffered (kExpPipe)
+  __device__ __forceinline__ float pass_exp_pipelined(float neg_mx, uint32_t y_words) const {
+    constexpr int pbase = HI ? C::kPHi : 0;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    // `po`: pair offset of the piece inside its 32-key chunk (0 / 8): the FMA-pipe exponentials are chosen by key
+    auto piece = [&](const uint32_t (&r)[16], int po, int col8) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool poly = po == 0 ? use_poly(j) : use_poly(8 + j);
+        const float p0 = ex2_sel(fmaf(__uint_as_float(r[2 * j]), scale, neg_mx), poly);
+        const float p1 = ex2_sel(fmaf(__uint_as_float(r[2 * j + 1]), scale, neg_mx), poly);
+        if (!kSumMma) s4[j & 3] += p0 + p1;
+        pk[j] = pack2(p0, p1);
+      }
+      if (SIDE && y_words != 0u) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 w = lds128(y_words + (k0 / 2 + col8 + 4 * j) * 4);
+          pk[4 * j + 0] = w.x;
+          pk[4 * j + 1] = w.y;
+          pk[4 * j + 2] = w.z;
+          pk[4 * j + 3] = w.w;
+        }
+      }
+      tmem_st_32x8(t_row + pbase + col8, pk);
+    };
+    uint32_t a[16], b[16];
+    tmem_ld_32x16(t_row + k0, a);
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      tmem_ld_wait();
+      tmem_ld_32x16(t_row + k0 + c * 32 + 16, b);
+      piece(a, 0, c * 16);
+      tmem_ld_wait();
+      if (HI || c < 2) tmem_ld_32x16(t_row + k0 + (c + 1) * 32, a);  // next chunk, or the upper half's tail (k0 + 96 = 192)
+      piece(b, 8, c * 16 + 8);
+    }
+    if (HI) {
+      tmem_ld_wait();
+      uint32_t pt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jj = 2 * j + e;
+          p[e] = kTail + jj < C::T ? ex2(fmaf(__uint_as_float(a[jj]), scale, neg_mx)) : 0.f;
+        }
+        if (!kSumMma) s4[j & 3] += p[0] + p[1];
+        pt[j] = pack2(p[0], p[1]);
+      }
+      if (SIDE && y_words != 0u) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 w = lds128(y_words + (kTail / 2 + 4 * j) * 4);
+          pt[4 * j + 0] = w.x;
+          pt[4 * j + 1] = w.y;
+          pt[4 * j + 2] = w.z;
+          pt[4 * j + 3] = w.w;
+        }
+      }
+      tmem_st_32x8(t_row + pbase + 48, pt);
+    }
+    return (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  }
+
   __device__ __forceinline__ float pass_exp(float neg_mx, uint32_t y_words) const {
+    if (kExpPipe) return pass_exp_pipelined(neg_mx, y_words);
     constexpr int pbase = HI ? C::kPHi : 0;
     constexpr bool merge = HI && kTailMerge;
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
