@@ -152,6 +152,13 @@ def test_fused_front_end_is_the_unfused_one(pipe, monkeypatch):
     assert got[True][0].shape[0] > 400
     assert torch.equal(got[True][0], got[False][0])
     assert torch.equal(got[True][1], got[False][1])
+    # the fused path in passes of a few jobs (crop index = pass offset + job index) and without coefficient tables
+    monkeypatch.setattr(pl, '_FUSED_FRONTEND', True)
+    for knob in ('OAKE_RESIZE_SLICE', 'OAKE_RESIZE_NO_TABLES'):
+        monkeypatch.setenv(knob, '5' if knob.endswith('SLICE') else '1')
+        objs = pipe.encode_objects(imgs, props)
+        assert torch.equal(torch.cat([o['embeddings'] for o in objs]), got[True][0])
+        monkeypatch.delenv(knob)
 
 
 def test_resize_paths_agree(pipe, monkeypatch):
