@@ -20,10 +20,10 @@ __device__ __forceinline__ float ex2(float x) {
 // 2^x for x <= 0 on the FMA pipe: round x to the nearest integer n with the 1.5 * 2^23 trick, a degree-3 minimax
 // polynomial for 2^f on f = x - n in [-0.5, 0.5] (max relative error 7.5e-5, a third of the half-ulp of the fp16 the
 // result is rounded to), and n added into the exponent field.  The MUFU pipe delivers 16 ex2 per clock and SM and
-// is what bounds the softmax (tools/probes/tmem_probe.cu); every kPolyEvery-th PAIR of keys takes this path
+// is what bounds the softmax (tools/probes/tmem_probe.cu); every kPolyEvery-th PAIR of keys (of a 32-key chunk) takes this path
 // instead, chosen by key index only, so a row's arithmetic does not depend on where the row sits.
 #ifndef OAKE_ATTN_POLY
-#define OAKE_ATTN_POLY 3
+#define OAKE_ATTN_POLY 4  // (every third pair measured best before the side warps, every fourth after: 139.7 vs 141.4 us)
 #endif
 constexpr int kPolyEvery = OAKE_ATTN_POLY;  // 0: every exponential on the MUFU pipe
 __device__ __forceinline__ float ex2_poly(float x) {
