@@ -415,7 +415,7 @@ class OakePipeline:
             if count and not fused:
                 timed('resize_u8', lambda: binding.check(self.lib.oake_resize_u8(
                     arena_ptr, arena_ptr, meta_ptr + o, count, tiles, self._err.data_ptr(), st)))
-                self.frontend_launches += 1
+                self.frontend_launches += 3  # prepare, FAST tiles, BIG tiles
         masks_ptr = None
         if variant == binding.VARIANT_T197 and n:
             masks_ptr = meta_ptr + job['masks_off']
@@ -432,8 +432,7 @@ class OakePipeline:
                     jobs_ptr = meta_ptr + job['stages'][0][2] + s * frontend.RESIZE_JOB.itemsize
                     timed('resize_u8', lambda: binding.check(self.lib.oake_resize_to_patches(
                         self.engine._handle, arena_ptr, jobs_ptr, b, variant, ws.data_ptr(), ws.numel(),
-                        self._err.data_ptr(), st)))
-                    self.frontend_launches += 3
+                        self._err.data_ptr(), st)))  # (its three kernels are counted by the handle)
                     binding.check(self.lib.oake_encode_patches(
                         self.engine._handle, b, variant, (masks_ptr + s * 196 * 4) if masks_ptr else None,
                         out[s:].data_ptr(), None, ws.data_ptr(), ws.numel(), st))
