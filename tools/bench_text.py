@@ -1,7 +1,9 @@
 """Micro-benchmark of the text tower (second half): the prompt-builder workload of
 oadp/prompts/vild.py:56-72 -- 74 templates x 1 217 category names, one (1217, L) token batch per template --
 on the GPU against the fp32 oracle on the host cores (bounded sample).  Prints JSON lines.
-Synthetic token ids (the BPE vocabulary is not available offline), seeded random weights."""
+Synthetic token ids (the BPE vocabulary is not available offline), seeded random weights.
+(Developer measurement, not product code: like bench.py's cpu_baseline leg it uses the oracle as the timed CPU baseline
+and as the checker of the sample; nothing under oadp_b200/ imports it -- tests/test_abi.py.)"""
 import json
 import os
 import pathlib
