@@ -182,6 +182,17 @@ def level_job(src_off: int, src_w: int, src_h: int, dst_off: int, dst_w: int, ds
     return job
 
 
+def fused_stage(stages, crops: np.ndarray) -> bool:
+    """True when the crops are exactly the outputs of ONE resize stage, each a whole 224 x 224 window (the globals and
+    objects tasks): such crops never exist as uint8 -- `oake_resize_to_patches` writes the tower's front-end matrix.
+    The blocks task (pyramid stages, crops = windows into the levels) is not."""
+    if len(stages) != 1 or crops.shape[0] == 0 or stages[0].size != crops.shape[0]:
+        return False
+    jobs = stages[0]
+    return bool((jobs['win_w'] == SIZE).all() and (jobs['win_h'] == SIZE).all()
+                and np.array_equal(jobs['dst_off'], crops['off']) and (crops['pitch_px'] == SIZE).all())
+
+
 def max_tiles(jobs: np.ndarray) -> int:
     if jobs.size == 0:
         return 0

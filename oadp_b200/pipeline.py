@@ -308,9 +308,7 @@ class OakePipeline:
         self._slot.jpeg_count = len(compressed)
         # crops that are exactly the outputs of one resize stage (globals, objects) never exist as uint8: the resize
         # kernel writes the tower's front-end matrix itself, chunk by chunk (oake_resize_to_patches)
-        fused = (_FUSED_FRONTEND and len(stages) == 1 and n > 0 and stages[0].size == n
-                 and bool((stages[0]['win_w'] == frontend.SIZE).all() and (stages[0]['win_h'] == frontend.SIZE).all())
-                 and np.array_equal(stages[0]['dst_off'], crops['off']))
+        fused = _FUSED_FRONTEND and frontend.fused_stage(stages, crops)
         return dict(n=n, variant=variant, img_bytes=img_bytes, meta_host_bytes=meta_host_bytes, jpeg=jpeg_job, fused=fused,
                     raw_images=len(images) - len(compressed), raw_ranges=raw_ranges if compressed else None,
                     stages=[(j.size, frontend.max_tiles(j), o) for j, o in zip(stages, stage_offs)],

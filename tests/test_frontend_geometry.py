@@ -97,3 +97,25 @@ def test_job_records_layout():
         frontend.crop_jobs(0, 640, 480, np.array([[0, 0, 3000, 3000]]), 0)
     lvl = frontend.level_job(0, 640, 480, 999, 426, 320)
     assert frontend.max_tiles(lvl) == 14 * 10
+
+
+def test_fused_stage_predicate():
+    """Which plans may skip the uint8 crops (oake_resize_to_patches): one stage whose jobs are the crops, whole windows."""
+    from oadp_b200 import frontend as fe
+    boxes = np.array([[0, 0, 640, 480], [10, 20, 200, 300]], dtype=np.int64)
+    jobs = fe.crop_jobs(0, 640, 480, boxes, 1 << 20)
+    crops = np.zeros(2, dtype=fe.CROP_SRC)
+    crops['off'] = jobs['dst_off']
+    crops['pitch_px'] = fe.SIZE
+    assert fe.fused_stage([jobs], crops)
+    assert not fe.fused_stage([jobs, jobs], crops)  # pyramid stages (blocks)
+    assert not fe.fused_stage([jobs[:1]], crops)  # crops that are not resize outputs (windows into a level)
+    moved = crops.copy()
+    moved['off'][1] += 3
+    assert not fe.fused_stage([jobs], moved)
+    level = fe.level_job(0, 640, 480, 1 << 20, 426, 320)
+    one = np.zeros(1, dtype=fe.CROP_SRC)
+    one['off'] = level['dst_off']
+    one['pitch_px'] = 426
+    assert not fe.fused_stage([level], one)  # a whole-image level is not a 224 x 224 window
+    assert not fe.fused_stage([jobs[:0]], crops[:0])
